@@ -1,0 +1,227 @@
+"""ctypes binding of libconesgpu.so (include/conesgpu.h).
+
+``ConesGpu`` is a thin owner of one ``cp_handle``.  Nothing here computes on the CPU: if the
+library is missing or no B200 is present the constructor raises — there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .params import CDetectParams, CGroundParams, DetectParams, GroundParams, to_c_detect, to_c_ground
+from .pointcloud2 import CCloudView, PointCloud2, make_view
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libconesgpu.so")
+
+CP_OK, CP_E_PARAM, CP_E_BADFIELD, CP_E_CAPACITY, CP_E_CUDA, CP_E_NOMEM, CP_E_STATE = range(7)
+
+TAP_SECTOR_LOW, TAP_CROP_INDEX, TAP_CROP_POINTS, TAP_CROP_OFFSETS, TAP_VOXEL_KEYS, TAP_VOXEL_ORDER, \
+    TAP_VOXEL_CLOUD, TAP_VOXEL_OFFSETS, TAP_LABELS = range(9)
+
+# every symbol include/conesgpu.h declares
+ABI_SYMBOLS = [
+    "cp_strerror", "cp_last_error", "cp_abi_version", "cp_create_error", "cp_create", "cp_destroy",
+    "cp_ground_remove", "cp_detect", "cp_batch_set_device_input", "cp_batch_set_host_input", "cp_batch_run",
+    "cp_sync", "cp_batch_results", "cp_detect_batch", "cp_last_run_ms", "cp_last_launch_count", "cp_stream",
+    "cp_debug_tap", "cp_debug_sort",
+]
+
+CLUSTER_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.uint32), ("min_index", np.uint32)])
+COUNTER_DTYPE = np.dtype([(n, np.uint32) for n in (
+    "n_points", "n_ground_kept", "n_cropped", "n_voxels", "n_components", "n_clusters", "key_bits", "passthrough")])
+
+
+class CConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_points", C.c_uint64), ("max_frames", C.c_uint32),
+                ("max_point_step", C.c_uint32), ("max_survivors", C.c_uint64), ("max_voxels", C.c_uint64)]
+
+
+class ConesGpuError(RuntimeError):
+    def __init__(self, status: int, detail: str):
+        super().__init__(f"libconesgpu status {status}: {detail}")
+        self.status = status
+        self.detail = detail
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load libconesgpu.so and declare the prototypes.  Fails loudly when it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            f"{p} is missing: build it with `python -m cones_perception_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(p)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    lib.cp_strerror.restype = C.c_char_p
+    lib.cp_strerror.argtypes = [C.c_int]
+    lib.cp_last_error.restype = C.c_char_p
+    lib.cp_last_error.argtypes = [vp]
+    lib.cp_create_error.restype = C.c_char_p
+    lib.cp_abi_version.restype = u32
+    lib.cp_create.argtypes = [C.POINTER(vp), C.POINTER(CConfig)]
+    lib.cp_destroy.argtypes = [vp]
+    lib.cp_destroy.restype = None
+    lib.cp_ground_remove.argtypes = [vp, C.POINTER(CCloudView), C.POINTER(CGroundParams), vp, C.POINTER(u32), vp]
+    lib.cp_detect.argtypes = [vp, C.POINTER(CCloudView), C.POINTER(CDetectParams), C.POINTER(CGroundParams), vp, u32,
+                              C.POINTER(u32), vp]
+    lib.cp_batch_set_device_input.argtypes = [vp, vp, u32, vp, u32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.cp_batch_set_host_input.argtypes = [vp, C.POINTER(CCloudView), u32]
+    lib.cp_batch_run.argtypes = [vp, C.POINTER(CDetectParams), C.POINTER(CGroundParams)]
+    lib.cp_sync.argtypes = [vp]
+    lib.cp_batch_results.argtypes = [vp, vp, vp, vp, u64, C.POINTER(u64)]
+    lib.cp_detect_batch.argtypes = [vp, C.POINTER(CCloudView), u32, C.POINTER(CDetectParams),
+                                    C.POINTER(CGroundParams), vp, vp, vp, u64, C.POINTER(u64)]
+    lib.cp_last_run_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.cp_last_launch_count.argtypes = [vp]
+    lib.cp_last_launch_count.restype = u32
+    lib.cp_stream.argtypes = [vp]
+    lib.cp_stream.restype = vp
+    lib.cp_debug_tap.argtypes = [vp, C.c_int, vp, u64, C.POINTER(u64)]
+    lib.cp_debug_sort.argtypes = [vp, vp, vp, u32, u32]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class ConesGpu:
+    """Owner of one cp_handle (one CUDA device, one stream, used by one thread at a time)."""
+
+    def __init__(self, max_points: int, max_frames: int = 1, device: int = 0, max_point_step: int = 16,
+                 max_survivors: int = 0, max_voxels: int = 0, taps: bool = False):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        if taps:
+            os.environ["CONESGPU_TAPS"] = "1"
+        try:
+            cfg = CConfig(device, max_points, max_frames, max_point_step, max_survivors, max_voxels)
+            st = self.lib.cp_create(C.byref(self._h), C.byref(cfg))
+        finally:
+            if taps:
+                os.environ.pop("CONESGPU_TAPS", None)
+        if st != CP_OK:
+            raise ConesGpuError(st, self.lib.cp_create_error().decode())
+        self.max_points, self.max_frames = max_points, max_frames
+        self._keep = None  # keeps batch inputs alive while the device reads them
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.cp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st: int):
+        if st != CP_OK:
+            raise ConesGpuError(st, self.lib.cp_last_error(self._h).decode())
+
+    # ---- node-equivalent calls --------------------------------------------------------
+    def ground_remove(self, msg: PointCloud2, g: GroundParams):
+        """GroundRemover::cloud_handler body (src/ground_removal.cpp:54-79).
+        Returns (cloud32 [N,8] float32 in PCL layout, n_kept, low17)."""
+        view = make_view(msg, fake_missing_intensity=False)
+        n = msg.n_points
+        out = np.empty((n, 8), dtype=np.float32)
+        low = np.empty(17, dtype=np.float32)
+        kept = C.c_uint32()
+        cg = to_c_ground(g)
+        self._ck(self.lib.cp_ground_remove(self._h, C.byref(view), C.byref(cg), out.ctypes.data, C.byref(kept),
+                                           low.ctypes.data))
+        return out, kept.value, low
+
+    def detect(self, msg: PointCloud2, d: DetectParams, g: GroundParams | None = None, cap: int = 4096,
+               fake_missing_intensity: bool = True):
+        """ConeDetector::cloud_handler hot path (src/cone_detection.cpp:151-167 + :261-273).
+        Returns (clusters structured array, counters structured scalar)."""
+        view = make_view(msg, fake_missing_intensity)
+        out = np.zeros(cap, dtype=CLUSTER_DTYPE)
+        ctr = np.zeros(1, dtype=COUNTER_DTYPE)
+        k = C.c_uint32()
+        cd = to_c_detect(d)
+        cg = to_c_ground(g) if g is not None else None
+        self._ck(self.lib.cp_detect(self._h, C.byref(view), C.byref(cd), C.byref(cg) if cg is not None else None,
+                                    out.ctypes.data, cap, C.byref(k), ctr.ctypes.data))
+        return out[:k.value].copy(), ctr[0]
+
+    # ---- batches ----------------------------------------------------------------------
+    def set_device_input(self, d_ptr: int, frame_points, point_step: int = 16, off=(0, 4, 8, 12), keep=None):
+        fp = np.ascontiguousarray(frame_points, dtype=np.uint32)
+        self._keep = keep
+        self._ck(self.lib.cp_batch_set_device_input(self._h, C.c_void_p(d_ptr), len(fp), fp.ctypes.data, point_step,
+                                                    off[0], off[1], off[2], off[3]))
+        self.n_frames = len(fp)
+
+    def set_host_input(self, msgs, fake_missing_intensity: bool = True):
+        views = (CCloudView * len(msgs))(*[make_view(m, fake_missing_intensity) for m in msgs])
+        self._keep = msgs
+        self._ck(self.lib.cp_batch_set_host_input(self._h, views, len(msgs)))
+        self.n_frames = len(msgs)
+
+    def run(self, d: DetectParams, g: GroundParams | None = None):
+        cd = to_c_detect(d)
+        cg = to_c_ground(g) if g is not None else None
+        self._ck(self.lib.cp_batch_run(self._h, C.byref(cd), C.byref(cg) if cg is not None else None))
+
+    def sync(self):
+        self._ck(self.lib.cp_sync(self._h))
+
+    def results(self, cap: int | None = None):
+        """Returns (counters[F], cluster_offsets[F+1], clusters[K_total])."""
+        F = self.n_frames
+        ctr = np.zeros(F, dtype=COUNTER_DTYPE)
+        off = np.zeros(F + 1, dtype=np.uint32)
+        total = C.c_uint64()
+        # first call sizes the output
+        self._ck(self.lib.cp_batch_results(self._h, ctr.ctypes.data, off.ctypes.data, None, 0, C.byref(total)))
+        out = np.zeros(total.value, dtype=CLUSTER_DTYPE)
+        if total.value:
+            self._ck(self.lib.cp_batch_results(self._h, None, None, out.ctypes.data, total.value, C.byref(total)))
+        return ctr, off, out
+
+    def detect_batch(self, msgs, d: DetectParams, g: GroundParams | None = None):
+        self.set_host_input(msgs)
+        self.run(d, g)
+        return self.results()
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.cp_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.cp_last_launch_count(self._h))
+
+    def stream(self) -> int:
+        return int(self.lib.cp_stream(self._h) or 0)
+
+    # ---- parity taps ------------------------------------------------------------------
+    def tap(self, which: int) -> np.ndarray:
+        dt = {TAP_SECTOR_LOW: np.float32, TAP_CROP_POINTS: np.float32, TAP_VOXEL_CLOUD: np.float32,
+              TAP_LABELS: np.int32}.get(which, np.uint32)
+        width = 4 if which in (TAP_CROP_POINTS, TAP_VOXEL_CLOUD) else 1
+        cap = (self.max_points + self.max_frames + 64) * max(1, width) * 4 + self.max_frames * 17 * 4
+        buf = np.empty(cap // 4, dtype=dt)
+        n = C.c_uint64()
+        self._ck(self.lib.cp_debug_tap(self._h, which, buf.ctypes.data, buf.nbytes, C.byref(n)))
+        out = buf[:n.value * width].copy()
+        return out.reshape(-1, 4) if width == 4 else out
+
+    def debug_sort(self, keys: np.ndarray, vals: np.ndarray, bits: int):
+        k = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        v = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._ck(self.lib.cp_debug_sort(self._h, k.ctypes.data, v.ctypes.data, len(k), bits))
+        return k, v

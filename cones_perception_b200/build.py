@@ -1,0 +1,65 @@
+"""Build recipe: compiles libconesgpu.so (sm_100a) and libconesscan.so in-tree."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_DIR = os.path.join(HERE, "_lib")
+GPU_LIB = os.path.join(LIB_DIR, "libconesgpu.so")
+SCAN_LIB = os.path.join(HERE, "scangen", "libconesscan.so")
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _fresh(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _nvcc() -> str:
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: libconesgpu.so cannot be built (there is no CPU fallback)")
+
+
+def build_gpu(force: bool = False, verbose: bool = False) -> str:
+    csrc = os.path.join(HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc))]
+    srcs.append(os.path.join(ROOT, "include", "conesgpu.h"))
+    if not force and _fresh(GPU_LIB, srcs):
+        return GPU_LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", GPU_LIB, os.path.join(csrc, "pipeline.cu")]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    subprocess.run(cmd, check=True)
+    return GPU_LIB
+
+
+def build_scangen(force: bool = False) -> str:
+    src = os.path.join(HERE, "scangen", "scan_gen.cpp")
+    if not force and _fresh(SCAN_LIB, [src]):
+        return SCAN_LIB
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", SCAN_LIB, src], check=True)
+    return SCAN_LIB
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_gpu(force, verbose)
+    build_scangen(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(GPU_LIB)
+    print(SCAN_LIB)

@@ -1,0 +1,1157 @@
+// pipeline.cu — handle, device memory plan, stream orchestration and the C ABI of
+// libconesgpu.so (include/conesgpu.h).  No CPU fallback: every compute entry point needs
+// a CUDA device; without one cp_create fails with CP_E_CUDA.
+#include "../../include/conesgpu.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "cluster_kernels.cuh"
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "stream_kernels.cuh"
+#include "voxel_kernels.cuh"
+
+using namespace cp;
+
+namespace {
+
+constexpr u32 kAbiVersion = 1;
+constexpr size_t kStageChunk = 64ull << 20;  // pinned staging chunk for pageable host clouds
+
+struct HostGeom {
+  std::vector<u32> frame_n;
+  std::vector<u64> frame_off;
+  std::vector<u32> frame_tile0;
+  std::vector<u32> tile_frame;
+  u32 uniform_n = 0, tpf = 0, n_tiles = 0, n_frames = 0;
+  u64 n_points = 0;
+};
+
+}  // namespace
+
+struct cp_handle {
+  cp_config cfg{};
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage[2] = {nullptr, nullptr};
+  std::string err = "";
+  u32 launches = 0;
+  bool batch_ready = false, ran = false;
+  bool taps = false, counted_ground = false;
+
+  u64 cap_c = 0, cap_v = 0;
+  u32 tiles_cap = 0, sort_tiles_cap = 0, hash_cap = 0;
+
+  // device memory
+  Ctl* d_ctl = nullptr;
+  uint8_t* d_in = nullptr;  // staged input (host batches)
+  size_t d_in_bytes = 0;
+  uint8_t* d_out32 = nullptr;
+  const uint8_t* in_ptr = nullptr;  // current batch input (d_in or caller memory)
+  Layout layout{};
+  HostGeom hg;
+  u32 *d_frame_n = nullptr, *d_frame_tile0 = nullptr, *d_tile_frame = nullptr;
+  u64* d_frame_off = nullptr;
+  u32 *d_low_key = nullptr, *d_bbox = nullptr, *d_c_off = nullptr, *d_gcount = nullptr, *d_v_off = nullptr;
+  u32 *d_ncomp_f = nullptr, *d_kcount_f = nullptr, *d_k_off = nullptr;
+  VoxelFrame* d_vf = nullptr;
+  float4* d_pts = nullptr;
+  u32 *d_src = nullptr, *d_frame = nullptr;
+  u64 *d_keys_a = nullptr, *d_keys_b = nullptr, *d_okeys_a = nullptr, *d_okeys_b = nullptr;
+  u32 *d_vals_a = nullptr, *d_vals_b = nullptr, *d_ovals_a = nullptr, *d_ovals_b = nullptr;
+  u32 *d_tile_hist = nullptr, *d_digit_total = nullptr;
+  u32 *d_excl = nullptr, *d_vstart = nullptr, *d_cstart = nullptr, *d_comp_start = nullptr;
+  float4* d_vox = nullptr;
+  u32 *d_vox_frame = nullptr, *d_parent = nullptr, *d_label = nullptr;
+  u64* d_hkeys = nullptr;
+  u32* d_hvals = nullptr;
+  ClusterRec* d_clusters = nullptr;
+  u64 *d_desc_a = nullptr, *d_desc_b = nullptr, *d_desc_c = nullptr, *d_desc_d = nullptr;
+  u32 *d_tap_keys = nullptr, *d_tap_order = nullptr;
+  i32* d_tap_labels = nullptr;
+  // pinned host mirrors
+  uint8_t* h_stage[2] = {nullptr, nullptr};
+  Ctl* h_ctl = nullptr;
+  u32* h_frame_u32 = nullptr;  // scratch for per-frame readback
+  std::vector<void*> dev_allocs, pin_allocs;
+};
+
+namespace {
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char buf_[512];                                                                         \
+      snprintf(buf_, sizeof(buf_), "%s:%d %s -> %s", __FILE__, __LINE__, #call,               \
+               cudaGetErrorString(e_));                                                       \
+      h->err = buf_;                                                                          \
+      return CP_E_CUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+template <typename T>
+cp_status dalloc(cp_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) {
+    h->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? CP_E_NOMEM : CP_E_CUDA;
+  }
+  h->dev_allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return CP_OK;
+}
+template <typename T>
+cp_status palloc(cp_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMallocHost(&q, count * sizeof(T));
+  if (e != cudaSuccess) {
+    h->err = std::string("cudaMallocHost failed: ") + cudaGetErrorString(e);
+    return CP_E_NOMEM;
+  }
+  h->pin_allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return CP_OK;
+}
+
+u32 ceil_log2_host(u64 v) {
+  u32 b = 0;
+  while ((1ull << b) < v && b < 63) ++b;
+  return b;
+}
+
+// ---- exact threshold solving: the reference compares (double)(float)sqrt(s)
+// against double parameters; since that is monotone in s, find the switching point once.
+double bits_to_double(u64 b) {
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+}
+// smallest non-negative double s (by bit pattern, up to +inf) with pred(s) true; pred monotone
+template <typename F>
+double first_true(F pred) {
+  const u64 inf_bits = 0x7FF0000000000000ull;
+  if (pred(0.0)) return 0.0;
+  if (!pred(bits_to_double(inf_bits))) return bits_to_double(0x7FF8000000000000ull);  // NaN: never
+  u64 lo = 0, hi = inf_bits;  // pred(lo) false, pred(hi) true
+  while (hi - lo > 1) {
+    const u64 mid = lo + (hi - lo) / 2;
+    if (pred(bits_to_double(mid))) hi = mid; else lo = mid;
+  }
+  return bits_to_double(hi);
+}
+float round_up_to_float(double t) {  // smallest float >= t
+  if (t != t) return -INFINITY;      // NaN threshold: the reference's compare is always false
+  float f = (float)t;
+  if ((double)f < t) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+cp_status make_crop(cp_handle* h, const cp_detect_params* d, CropK* c) {
+  memset(c, 0, sizeof(*c));
+  c->do_crop = 1;
+  const double dmax = d->distance_treshold_max, dmin = d->distance_treshold_min;
+  // src/cone_detection.cpp:195  p.z < level_threshold  (float promoted to double)
+  c->zthr = round_up_to_float(d->level_threshold);
+  // :196-197 via utils.cpp:32-34:  d = (float)sqrt(s);  drop iff d > dmax or d < dmin
+  auto dist = [](double s) { return (double)(float)sqrt(s); };
+  c->smax = first_true([&](double s) { return dist(s) > dmax; });          // drop iff s >= smax
+  c->smin = first_true([&](double s) { return !(dist(s) < dmin); });       // drop iff s <  smin
+  if (c->smax != c->smax) c->smax = INFINITY;  // never dropped by dmax (inf >= inf only for s = inf,
+                                               // where (float)sqrt(inf)=inf > dmax is false iff dmax=inf)
+  if (c->smin != c->smin) c->smin = INFINITY;  // always dropped by dmin
+  const double g = 2e-6;
+  c->smax_lo = (float)(c->smax * (1.0 - g));
+  c->smax_hi = (float)(c->smax * (1.0 + g));
+  c->smin_lo = (float)(c->smin * (1.0 - g));
+  c->smin_hi = (float)(c->smin * (1.0 + g));
+  if (c->smax == 0.0) c->smax_lo = -1.0f, c->smax_hi = 0.0f;  // everything dropped: sf >= 0 >= smax_hi
+  if (c->smin == 0.0) c->smin_lo = -1.0f, c->smin_hi = -1.0f; // nothing dropped by dmin
+  // :200-201  -theta >= a  or  a >= theta  <=>  !(|a| < F), F = smallest float >= theta
+  const double theta = d->angle_threshold * M_PI / 180;
+  c->f_hi = (theta != theta) ? INFINITY : round_up_to_float(theta);
+  c->f_lo_guard = c->f_hi - 4e-6f;
+  c->f_hi_guard = c->f_hi + 4e-6f;
+  (void)h;
+  return CP_OK;
+}
+
+// does the ground node's zero filler point (0,0,0) survive the crop?  (host restatement of
+// the predicate for this single constant point; needed to honour src/ground_removal.cpp:79)
+bool zero_point_survives(const cp_detect_params* d) {
+  if (0.0 < d->level_threshold) return false;
+  const double dist = 0.0;
+  if (dist > d->distance_treshold_max) return false;
+  if (dist < d->distance_treshold_min) return false;
+  const double a = 0.0, theta = d->angle_threshold * M_PI / 180;
+  if (-theta >= a) return false;
+  if (a >= theta) return false;
+  return true;
+}
+
+// host upper bound on the voxel key width, from the crop's extents (only used to decide
+// how many sort passes to enqueue; the live width is computed on the device)
+u32 voxel_bits_bound(const cp_detect_params* d, const VoxelK& vk, u64 cap_c) {
+  const double dmax = fabs(d->distance_treshold_max);
+  const double zlo = std::max(-dmax, d->level_threshold);
+  const double ex = 2.0 * dmax * vk.inv[0] + 3.0, ey = 2.0 * dmax * vk.inv[1] + 3.0;
+  const double ez = std::max(0.0, dmax - zlo) * vk.inv[2] + 3.0;
+  const double cells = ex * ey * ez;
+  u32 b = 32;
+  if (cells == cells && cells < 2147483648.0) b = ceil_log2_host((u64)cells + 1);
+  // passthrough frames key by position: up to ceil(log2(cap_c)) bits
+  return std::max(b, std::min<u32>(32u, ceil_log2_host(cap_c)));
+}
+
+cp_status make_cluster(cp_handle* h, const cp_detect_params* d, u32 n_frames, ClusterK* k, u32* csort_bits,
+                       u32* osort_bits) {
+  // src/cone_detection.cpp:212  sqrt(pow(CONE_HEIGHT,2)+pow(CONE_WIDTH,2)) in double;
+  // PCL extract(): static_cast<float>(tolerance); KdTreeFLANN::radiusSearch: (float)(r*r) in double
+  const double tol = sqrt((double)d->cone_height * (double)d->cone_height +
+                          (double)d->cone_width * (double)d->cone_width);
+  const float tol_f = (float)tol;
+  k->r2 = (float)((double)tol_f * (double)tol_f);
+  if (!(tol_f > 0.0f) || !isfinite(tol_f)) {
+    h->err = "cone_width/cone_height give a non-positive or non-finite cluster tolerance";
+    return CP_E_PARAM;
+  }
+  const double edge = (double)tol_f * 1.01;
+  double reach = fabs(d->distance_treshold_max);
+  if (!(reach < 1e6)) {
+    h->err = "distance_treshold_max must be finite and below 1e6 m";
+    return CP_E_PARAM;
+  }
+  reach += 2 * edge;
+  const u64 nx = (u64)ceil(2.0 * reach / edge) + 2;
+  k->inv_h = (float)(1.0 / edge);
+  k->origin = (float)reach;
+  k->nx = (u32)nx;
+  const u64 cells = (u64)n_frames * nx * nx * nx;
+  if (nx > (1u << 20) || ceil_log2_host(cells) > 60) {
+    h->err = "neighbour grid too large for 64-bit cell keys";
+    return CP_E_PARAM;
+  }
+  *csort_bits = ceil_log2_host(cells);
+  if (*csort_bits == 0) *csort_bits = 1;
+  k->min_size = d->min_cluster_size < 0 ? 0u : (u32)d->min_cluster_size;
+  k->max_size = d->max_cluster_size < 0 ? 0u : (u32)d->max_cluster_size;
+  k->frame_bits = ceil_log2_host(n_frames);
+  k->size_bits = ceil_log2_host((u64)k->max_size + 1);
+  *osort_bits = k->frame_bits + k->size_bits + 1;
+  return CP_OK;
+}
+
+__global__ void init_kernel(Ctl* ctl, u32 n_frames, float default_low, u32* low_key, u32* bbox, u32* c_off,
+                            u32* gcount, u32* ncomp_f, u32* kcount_f, u64* desc_a, u32 na, u64* desc_b,
+                            u64* desc_c, u64* desc_d, u32 nb) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  if (t == 0) {
+    Ctl z;
+    memset(&z, 0, sizeof(z));
+    *ctl = z;
+    c_off[0] = 0;
+  }
+  const u32 lk = f2ord(default_low);
+  for (u32 i = t; i < n_frames * kSectStride; i += stride) low_key[i] = lk;
+  for (u32 i = t; i < n_frames * 8; i += stride) bbox[i] = ((i & 7u) < 4u) ? 0xFFFFFFFFu : 0u;
+  for (u32 i = t; i < n_frames; i += stride) {
+    gcount[i] = 0;
+    ncomp_f[i] = 0;
+    kcount_f[i] = 0;
+    c_off[i + 1] = 0;
+  }
+  for (u32 i = t; i < na; i += stride) desc_a[i] = 0;
+  for (u32 i = t; i < nb; i += stride) {
+    desc_b[i] = 0;
+    desc_c[i] = 0;
+    desc_d[i] = 0;
+  }
+}
+
+__global__ void tap_voxel_kernel(const Ctl* ctl, const u64* keys_a, const u64* keys_b, const u32* vals_a,
+                                 const u32* vals_b, u32* tap_keys, u32* tap_order) {
+  const u32 n = ctl->n_surv;
+  const bool inb = sorted_in_b(ctl->vsort_bits);
+  const u64* keys = inb ? keys_b : keys_a;
+  const u32* vals = inb ? vals_b : vals_a;
+  const u64 mask = (ctl->voxel_key_bits >= 64) ? ~0ull : ((1ull << ctl->voxel_key_bits) - 1ull);
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    tap_keys[i] = (u32)(keys[i] & mask);
+    tap_order[i] = vals[i];
+  }
+}
+
+cp_status check_view(cp_handle* h, const cp_cloud_view* v) {
+  if (!v) {
+    h->err = "NULL cloud view";
+    return CP_E_PARAM;
+  }
+  const u64 n = (u64)v->width * v->height;
+  if (n && !v->data) {
+    h->err = "cloud view has points but a NULL data pointer";
+    return CP_E_PARAM;
+  }
+  if (v->is_bigendian) {
+    h->err = "big-endian PointCloud2 data is not supported (pcl::fromROSMsg does not swap either)";
+    return CP_E_BADFIELD;
+  }
+  if (v->off_x < 0 || v->off_y < 0 || v->off_z < 0) {
+    h->err = "x/y/z FLOAT32 fields are required";
+    return CP_E_BADFIELD;
+  }
+  const i32 mx = std::max(std::max(v->off_x, v->off_y), std::max(v->off_z, v->off_intensity));
+  if ((u32)mx + 4 > v->point_step) {
+    h->err = "field offset + 4 exceeds point_step";
+    return CP_E_BADFIELD;
+  }
+  if (v->height > 1 && v->row_step < v->width * v->point_step) {
+    h->err = "row_step smaller than width * point_step";
+    return CP_E_BADFIELD;
+  }
+  return CP_OK;
+}
+
+Layout make_layout(u32 step, i32 ox, i32 oy, i32 oz, i32 oi) {
+  Layout L;
+  L.step = step;
+  L.ox = ox;
+  L.oy = oy;
+  L.oz = oz;
+  L.oi = oi;
+  if (step == 16 && ox == 0 && oy == 4 && oz == 8 && oi == 12)
+    L.mode = 0;
+  else if (step % 4 == 0 && ox % 4 == 0 && oy % 4 == 0 && oz % 4 == 0 && (oi < 0 || oi % 4 == 0))
+    L.mode = 1;
+  else
+    L.mode = 2;
+  return L;
+}
+
+cp_status set_geometry(cp_handle* h, const u32* frame_points, u32 n_frames) {
+  HostGeom& g = h->hg;
+  if (n_frames == 0 || n_frames > h->cfg.max_frames) {
+    h->err = "n_frames is 0 or exceeds cp_config.max_frames";
+    return n_frames ? CP_E_CAPACITY : CP_E_PARAM;
+  }
+  g.n_frames = n_frames;
+  g.frame_n.assign(frame_points, frame_points + n_frames);
+  g.frame_off.resize(n_frames);
+  g.frame_tile0.resize(n_frames);
+  u64 off = 0;
+  u64 tiles = 0;
+  bool uniform = true;
+  for (u32 f = 0; f < n_frames; ++f) {
+    g.frame_off[f] = off;
+    g.frame_tile0[f] = (u32)tiles;
+    off += frame_points[f];
+    u64 t = ((u64)frame_points[f] + kStreamTile - 1) / kStreamTile;
+    if (t == 0) t = 1;  // empty frames still own one (empty) tile so their offsets get written
+    tiles += t;
+    if (frame_points[f] != frame_points[0]) uniform = false;
+  }
+  if (off > h->cfg.max_points || off >= (1ull << 31)) {
+    h->err = "batch holds more points than cp_config.max_points (or >= 2^31)";
+    return CP_E_CAPACITY;
+  }
+  if (tiles > h->tiles_cap) {
+    h->err = "batch needs more stream tiles than the handle was sized for";
+    return CP_E_CAPACITY;
+  }
+  g.n_points = off;
+  g.n_tiles = (u32)tiles;
+  g.uniform_n = (uniform && frame_points[0] > 0) ? frame_points[0] : 0;
+  g.tpf = g.uniform_n ? (g.uniform_n + kStreamTile - 1) / kStreamTile : 0;
+  CK(cudaMemcpyAsync(h->d_frame_n, g.frame_n.data(), sizeof(u32) * n_frames, cudaMemcpyHostToDevice, h->stream));
+  if (!g.uniform_n) {
+    g.tile_frame.resize(g.n_tiles);
+    for (u32 f = 0; f < n_frames; ++f) {
+      const u32 t1 = (f + 1 < n_frames) ? g.frame_tile0[f + 1] : g.n_tiles;
+      for (u32 t = g.frame_tile0[f]; t < t1; ++t) g.tile_frame[t] = f;
+    }
+    // pageable sources: the copies below are staged by the runtime before returning
+    CK(cudaMemcpyAsync(h->d_frame_off, g.frame_off.data(), sizeof(u64) * n_frames, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_frame_tile0, g.frame_tile0.data(), sizeof(u32) * n_frames, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_tile_frame, g.tile_frame.data(), sizeof(u32) * g.n_tiles, cudaMemcpyHostToDevice, h->stream));
+  }
+  return CP_OK;
+}
+
+Geom device_geom(const cp_handle* h) {
+  Geom g;
+  g.n_frames = h->hg.n_frames;
+  g.uniform_n = h->hg.uniform_n;
+  g.tpf = h->hg.tpf;
+  g.n_tiles = h->hg.n_tiles;
+  g.frame_n = h->d_frame_n;
+  g.frame_off = h->d_frame_off;
+  g.tile_frame = h->d_tile_frame;
+  g.frame_tile0 = h->d_frame_tile0;
+  return g;
+}
+
+u32 grid_for(u64 work, u32 block, int sms, int per_sm) {
+  u64 b = (work + block - 1) / block;
+  if (b == 0) b = 1;
+  const u64 cap = (u64)sms * per_sm;
+  return (u32)(b < cap ? b : cap);
+}
+
+template <bool OUT32>
+void launch_compact(cp_handle* h, const Geom& g, const CropK& c, const GroundK& gk, const CompactOut& o, u32 grid) {
+  switch (h->layout.mode) {
+    case 0: mask_crop_compact_kernel<0, OUT32><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, o); break;
+    case 1: mask_crop_compact_kernel<1, OUT32><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, o); break;
+    default: mask_crop_compact_kernel<2, OUT32><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, o); break;
+  }
+}
+void launch_sector_min(cp_handle* h, const Geom& g, u32 grid) {
+  switch (h->layout.mode) {
+    case 0: ground_sector_min_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key); break;
+    case 1: ground_sector_min_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key); break;
+    default: ground_sector_min_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key); break;
+  }
+}
+
+void launch_init(cp_handle* h, float default_low) {
+  const u32 nb = (u32)(h->cap_c / kHeadTile + 2);
+  init_kernel<<<h->sms * 2, 256, 0, h->stream>>>(h->d_ctl, h->hg.n_frames, default_low, h->d_low_key, h->d_bbox,
+                                                 h->d_c_off, h->d_gcount, h->d_ncomp_f, h->d_kcount_f,
+                                                 h->d_desc_a, h->hg.n_tiles, h->d_desc_b, h->d_desc_c, h->d_desc_d, nb);
+  h->launches++;
+}
+
+SortArgs sort_args(cp_handle* h, bool order_sort, const u32* d_n, const u32* d_bits) {
+  SortArgs a;
+  a.keys_a = order_sort ? h->d_okeys_a : h->d_keys_a;
+  a.keys_b = order_sort ? h->d_okeys_b : h->d_keys_b;
+  a.vals_a = order_sort ? h->d_ovals_a : h->d_vals_a;
+  a.vals_b = order_sort ? h->d_ovals_b : h->d_vals_b;
+  a.d_n = d_n;
+  a.d_bits = d_bits;
+  a.tile_hist = h->d_tile_hist;
+  a.digit_total = h->d_digit_total;
+  a.tiles_cap = h->sort_tiles_cap;
+  return a;
+}
+
+cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_ground_params* ground) {
+  if (!d) {
+    h->err = "NULL detect params";
+    return CP_E_PARAM;
+  }
+  if (!h->batch_ready) {
+    h->err = "no batch input set";
+    return CP_E_STATE;
+  }
+  const float leaf[3] = {(float)d->voxel_filter_leaf_size_x, (float)d->voxel_filter_leaf_size_y,
+                         (float)d->voxel_filter_leaf_size_z};
+  for (int a = 0; a < 3; ++a)
+    if (!(leaf[a] > 0.0f) || !isfinite(leaf[a])) {
+      h->err = "voxel_filter_leaf_size_* must be positive and finite";
+      return CP_E_PARAM;
+    }
+  CropK crop;
+  cp_status st = make_crop(h, d, &crop);
+  if (st) return st;
+  ClusterK ck;
+  u32 csort_bits = 0, osort_bits = 0;
+  st = make_cluster(h, d, h->hg.n_frames, &ck, &csort_bits, &osort_bits);
+  if (st) return st;
+  GroundK gk;
+  gk.do_ground = ground ? 1 : 0;
+  gk.pad_survives = (ground && zero_point_survives(d)) ? 1 : 0;
+  gk.want_count = gk.pad_survives;
+  h->counted_ground = gk.want_count != 0;
+  VoxelK vk;
+  for (int a = 0; a < 3; ++a) vk.inv[a] = 1.0f / leaf[a];
+  vk.frame_bits = ceil_log2_host(h->hg.n_frames);
+
+  const Geom g = device_geom(h);
+  const u32 F = h->hg.n_frames;
+  h->launches = 0;
+  cudaEventRecord(h->ev0, h->stream);
+  launch_init(h, ground ? ground->default_lowest_point : 0.0f);
+  const u32 sgrid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, 8);
+  if (ground) {
+    launch_sector_min(h, g, sgrid);
+    h->launches++;
+  }
+  CompactOut co;
+  co.pts = h->d_pts;
+  co.src = h->d_src;
+  co.frame = h->d_frame;
+  co.cap = (u32)h->cap_c;
+  co.c_off = h->d_c_off;
+  co.bbox_key = h->d_bbox;
+  co.gcount = h->d_gcount;
+  co.desc = h->d_desc_a;
+  co.ctl = h->d_ctl;
+  co.out32 = nullptr;
+  launch_compact<false>(h, g, crop, gk, co, sgrid);
+  h->launches++;
+
+  // ---- VoxelGrid
+  const u32 fgrid = (F + 255) / 256;
+  voxel_setup_kernel<<<fgrid, 256, 0, h->stream>>>(F, vk, h->d_bbox, h->d_c_off, h->d_vf, h->d_ctl);
+  voxel_bits_kernel<<<1, 1, 0, h->stream>>>(h->d_ctl, vk.frame_bits);
+  const u32 cgrid = grid_for(h->cap_c, 256, h->sms, 8);
+  voxel_key_kernel<<<cgrid, 256, 0, h->stream>>>(h->d_ctl, vk, h->d_pts, h->d_frame, h->d_c_off, h->d_vf,
+                                                 h->d_keys_a, h->d_vals_a);
+  h->launches += 3;
+  {
+    SortArgs sa = sort_args(h, false, &h->d_ctl->n_surv, &h->d_ctl->vsort_bits);
+    h->launches += radix_sort_enqueue(h->stream, sa, voxel_bits_bound(d, vk, h->cap_c) + vk.frame_bits,
+                                      (u32)h->cap_c, h->sms);
+  }
+  if (h->taps) {
+    tap_voxel_kernel<<<cgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b,
+                                                   h->d_tap_keys, h->d_tap_order);
+    h->launches++;
+  }
+  const u32 hgrid = grid_for(h->cap_c, kHeadTile, h->sms, 4);
+  {
+    HeadArgs ha;
+    ha.keys_a = h->d_keys_a;
+    ha.keys_b = h->d_keys_b;
+    ha.d_bits = &h->d_ctl->vsort_bits;
+    ha.d_n = &h->d_ctl->n_surv;
+    ha.excl = h->d_excl;
+    ha.starts = h->d_vstart;
+    ha.starts_cap = (u32)h->cap_v;
+    ha.d_total = &h->d_ctl->n_vox;
+    ha.desc = h->d_desc_b;
+    ha.ticket = &h->d_ctl->ticket[1];
+    ha.error = &h->d_ctl->error;
+    ha.err_bit = kErrVoxels;
+    segment_heads_kernel<<<hgrid, kHeadThreads, 0, h->stream>>>(ha);
+  }
+  const u32 vgrid = grid_for(h->cap_v, 256, h->sms, 8);
+  VoxelOut vo;
+  vo.vox = h->d_vox;
+  vo.vox_frame = h->d_vox_frame;
+  vo.v_off = h->d_v_off;
+  voxel_mean_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b,
+                                                  h->d_vstart, h->d_pts, h->d_src, h->d_frame_n, h->hg.uniform_n,
+                                                  h->d_gcount, vo);
+  voxel_offsets_kernel<<<(F + 1 + 255) / 256, 256, 0, h->stream>>>(h->d_ctl, F, h->d_c_off, h->d_excl, h->d_v_off);
+  h->launches += 3;
+
+  // ---- Euclidean clustering
+  cluster_bits_kernel<<<1, 1, 0, h->stream>>>(h->d_ctl, csort_bits, osort_bits);
+  cell_key_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, ck, h->d_vox, h->d_vox_frame, h->d_keys_a, h->d_vals_a,
+                                                h->d_parent);
+  h->launches += 2;
+  {
+    SortArgs sa = sort_args(h, false, &h->d_ctl->n_vox, &h->d_ctl->csort_bits);
+    h->launches += radix_sort_enqueue(h->stream, sa, csort_bits, (u32)h->cap_v, h->sms);
+  }
+  const u32 hvgrid = grid_for(h->cap_v, kHeadTile, h->sms, 4);
+  {
+    HeadArgs ha;
+    ha.keys_a = h->d_keys_a;
+    ha.keys_b = h->d_keys_b;
+    ha.d_bits = &h->d_ctl->csort_bits;
+    ha.d_n = &h->d_ctl->n_vox;
+    ha.excl = nullptr;
+    ha.starts = h->d_cstart;
+    ha.starts_cap = (u32)h->cap_v;
+    ha.d_total = &h->d_ctl->n_cells;
+    ha.desc = h->d_desc_c;
+    ha.ticket = &h->d_ctl->ticket[2];
+    ha.error = &h->d_ctl->error;
+    ha.err_bit = kErrInternal;
+    segment_heads_kernel<<<hvgrid, kHeadThreads, 0, h->stream>>>(ha);
+  }
+  hash_setup_kernel<<<1, 1, 0, h->stream>>>(h->d_ctl, h->hash_cap);
+  hash_clear_kernel<<<grid_for(h->hash_cap, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_ctl, h->d_hkeys);
+  hash_insert_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_cstart, h->d_hkeys,
+                                                   h->d_hvals);
+  neighbour_union_kernel<<<grid_for(h->cap_v * 27ull, 256, h->sms, 8), 256, 0, h->stream>>>(
+      h->d_ctl, ck, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b, h->d_cstart, h->d_hkeys, h->d_hvals,
+      h->d_vox, h->d_parent);
+  flatten_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_parent, h->d_label, h->d_keys_a, h->d_vals_a);
+  h->launches += 6;
+  {
+    SortArgs sa = sort_args(h, false, &h->d_ctl->n_vox, &h->d_ctl->lsort_bits);
+    h->launches += radix_sort_enqueue(h->stream, sa, ceil_log2_host(h->cap_v) + 1, (u32)h->cap_v, h->sms);
+  }
+  {
+    HeadArgs ha;
+    ha.keys_a = h->d_keys_a;
+    ha.keys_b = h->d_keys_b;
+    ha.d_bits = &h->d_ctl->lsort_bits;
+    ha.d_n = &h->d_ctl->n_vox;
+    ha.excl = nullptr;
+    ha.starts = h->d_comp_start;
+    ha.starts_cap = (u32)h->cap_v;
+    ha.d_total = &h->d_ctl->n_comp;
+    ha.desc = h->d_desc_d;
+    ha.ticket = &h->d_ctl->ticket[3];
+    ha.error = &h->d_ctl->error;
+    ha.err_bit = kErrInternal;
+    segment_heads_kernel<<<hvgrid, kHeadThreads, 0, h->stream>>>(ha);
+  }
+  component_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, ck, h->d_keys_a, h->d_keys_b, h->d_comp_start,
+                                                 h->d_vox_frame, h->d_ncomp_f, h->d_kcount_f, h->d_okeys_a,
+                                                 h->d_ovals_a, h->d_ctl);
+  frame_scan_kernel<<<1, 1024, 0, h->stream>>>(F, h->d_kcount_f, h->d_k_off);
+  h->launches += 3;
+  {
+    SortArgs sa = sort_args(h, true, &h->d_ctl->n_comp, &h->d_ctl->osort_bits);
+    h->launches += radix_sort_enqueue(h->stream, sa, osort_bits, (u32)h->cap_v, h->sms);
+  }
+  emit_clusters_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_ovals_a, h->d_ovals_b, h->d_keys_a, h->d_keys_b,
+                                                     h->d_vals_a, h->d_vals_b, h->d_comp_start, h->d_vox,
+                                                     h->d_vox_frame, h->d_v_off, h->d_clusters, (u32)h->cap_v,
+                                                     h->d_ctl);
+  h->launches++;
+  if (h->taps) {
+    local_labels_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_label, h->d_vox_frame, h->d_v_off,
+                                                      h->d_tap_labels);
+    h->launches++;
+  }
+  cudaEventRecord(h->ev1, h->stream);
+  CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
+  h->ran = true;
+  return CP_OK;
+}
+
+// copy a host cloud into the device input buffer at byte offset `dst_off`
+cp_status stage_view(cp_handle* h, const cp_cloud_view* v, size_t dst_off, int* ring) {
+  const u64 n = (u64)v->width * v->height;
+  if (n == 0) return CP_OK;
+  const size_t row_bytes = (size_t)v->width * v->point_step;
+  const bool contiguous = (v->height <= 1) || (v->row_step == row_bytes);
+  cudaPointerAttributes attr;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&attr, v->data) == cudaSuccess)
+    pinned = (attr.type == cudaMemoryTypeHost);
+  else
+    cudaGetLastError();
+  if (pinned && contiguous) {
+    CK(cudaMemcpyAsync(h->d_in + dst_off, v->data, row_bytes * v->height, cudaMemcpyHostToDevice, h->stream));
+    return CP_OK;
+  }
+  // pageable (or row-padded) source: pack through the pinned ring, chunk by chunk
+  const size_t total = row_bytes * v->height;
+  size_t done = 0;
+  while (done < total) {
+    const size_t chunk = std::min(kStageChunk, total - done);
+    const int r = *ring;
+    CK(cudaEventSynchronize(h->ev_stage[r]));
+    if (contiguous) {
+      memcpy(h->h_stage[r], v->data + done, chunk);
+    } else {
+      size_t w = 0;
+      while (w < chunk) {  // row-wise pack (rows are row_step apart in the source)
+        const size_t pos = done + w;
+        const size_t row = pos / row_bytes, col = pos % row_bytes;
+        const size_t take = std::min(row_bytes - col, chunk - w);
+        memcpy(h->h_stage[r] + w, v->data + row * v->row_step + col, take);
+        w += take;
+      }
+    }
+    CK(cudaMemcpyAsync(h->d_in + dst_off + done, h->h_stage[r], chunk, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev_stage[r], h->stream));
+    *ring = r ^ 1;
+    done += chunk;
+  }
+  return CP_OK;
+}
+
+cp_status device_errors(cp_handle* h) {
+  const u32 e = h->h_ctl->error;
+  if (!e) return CP_OK;
+  if (e & kErrSurvivors) h->err = "more crop survivors than cp_config.max_survivors";
+  else if (e & kErrVoxels) h->err = "more voxels / clusters than cp_config.max_voxels";
+  else if (e & kErrHash) h->err = "neighbour-grid hash table too small for this batch";
+  else h->err = "internal capacity error";
+  return CP_E_CAPACITY;
+}
+
+}  // namespace
+
+// ======================================================================== C ABI
+extern "C" {
+
+const char* cp_strerror(cp_status s) {
+  switch (s) {
+    case CP_OK: return "ok";
+    case CP_E_PARAM: return "invalid parameter";
+    case CP_E_BADFIELD: return "unsupported PointCloud2 field layout";
+    case CP_E_CAPACITY: return "capacity exceeded";
+    case CP_E_CUDA: return "CUDA error";
+    case CP_E_NOMEM: return "out of memory";
+    case CP_E_STATE: return "invalid call order";
+  }
+  return "unknown status";
+}
+
+const char* cp_last_error(const cp_handle* h) { return h ? h->err.c_str() : "NULL handle"; }
+uint32_t cp_abi_version(void) { return kAbiVersion; }
+
+static std::string g_create_error;
+const char* cp_create_error(void) { return g_create_error.c_str(); }
+
+cp_status cp_create(cp_handle** out, const cp_config* cfg) {
+  if (!out || !cfg) return CP_E_PARAM;
+  *out = nullptr;
+  if (cfg->max_points == 0 || cfg->max_frames == 0 || cfg->max_points >= (1ull << 31)) {
+    g_create_error = "max_points must be in [1, 2^31) and max_frames >= 1";
+    return CP_E_PARAM;
+  }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(ce) +
+                     " (libconesgpu has no CPU fallback)";
+    cudaGetLastError();
+    return CP_E_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = "device ordinal out of range";
+    return CP_E_PARAM;
+  }
+  cp_handle* h = new (std::nothrow) cp_handle();
+  if (!h) return CP_E_NOMEM;
+  h->cfg = *cfg;
+  cp_status st = CP_OK;
+  auto fail = [&](cp_status s) {
+    g_create_error = h->err;
+    cp_destroy(h);
+    return s;
+  };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) {
+    h->err = "cudaSetDevice failed";
+    return fail(CP_E_CUDA);
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) {
+    h->err = "cudaGetDeviceProperties failed";
+    return fail(CP_E_CUDA);
+  }
+  if (prop.major < 10) {
+    h->err = "libconesgpu is built for sm_100a only; device compute capability is too low";
+    return fail(CP_E_CUDA);
+  }
+  h->sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming) != cudaSuccess) {
+    h->err = "stream/event creation failed";
+    return fail(CP_E_CUDA);
+  }
+  const char* tap_env = getenv("CONESGPU_TAPS");
+  h->taps = tap_env && tap_env[0] == '1';
+  const u64 P = cfg->max_points;
+  const u32 F = cfg->max_frames;
+  h->cap_c = cfg->max_survivors ? std::min<u64>(cfg->max_survivors, P + F) : P + F;
+  h->cap_v = cfg->max_voxels ? std::min<u64>(cfg->max_voxels, h->cap_c) : h->cap_c;
+  h->tiles_cap = (u32)(P / kStreamTile + F + 1);
+  h->sort_tiles_cap = (u32)(h->cap_c / kSortTile + 2);
+  u64 hc = 64;
+  while (hc < 2 * h->cap_v) hc <<= 1;
+  h->hash_cap = (u32)std::min<u64>(hc, 1ull << 31);
+  const u32 step = cfg->max_point_step ? cfg->max_point_step : 16;
+  h->d_in_bytes = (size_t)P * step;
+#define A(call)                \
+  do {                         \
+    st = (call);               \
+    if (st) return fail(st);   \
+  } while (0)
+  A(dalloc(h, &h->d_ctl, 1));
+  A(dalloc(h, &h->d_frame_n, F));
+  A(dalloc(h, &h->d_frame_off, F));
+  A(dalloc(h, &h->d_frame_tile0, F));
+  A(dalloc(h, &h->d_tile_frame, h->tiles_cap));
+  A(dalloc(h, &h->d_low_key, (size_t)F * kSectStride));
+  A(dalloc(h, &h->d_bbox, (size_t)F * 8));
+  A(dalloc(h, &h->d_c_off, F + 1));
+  A(dalloc(h, &h->d_gcount, F));
+  A(dalloc(h, &h->d_v_off, F + 1));
+  A(dalloc(h, &h->d_ncomp_f, F));
+  A(dalloc(h, &h->d_kcount_f, F));
+  A(dalloc(h, &h->d_k_off, F + 1));
+  A(dalloc(h, &h->d_vf, F));
+  A(dalloc(h, &h->d_pts, h->cap_c));
+  A(dalloc(h, &h->d_src, h->cap_c));
+  A(dalloc(h, &h->d_frame, h->cap_c));
+  A(dalloc(h, &h->d_keys_a, h->cap_c));
+  A(dalloc(h, &h->d_keys_b, h->cap_c));
+  A(dalloc(h, &h->d_vals_a, h->cap_c));
+  A(dalloc(h, &h->d_vals_b, h->cap_c));
+  A(dalloc(h, &h->d_okeys_a, h->cap_v));
+  A(dalloc(h, &h->d_okeys_b, h->cap_v));
+  A(dalloc(h, &h->d_ovals_a, h->cap_v));
+  A(dalloc(h, &h->d_ovals_b, h->cap_v));
+  A(dalloc(h, &h->d_tile_hist, (size_t)kRadix * h->sort_tiles_cap));
+  A(dalloc(h, &h->d_digit_total, kRadix));
+  A(dalloc(h, &h->d_excl, h->cap_c));
+  A(dalloc(h, &h->d_vstart, h->cap_v));
+  A(dalloc(h, &h->d_cstart, h->cap_v));
+  A(dalloc(h, &h->d_comp_start, h->cap_v));
+  A(dalloc(h, &h->d_vox, h->cap_v));
+  A(dalloc(h, &h->d_vox_frame, h->cap_v));
+  A(dalloc(h, &h->d_parent, h->cap_v));
+  A(dalloc(h, &h->d_label, h->cap_v));
+  A(dalloc(h, &h->d_hkeys, h->hash_cap));
+  A(dalloc(h, &h->d_hvals, h->hash_cap));
+  A(dalloc(h, &h->d_clusters, h->cap_v));
+  A(dalloc(h, &h->d_desc_a, h->tiles_cap));
+  const size_t nb = h->cap_c / kHeadTile + 2;
+  A(dalloc(h, &h->d_desc_b, nb));
+  A(dalloc(h, &h->d_desc_c, nb));
+  A(dalloc(h, &h->d_desc_d, nb));
+  if (h->taps) {
+    A(dalloc(h, &h->d_tap_keys, h->cap_c));
+    A(dalloc(h, &h->d_tap_order, h->cap_c));
+    A(dalloc(h, &h->d_tap_labels, h->cap_v));
+  }
+  A(palloc(h, &h->h_stage[0], kStageChunk));
+  A(palloc(h, &h->h_stage[1], kStageChunk));
+  A(palloc(h, &h->h_ctl, 1));
+  A(palloc(h, &h->h_frame_u32, (size_t)(F + 1) * 8));
+#undef A
+  memset(h->h_ctl, 0, sizeof(Ctl));
+  *out = h;
+  return CP_OK;
+}
+
+void cp_destroy(cp_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->dev_allocs) cudaFree(p);
+  for (void* p : h->pin_allocs) cudaFreeHost(p);
+  if (h->d_out32) cudaFree(h->d_out32);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+cp_status cp_batch_set_device_input(cp_handle* h, const void* d_points, uint32_t n_frames,
+                                    const uint32_t* frame_points, uint32_t point_step, int32_t off_x,
+                                    int32_t off_y, int32_t off_z, int32_t off_intensity) {
+  if (!h) return CP_E_PARAM;
+  if (!d_points || !frame_points) {
+    h->err = "NULL device pointer or frame_points";
+    return CP_E_PARAM;
+  }
+  if (off_x < 0 || off_y < 0 || off_z < 0 ||
+      (u32)std::max(std::max(off_x, off_y), std::max(off_z, off_intensity)) + 4 > point_step) {
+    h->err = "x/y/z offsets missing or beyond point_step";
+    return CP_E_BADFIELD;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  h->batch_ready = false;
+  cp_status st = set_geometry(h, frame_points, n_frames);
+  if (st) return st;
+  h->layout = make_layout(point_step, off_x, off_y, off_z, off_intensity);
+  if (h->layout.mode == 0 && ((uintptr_t)d_points & 15u)) h->layout.mode = 1;
+  h->in_ptr = static_cast<const uint8_t*>(d_points);
+  h->batch_ready = true;
+  h->ran = false;
+  return CP_OK;
+}
+
+cp_status cp_batch_set_host_input(cp_handle* h, const cp_cloud_view* frames, uint32_t n_frames) {
+  if (!h) return CP_E_PARAM;
+  if (!frames || n_frames == 0) {
+    h->err = "NULL frames or n_frames == 0";
+    return CP_E_PARAM;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  h->batch_ready = false;
+  std::vector<u32> fp(n_frames);
+  size_t bytes = 0;
+  for (u32 f = 0; f < n_frames; ++f) {
+    cp_status st = check_view(h, &frames[f]);
+    if (st) return st;
+    const cp_cloud_view& v = frames[f];
+    if (v.point_step != frames[0].point_step || v.off_x != frames[0].off_x || v.off_y != frames[0].off_y ||
+        v.off_z != frames[0].off_z || v.off_intensity != frames[0].off_intensity) {
+      h->err = "all frames of a batch must share point_step and field offsets";
+      return CP_E_BADFIELD;
+    }
+    const u64 n = (u64)v.width * v.height;
+    if (n >= (1ull << 31)) {
+      h->err = "frame too large";
+      return CP_E_CAPACITY;
+    }
+    fp[f] = (u32)n;
+    bytes += (size_t)n * v.point_step;
+  }
+  if (bytes > h->d_in_bytes) {
+    h->err = "batch bytes exceed max_points * max_point_step of the handle";
+    return CP_E_CAPACITY;
+  }
+  if (!h->d_in) {  // staged input buffer: only handles that take host clouds pay for it
+    cp_status sa = dalloc(h, &h->d_in, h->d_in_bytes);
+    if (sa) return sa;
+  }
+  cp_status st = set_geometry(h, fp.data(), n_frames);
+  if (st) return st;
+  size_t off = 0;
+  int ring = 0;
+  for (u32 f = 0; f < n_frames; ++f) {
+    st = stage_view(h, &frames[f], off, &ring);
+    if (st) return st;
+    off += (size_t)fp[f] * frames[f].point_step;
+  }
+  h->layout = make_layout(frames[0].point_step, frames[0].off_x, frames[0].off_y, frames[0].off_z,
+                          frames[0].off_intensity);
+  h->in_ptr = h->d_in;
+  h->batch_ready = true;
+  h->ran = false;
+  return CP_OK;
+}
+
+cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_params* ground) {
+  if (!h) return CP_E_PARAM;
+  CK(cudaSetDevice(h->cfg.device));
+  return enqueue_pipeline(h, d, ground);
+}
+
+cp_status cp_sync(cp_handle* h) {
+  if (!h) return CP_E_PARAM;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if (h->ran) return device_errors(h);
+  return CP_OK;
+}
+
+cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* cluster_offsets, cp_cluster* out,
+                           uint64_t cap, uint64_t* n_total) {
+  if (!h) return CP_E_PARAM;
+  if (!h->ran) {
+    h->err = "cp_batch_results before cp_batch_run";
+    return CP_E_STATE;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  cp_status st = cp_sync(h);
+  if (st) return st;
+  const u32 F = h->hg.n_frames;
+  const u64 K = h->h_ctl->n_clusters;
+  if (n_total) *n_total = K;
+  u32* s = h->h_frame_u32;
+  if (cluster_offsets) {
+    CK(cudaMemcpyAsync(s, h->d_k_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(cluster_offsets, s, sizeof(u32) * (F + 1));
+  }
+  if (counters) {
+    std::vector<u32> c_off(F + 1), v_off(F + 1), ncomp(F), kc(F), gc(F);
+    std::vector<VoxelFrame> vf(F);
+    CK(cudaMemcpyAsync(c_off.data(), h->d_c_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(v_off.data(), h->d_v_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ncomp.data(), h->d_ncomp_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(kc.data(), h->d_kcount_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(gc.data(), h->d_gcount, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(vf.data(), h->d_vf, sizeof(VoxelFrame) * F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (u32 f = 0; f < F; ++f) {
+      cp_frame_counters& c = counters[f];
+      c.n_points = h->hg.frame_n[f];
+      c.n_ground_kept = h->counted_ground ? gc[f] : 0xFFFFFFFFu;  // only counted when the filler point matters
+      c.n_cropped = c_off[f + 1] - c_off[f];
+      c.n_voxels = v_off[f + 1] - v_off[f];
+      c.n_components = ncomp[f];
+      c.n_clusters = kc[f];
+      c.key_bits = vf[f].bits;
+      c.passthrough = vf[f].passthrough;
+    }
+  }
+  if (out) {
+    if (K > cap) {
+      h->err = "cluster output buffer too small";
+      return CP_E_CAPACITY;
+    }
+    if (K) {
+      CK(cudaMemcpyAsync(out, h->d_clusters, sizeof(cp_cluster) * K, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+  }
+  return CP_OK;
+}
+
+cp_status cp_detect_batch(cp_handle* h, const cp_cloud_view* frames, uint32_t n_frames, const cp_detect_params* d,
+                          const cp_ground_params* ground, cp_frame_counters* counters, uint32_t* cluster_offsets,
+                          cp_cluster* out, uint64_t cap, uint64_t* n_total) {
+  cp_status st = cp_batch_set_host_input(h, frames, n_frames);
+  if (st) return st;
+  st = cp_batch_run(h, d, ground);
+  if (st) return st;
+  return cp_batch_results(h, counters, cluster_offsets, out, cap, n_total);
+}
+
+cp_status cp_detect(cp_handle* h, const cp_cloud_view* in, const cp_detect_params* d, const cp_ground_params* ground,
+                    cp_cluster* out, uint32_t cap, uint32_t* n_clusters, cp_frame_counters* counters) {
+  if (!h) return CP_E_PARAM;
+  if (!n_clusters) {
+    h->err = "NULL n_clusters";
+    return CP_E_PARAM;
+  }
+  uint64_t total = 0;
+  cp_status st = cp_detect_batch(h, in, 1, d, ground, counters, nullptr, out, cap, &total);
+  *n_clusters = (uint32_t)total;
+  return st;
+}
+
+cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_ground_params* g, void* out_xyzi32,
+                           uint32_t* n_kept, float* low17) {
+  if (!h) return CP_E_PARAM;
+  if (!g || !out_xyzi32) {
+    h->err = "NULL ground params or output";
+    return CP_E_PARAM;
+  }
+  cp_status st = cp_batch_set_host_input(h, in, 1);
+  if (st) return st;
+  const u32 n = h->hg.frame_n[0];
+  if (!h->d_out32) {
+    cudaError_t e = cudaMalloc(&h->d_out32, (size_t)h->cfg.max_points * 32);
+    if (e != cudaSuccess) {
+      h->err = "cudaMalloc of the 32-byte output cloud failed";
+      return CP_E_NOMEM;
+    }
+  }
+  const Geom geo = device_geom(h);
+  h->launches = 0;
+  launch_init(h, g->default_lowest_point);
+  const u32 sgrid = grid_for((u64)geo.n_tiles * kStreamThreads, kStreamThreads, h->sms, 8);
+  launch_sector_min(h, geo, sgrid);
+  CropK crop;
+  memset(&crop, 0, sizeof(crop));
+  GroundK gk;
+  gk.do_ground = 1;
+  gk.want_count = 0;
+  gk.pad_survives = 0;
+  CompactOut co;
+  memset(&co, 0, sizeof(co));
+  co.cap = n;
+  co.c_off = h->d_c_off;
+  co.bbox_key = h->d_bbox;
+  co.gcount = h->d_gcount;
+  co.desc = h->d_desc_a;
+  co.ctl = h->d_ctl;
+  co.out32 = h->d_out32;
+  launch_compact<true>(h, geo, crop, gk, co, sgrid);
+  pad_zero_points_kernel<<<grid_for(n, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_out32, h->d_ctl, n);
+  h->launches += 3;
+  CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_xyzi32, h->d_out32, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+  if (low17) CK(cudaMemcpyAsync(h->h_frame_u32, h->d_low_key, sizeof(u32) * kNSect, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if (n_kept) *n_kept = h->h_ctl->n_surv;
+  if (low17)
+    for (int s = 0; s < kNSect; ++s) low17[s] = ord2f(h->h_frame_u32[s]);
+  h->ran = false;
+  return CP_OK;
+}
+
+cp_status cp_last_run_ms(cp_handle* h, float* ms) {
+  if (!h || !ms) return CP_E_PARAM;
+  if (!h->ran) {
+    h->err = "no batch has run";
+    return CP_E_STATE;
+  }
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return CP_OK;
+}
+
+uint32_t cp_last_launch_count(const cp_handle* h) { return h ? h->launches : 0; }
+void* cp_stream(cp_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+cp_status cp_debug_tap(cp_handle* h, cp_tap which, void* out, uint64_t cap_bytes, uint64_t* count) {
+  if (!h || !out || !count) return CP_E_PARAM;
+  if (!h->ran) {
+    h->err = "cp_debug_tap before a batch ran";
+    return CP_E_STATE;
+  }
+  cp_status st = cp_sync(h);
+  if (st) return st;
+  const u32 F = h->hg.n_frames;
+  const Ctl& c = *h->h_ctl;
+  const void* src = nullptr;
+  u64 n = 0, esz = 4;
+  bool need_taps = false;
+  switch (which) {
+    case CP_TAP_SECTOR_LOW: src = h->d_low_key; n = (u64)F * kSectStride; break;
+    case CP_TAP_CROP_INDEX: src = h->d_src; n = c.n_surv; break;
+    case CP_TAP_CROP_POINTS: src = h->d_pts; n = c.n_surv; esz = 16; break;
+    case CP_TAP_CROP_OFFSETS: src = h->d_c_off; n = F + 1; break;
+    case CP_TAP_VOXEL_KEYS: src = h->d_tap_keys; n = c.n_surv; need_taps = true; break;
+    case CP_TAP_VOXEL_ORDER: src = h->d_tap_order; n = c.n_surv; need_taps = true; break;
+    case CP_TAP_VOXEL_CLOUD: src = h->d_vox; n = c.n_vox; esz = 16; break;
+    case CP_TAP_VOXEL_OFFSETS: src = h->d_v_off; n = F + 1; break;
+    case CP_TAP_LABELS: src = h->d_tap_labels; n = c.n_vox; need_taps = true; break;
+    default: h->err = "unknown tap"; return CP_E_PARAM;
+  }
+  if (need_taps && !h->taps) {
+    h->err = "this tap needs CONESGPU_TAPS=1 in the environment when the handle is created";
+    return CP_E_STATE;
+  }
+  if (which == CP_TAP_SECTOR_LOW) {
+    // decode the ordered-int minima into floats, 17 per frame
+    if ((u64)F * kNSect * 4 > cap_bytes) {
+      h->err = "tap buffer too small";
+      return CP_E_CAPACITY;
+    }
+    std::vector<u32> tmp(n);
+    CK(cudaMemcpy(tmp.data(), src, n * 4, cudaMemcpyDeviceToHost));
+    float* o = static_cast<float*>(out);
+    for (u32 f = 0; f < F; ++f)
+      for (int s = 0; s < kNSect; ++s) o[f * kNSect + s] = ord2f(tmp[f * kSectStride + s]);
+    *count = (u64)F * kNSect;
+    return CP_OK;
+  }
+  if (n * esz > cap_bytes) {
+    h->err = "tap buffer too small";
+    return CP_E_CAPACITY;
+  }
+  if (n) CK(cudaMemcpy(out, src, n * esz, cudaMemcpyDeviceToHost));
+  *count = n;
+  return CP_OK;
+}
+
+cp_status cp_debug_sort(cp_handle* h, uint64_t* keys, uint32_t* vals, uint32_t n, uint32_t bits) {
+  if (!h || !keys || !vals) return CP_E_PARAM;
+  if (n > h->cap_v || bits > 64) {
+    h->err = "cp_debug_sort: n exceeds max_voxels or bits > 64";
+    return CP_E_CAPACITY;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->d_okeys_a, keys, sizeof(u64) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_ovals_a, vals, sizeof(u32) * n, cudaMemcpyHostToDevice, h->stream));
+  Ctl z;
+  memset(&z, 0, sizeof(z));
+  z.n_comp = n;
+  z.osort_bits = bits;
+  CK(cudaMemcpyAsync(h->d_ctl, &z, sizeof(z), cudaMemcpyHostToDevice, h->stream));
+  SortArgs sa = sort_args(h, true, &h->d_ctl->n_comp, &h->d_ctl->osort_bits);
+  radix_sort_enqueue(h->stream, sa, bits, n, h->sms);
+  const bool inb = sorted_in_b(bits);
+  CK(cudaMemcpyAsync(keys, inb ? h->d_okeys_b : h->d_okeys_a, sizeof(u64) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(vals, inb ? h->d_ovals_b : h->d_ovals_a, sizeof(u32) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return CP_OK;
+}
+
+}  // extern "C"

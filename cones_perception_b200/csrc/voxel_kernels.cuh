@@ -1,0 +1,249 @@
+// voxel_kernels.cuh — pcl::VoxelGrid<PointXYZI>::applyFilter restated for batches of frames
+// (reference call site: downsample(), src/cone_detection.cpp:240-249; semantics: SURVEY.md
+// Appendix A.4).  Stages: per-frame grid setup from the survivors' bounding box -> voxel key
+// per survivor -> (radix sort, radix_sort.cuh) -> segment heads -> sequential fp32 mean per
+// voxel in ascending point order.
+#pragma once
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+namespace cp {
+
+struct VoxelFrame {
+  i32 min_b[3];
+  u32 mul1, mul2;    // divb_mul_[1], divb_mul_[2]
+  u32 passthrough;   // PCL's "leaf size too small" guard: output = input
+  u32 bits;          // ceil(log2(cells))
+  u32 pad;
+};
+
+struct VoxelK {
+  float inv[3];      // inverse_leaf_size_ = 1.0f / (float)leaf
+  u32 frame_bits;    // ceil(log2(n_frames))
+};
+
+// one thread per frame
+__global__ void voxel_setup_kernel(u32 n_frames, VoxelK k, const u32* __restrict__ bbox_key,
+                                   const u32* __restrict__ c_off, VoxelFrame* __restrict__ vf, Ctl* ctl) {
+  const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 bits = 0;
+  if (f < n_frames) {
+    VoxelFrame v;
+    v.pad = 0;
+    const u32 cnt = c_off[f + 1] - c_off[f];
+    if (cnt == 0) {
+      v.min_b[0] = v.min_b[1] = v.min_b[2] = 0;
+      v.mul1 = v.mul2 = 0;
+      v.passthrough = 0;
+      v.bits = 0;
+    } else {
+      float mn[3], mx[3];
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = ord2f(bbox_key[f * 8 + a]);
+        mx[a] = ord2f(bbox_key[f * 8 + 4 + a]);
+      }
+      long long d[3];
+      i32 div_b[3];
+      for (int a = 0; a < 3; ++a) {
+        d[a] = (long long)__fmul_rn(__fsub_rn(mx[a], mn[a]), k.inv[a]) + 1;
+        v.min_b[a] = (i32)floorf(__fmul_rn(mn[a], k.inv[a]));
+        const i32 max_b = (i32)floorf(__fmul_rn(mx[a], k.inv[a]));
+        div_b[a] = max_b - v.min_b[a] + 1;
+      }
+      if (d[0] * d[1] * d[2] > 2147483647ll) {
+        v.passthrough = 1;
+        v.mul1 = v.mul2 = 0;
+        v.bits = ceil_log2_u64(cnt);
+      } else {
+        v.passthrough = 0;
+        v.mul1 = (u32)div_b[0];
+        v.mul2 = (u32)div_b[0] * (u32)div_b[1];
+        const u64 cells = (u64)(u32)div_b[0] * (u32)div_b[1] * (u32)div_b[2];
+        v.bits = cells >= (1ull << 31) ? 32u : ceil_log2_u64(cells);
+      }
+    }
+    vf[f] = v;
+    bits = v.bits;
+  }
+  bits = __reduce_max_sync(kFull, bits);
+  if (lane_id() == 0 && bits) atomicMax(&ctl->voxel_key_bits, bits);
+}
+
+// after voxel_setup: total sort width = key bits + frame bits
+__global__ void voxel_bits_kernel(Ctl* ctl, u32 frame_bits) {
+  ctl->vsort_bits = ctl->voxel_key_bits + frame_bits;
+}
+
+// one thread per survivor: PCL idx (uint32) prefixed by the frame id
+__global__ void voxel_key_kernel(const Ctl* __restrict__ ctl, VoxelK k, const float4* __restrict__ pts,
+                                 const u32* __restrict__ frame, const u32* __restrict__ c_off,
+                                 const VoxelFrame* __restrict__ vf, u64* __restrict__ keys,
+                                 u32* __restrict__ vals) {
+  const u32 n = ctl->n_surv;
+  const u32 kb = ctl->voxel_key_bits;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const u32 f = frame[i];
+    const VoxelFrame v = vf[f];
+    u32 idx;
+    if (v.passthrough) {
+      idx = i - c_off[f];
+    } else {
+      const float4 p = pts[i];
+      const i32 i0 = (i32)__fsub_rn(floorf(__fmul_rn(p.x, k.inv[0])), (float)v.min_b[0]);
+      const i32 i1 = (i32)__fsub_rn(floorf(__fmul_rn(p.y, k.inv[1])), (float)v.min_b[1]);
+      const i32 i2 = (i32)__fsub_rn(floorf(__fmul_rn(p.z, k.inv[2])), (float)v.min_b[2]);
+      idx = (u32)i0 + (u32)i1 * v.mul1 + (u32)i2 * v.mul2;
+    }
+    keys[i] = ((u64)f << kb) | (u64)idx;
+    vals[i] = i;
+  }
+}
+
+// ---- generic "segment heads" pass over a sorted key array ---------------------------------
+// head[i] = (i == 0 || key[i] != key[i-1]); writes excl[i] = number of heads before i
+// (optional), starts[seg] = i for every head, *d_total = number of segments.
+constexpr int kHeadThreads = 256;
+constexpr int kHeadItems = 4;
+constexpr int kHeadTile = kHeadThreads * kHeadItems;
+
+struct HeadArgs {
+  const u64* keys_a;
+  const u64* keys_b;
+  const u32* d_bits;   // selects A or B (result parity of the preceding sort)
+  const u32* d_n;
+  u32* excl;           // may be NULL
+  u32* starts;
+  u32 starts_cap;
+  u32* d_total;
+  u64* desc;
+  u32* ticket;
+  u32* error;
+  u32 err_bit;
+};
+
+__global__ void __launch_bounds__(kHeadThreads) segment_heads_kernel(HeadArgs a) {
+  const u32 n = *a.d_n;
+  const u64* keys = sorted_in_b(*a.d_bits) ? a.keys_b : a.keys_a;
+  const u32 tiles = (n + kHeadTile - 1) / kHeadTile;
+  __shared__ u32 wsum[kHeadThreads / 32];
+  __shared__ u32 s_tile, s_excl;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    if (tile >= tiles) break;
+    const u32 i0 = tile * kHeadTile + threadIdx.x * kHeadItems;
+    u64 prev = (i0 > 0 && i0 <= n) ? keys[i0 - 1] : 0ull;
+    u32 flags = 0, cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kHeadItems; ++j) {
+      const u32 i = i0 + j;
+      if (i < n) {
+        const u64 kcur = keys[i];
+        if (i == 0 || kcur != prev) {
+          flags |= 1u << j;
+          ++cnt;
+        }
+        prev = kcur;
+      }
+    }
+    u32 inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    u32 woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kHeadThreads / 32; ++w) {
+      const u32 t = wsum[w];
+      if (w < warp) woff += t;
+      total += t;
+    }
+    if (warp == 0) {
+      const u32 e = lookback_exclusive(a.desc, tile, total);
+      if (lane == 0) s_excl = e;
+    }
+    __syncthreads();
+    u32 run = s_excl + woff + inc - cnt;
+    if (threadIdx.x == 0 && tile == tiles - 1) {
+      *a.d_total = min(s_excl + total, a.starts_cap);
+      if (s_excl + total > a.starts_cap) atomicOr(a.error, a.err_bit);
+    }
+#pragma unroll
+    for (int j = 0; j < kHeadItems; ++j) {
+      const u32 i = i0 + j;
+      if (i < n) {
+        if (a.excl) a.excl[i] = run;
+        if (flags & (1u << j)) {
+          if (run < a.starts_cap) a.starts[run] = i;
+          ++run;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// one thread per voxel: CentroidPoint<PointXYZI> = sequential fp32 sums in record order,
+// divided by the count (IEEE division)
+struct VoxelOut {
+  float4* vox;       // [V] x, y, z, intensity means
+  u32* vox_frame;    // [V]
+  u32* v_off;        // [F+1]
+};
+
+__global__ void voxel_mean_kernel(const Ctl* __restrict__ ctl, const u64* keys_a, const u64* keys_b,
+                                  const u32* vals_a, const u32* vals_b, const u32* __restrict__ starts,
+                                  const float4* __restrict__ pts, const u32* __restrict__ src,
+                                  const u32* __restrict__ frame_n, u32 uniform_n,
+                                  const u32* __restrict__ gcount, VoxelOut o) {
+  const u32 nv = ctl->n_vox, n = ctl->n_surv;
+  const bool inb = sorted_in_b(ctl->vsort_bits);
+  const u64* keys = inb ? keys_b : keys_a;
+  const u32* vals = inb ? vals_b : vals_a;
+  const u32 kb = ctl->voxel_key_bits;
+  for (u32 v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+    const u32 b = starts[v];
+    const u32 e = (v + 1 < nv) ? starts[v + 1] : n;
+    const u32 f = (u32)(keys[b] >> kb);
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    u32 cnt = e - b;
+    for (u32 r = b; r < e; ++r) {
+      const u32 pi = vals[r];
+      const float4 p = pts[pi];
+      sx = __fadd_rn(sx, p.x);
+      sy = __fadd_rn(sy, p.y);
+      sz = __fadd_rn(sz, p.z);
+      si = __fadd_rn(si, p.w);
+      if (src[pi] == 0xFFFFFFFFu) {
+        // the record standing for the ground node's zero padding: adding zeros leaves the
+        // sums unchanged, only the count grows by (N - G) - 1
+        const u32 nf = uniform_n ? uniform_n : frame_n[f];
+        cnt += (nf - gcount[f]) - 1u;
+      }
+    }
+    const float c = (float)cnt;
+    o.vox[v] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+    o.vox_frame[v] = f;
+  }
+}
+
+// v_off[f] = number of voxels in frames < f  (from the heads' exclusive counts)
+__global__ void voxel_offsets_kernel(const Ctl* __restrict__ ctl, u32 n_frames, const u32* __restrict__ c_off,
+                                     const u32* __restrict__ excl, u32* __restrict__ v_off) {
+  const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > n_frames) return;
+  const u32 n = ctl->n_surv, nv = ctl->n_vox;
+  if (f == n_frames) {
+    v_off[f] = nv;
+    return;
+  }
+  const u32 c = c_off[f];
+  v_off[f] = (c < n) ? excl[c] : nv;
+}
+
+}  // namespace cp

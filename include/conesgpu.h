@@ -1,0 +1,187 @@
+/*
+ * conesgpu.h — C ABI of libconesgpu.so, the B200 (sm_100a) implementation of the
+ * cones_perception point-cloud hot path.
+ *
+ * The reference (dmn-sjk/cones_perception) has no plugin/FFI interface; its seam is the
+ * body of two ROS subscriber callbacks.  Each entry point below names the reference
+ * lines it replaces (paths relative to the upstream repository):
+ *
+ *   cp_ground_remove   GroundRemover::cloud_handler body   src/ground_removal.cpp:54-79
+ *   cp_detect          ConeDetector::cloud_handler          src/cone_detection.cpp:151-167
+ *                      + the centroid mean loop             src/cone_detection.cpp:261-273
+ *                      (filter_points_position :189-204, downsample :240-249,
+ *                       euclidan_cluster :206-220, perception_handling::euclidan_dist
+ *                       src/perception_handling/utils.cpp:32-34)
+ *   cp_batch_*         the same path over many independent frames per launch
+ *                      (BASELINE.json configs 3-5)
+ *
+ * Plain C types only: no exceptions, no C++ or torch types cross this boundary.
+ * A handle is used by one thread at a time (the reference nodes are single-threaded
+ * ros::spin(), src/cone_detection.cpp:127, src/ground_removal.cpp:47).
+ * There is no CPU fallback: every compute entry point fails with CP_E_CUDA when no
+ * sm_100-class device is usable.
+ */
+#ifndef CONESGPU_H
+#define CONESGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cp_handle cp_handle;
+
+typedef enum cp_status {
+  CP_OK = 0,
+  CP_E_PARAM = 1,    /* NULL pointer, non-finite or out-of-range parameter           */
+  CP_E_BADFIELD = 2, /* x/y/z field missing, big-endian data, point_step too small   */
+  CP_E_CAPACITY = 3, /* more points / survivors / voxels / clusters than the handle or
+                        the caller's output buffer can hold — never silently truncated */
+  CP_E_CUDA = 4,     /* CUDA runtime error; see cp_last_error()                      */
+  CP_E_NOMEM = 5,
+  CP_E_STATE = 6     /* call order violated (e.g. results read before a batch ran)   */
+} cp_status;
+
+/* sensor_msgs/PointCloud2 with the fields already resolved to byte offsets, the way
+ * pcl::fromROSMsg resolves them (src/cone_detection.cpp:151,153; ground_removal.cpp:54).
+ * off_intensity < 0: field absent => intensity = 0 (ground_removal node behaviour).
+ * The cone_detection node fakes a missing field at offset 0 (src/cone_detection.cpp:
+ * 142-151): its shell passes off_intensity = 0 in that case. */
+typedef struct cp_cloud_view {
+  const uint8_t* data;
+  uint32_t width, height, point_step, row_step;
+  int32_t off_x, off_y, off_z, off_intensity;
+  uint8_t is_bigendian, is_dense;
+} cp_cloud_view;
+
+/* GroundRemover members, src/ground_removal.cpp:18-19 (names as in
+ * config/ground_removal_params.yaml).  num_of_sectors only sizes the reference's table;
+ * the sector angle is fixed at (360/16 = 22 deg) by the member initialiser (:20). */
+typedef struct cp_ground_params {
+  int32_t num_of_sectors;
+  float default_lowest_point;
+} cp_ground_params;
+
+/* ConeDetector members, src/cone_detection.cpp:22-43, same types and (typo'd) names as
+ * config/cones_detection_params_*.yaml. */
+typedef struct cp_detect_params {
+  double distance_treshold_max, distance_treshold_min, level_threshold, angle_threshold;
+  double voxel_filter_leaf_size_x, voxel_filter_leaf_size_y, voxel_filter_leaf_size_z;
+  int32_t min_cluster_size, max_cluster_size;
+  float cone_width, cone_height; /* CONE_WIDTH 0.228f, CONE_HEIGHT 0.325f (:22-23) */
+} cp_detect_params;
+
+/* one detected cone candidate before the host-side extension / temporal gate
+ * (src/cone_detection.cpp:276-340 stays in the node shell) */
+typedef struct cp_cluster {
+  float x, y;         /* mean of member voxel centroids (fp32, ascending voxel index) */
+  uint32_t size;      /* member voxels                                               */
+  uint32_t min_index; /* smallest member voxel index: canonical cluster label        */
+} cp_cluster;
+
+typedef struct cp_frame_counters {
+  uint32_t n_points;      /* N  input points                           */
+  uint32_t n_ground_kept; /* G  after ground removal (= N when off)    */
+  uint32_t n_cropped;     /* C  after the distance/angle/level crop    */
+  uint32_t n_voxels;      /* V  occupied voxels                        */
+  uint32_t n_components;  /*    connected components before the filter */
+  uint32_t n_clusters;    /* K  components with min <= size <= max     */
+  uint32_t key_bits;      /*    significant bits of this frame's voxel key */
+  uint32_t passthrough;   /*    1 if VoxelGrid's int32 overflow guard fired */
+} cp_frame_counters;
+
+typedef struct cp_config {
+  int32_t device;          /* CUDA device ordinal                                   */
+  uint64_t max_points;     /* total points per call/batch                           */
+  uint32_t max_frames;     /* frames per batch                                      */
+  uint32_t max_point_step; /* bytes per point of host clouds to stage (>= 16)       */
+  uint64_t max_survivors;  /* points after the crop, whole batch (0 = max_points)   */
+  uint64_t max_voxels;     /* voxels, whole batch (0 = max_survivors)               */
+} cp_config;
+
+const char* cp_strerror(cp_status s);
+const char* cp_last_error(const cp_handle* h); /* detail of the last failure, never NULL */
+uint32_t cp_abi_version(void);
+const char* cp_create_error(void);            /* detail of the last failed cp_create */
+
+cp_status cp_create(cp_handle** out, const cp_config* cfg);
+void cp_destroy(cp_handle* h);
+
+/* --- node-equivalent single-frame calls (host buffers in, host buffers out) -------- */
+
+/* src/ground_removal.cpp:54-79.  out_xyzi32 receives width*height points in the PCL
+ * PointXYZI layout toROSMsg emits (:86): x@0 y@4 z@8 1.0f@12 intensity@16, 32 B/point,
+ * survivors first (input order) then zero points.  low17 (optional) receives the 17
+ * per-sector minima. */
+cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_ground_params* g,
+                           void* out_xyzi32, uint32_t* n_kept, float* low17);
+
+/* src/cone_detection.cpp:151-167 + :261-273.  ground may be NULL (ground_removal:=false)
+ * or non-NULL to fuse the ground_removal node in front (ground_removal:=true).
+ * Clusters are returned in canonical order: size descending, then min_index ascending. */
+cp_status cp_detect(cp_handle* h, const cp_cloud_view* in, const cp_detect_params* d,
+                    const cp_ground_params* ground, cp_cluster* out, uint32_t cap,
+                    uint32_t* n_clusters, cp_frame_counters* counters);
+
+/* --- batches of independent frames ------------------------------------------------- */
+
+/* Describe a batch whose points are already in device memory (HBM-resident input).
+ * d_points: n_frames frames back to back, frame f holding frame_points[f] points of
+ * point_step bytes each with the given field offsets; the pointer must stay valid until
+ * the batch has run. */
+cp_status cp_batch_set_device_input(cp_handle* h, const void* d_points, uint32_t n_frames,
+                                    const uint32_t* frame_points, uint32_t point_step,
+                                    int32_t off_x, int32_t off_y, int32_t off_z,
+                                    int32_t off_intensity);
+
+/* Stage a batch from host memory: pinned staging + chunked cudaMemcpyAsync overlapped
+ * with nothing yet (the copy is enqueued on the handle's stream). */
+cp_status cp_batch_set_host_input(cp_handle* h, const cp_cloud_view* frames, uint32_t n_frames);
+
+/* Enqueue the whole pipeline for the current batch on the handle's stream (async). */
+cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_params* ground);
+
+/* Wait for the stream; surfaces device-side capacity errors. */
+cp_status cp_sync(cp_handle* h);
+
+/* After cp_sync: per-frame counters (n_frames entries) and clusters.  cluster_offsets has
+ * n_frames+1 entries; frame f's clusters are out[cluster_offsets[f] .. cluster_offsets[f+1]). */
+cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* cluster_offsets,
+                           cp_cluster* out, uint64_t cap, uint64_t* n_total);
+
+/* One call = stage (H2D) + run + results (D2H) for host-resident frames. */
+cp_status cp_detect_batch(cp_handle* h, const cp_cloud_view* frames, uint32_t n_frames,
+                          const cp_detect_params* d, const cp_ground_params* ground,
+                          cp_frame_counters* counters, uint32_t* cluster_offsets, cp_cluster* out,
+                          uint64_t cap, uint64_t* n_total);
+
+/* Device time of the last cp_batch_run (CUDA events on the handle's stream), ms. */
+cp_status cp_last_run_ms(cp_handle* h, float* ms);
+/* Kernel launches enqueued by the last cp_batch_run / cp_detect / cp_ground_remove. */
+uint32_t cp_last_launch_count(const cp_handle* h);
+/* The handle's stream as a cudaStream_t, for callers that time with their own events. */
+void* cp_stream(cp_handle* h);
+
+/* --- stage taps for parity tests (valid after cp_sync, whole batch, frame-major) ----
+ * Every tap copies device state of the last run to host memory.  count = entries written. */
+typedef enum cp_tap {
+  CP_TAP_SECTOR_LOW = 0,   /* float   [n_frames*17]  per-sector minima                    */
+  CP_TAP_CROP_INDEX = 1,   /* uint32  [C_total]  frame-local input index of each survivor */
+  CP_TAP_CROP_POINTS = 2,  /* float4  [C_total]  surviving points x,y,z,intensity         */
+  CP_TAP_CROP_OFFSETS = 3, /* uint32  [n_frames+1]                                        */
+  CP_TAP_VOXEL_KEYS = 4,   /* uint32  [C_total]  sorted PCL voxel idx, with multiplicity  */
+  CP_TAP_VOXEL_ORDER = 5,  /* uint32  [C_total]  survivor position of each sorted record  */
+  CP_TAP_VOXEL_CLOUD = 6,  /* float4  [V_total]  voxel centroids x,y,z,intensity          */
+  CP_TAP_VOXEL_OFFSETS = 7,/* uint32  [n_frames+1]                                        */
+  CP_TAP_LABELS = 8        /* int32   [V_total]  frame-local min voxel index of component */
+} cp_tap;
+cp_status cp_debug_tap(cp_handle* h, cp_tap which, void* out, uint64_t cap_bytes, uint64_t* count);
+
+/* Stand-alone exercise of the radix sort used inside the pipeline (tests only):
+ * sorts n (key, value) pairs on the device by the low `bits` bits of the key, stably. */
+cp_status cp_debug_sort(cp_handle* h, uint64_t* keys, uint32_t* vals, uint32_t n, uint32_t bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

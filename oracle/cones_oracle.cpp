@@ -1,0 +1,651 @@
+// cones_oracle.cpp — CPU ORACLE. TEST INFRASTRUCTURE ONLY (see cones_oracle.h).
+//
+// PARITY UNPINNED: no golden vectors exist in the reference; PCL/FLANN are absent.
+// Every function cites the reference file:line (relative to the upstream repo) and
+// the SURVEY.md appendix paragraph it restates.  Nothing here is copied from the
+// reference or from PCL; the semantics are re-derived from the call sites.
+//
+// Two modes:
+//   ORC_CANONICAL    — deterministic: stable voxel sort (ascending point index inside a
+//                      voxel), cluster order = size desc, then min index asc.  This is
+//                      the bit-exact target of the CUDA path.
+//   ORC_PCL_FAITHFUL — PCL's cost profile and container algorithms: unstable std::sort
+//                      of (idx, index) records, kd-tree (leaf 15) built twice, sorted
+//                      radius search per voxel, BFS flood fill, std::sort on reverse
+//                      iterators for the final size ordering.  Used as the CPU baseline
+//                      and to show canonical differs from PCL order only within 1e-5 m.
+#include "cones_oracle.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+using clk = std::chrono::steady_clock;
+inline double secs(clk::time_point a, clk::time_point b) {
+  return std::chrono::duration<double>(b - a).count();
+}
+
+// "atan2f" as defined by SURVEY A.2: glibc's float atan2f is not correctly rounded and
+// differs between glibc versions, so the oracle pins the angle to the double-precision
+// result rounded once to float.
+inline float oracle_atan2f(float y, float x) {
+  return static_cast<float>(std::atan2(static_cast<double>(y), static_cast<double>(x)));
+}
+
+// src/ground_removal.cpp:20 — (360 / 16) is integer division = 22, then * M_PI / 180 in
+// double, stored to float.  The initialiser runs with the default num_of_sectors (Q3).
+inline float sector_angle_rad() {
+  const int num_of_sectors_default = 16;
+  return static_cast<float>((360 / num_of_sectors_default) * M_PI / 180);
+}
+
+inline bool finite3(const orc_point& p) {
+  return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z);
+}
+
+// src/ground_removal.cpp:61-64 / :72-74
+inline int sector_of(float x, float y) {
+  float atan_angle = oracle_atan2f(y, x);
+  float angle = (atan_angle < 0) ? static_cast<float>(static_cast<double>(atan_angle) + 2 * M_PI)
+                                 : atan_angle;
+  return static_cast<int>(std::floor(angle / sector_angle_rad()));
+}
+
+// src/perception_handling/utils.cpp:32-34 with (x2,y2,z2) = 0: float differences, squares
+// and sum in double (pow(float,int) promotes), sqrt in double, returned as float.
+inline float euclidan_dist0(float x, float y, float z) {
+  double s = static_cast<double>(x) * static_cast<double>(x) +
+             static_cast<double>(y) * static_cast<double>(y);
+  s = s + static_cast<double>(z) * static_cast<double>(z);
+  return static_cast<float>(std::sqrt(s));
+}
+
+inline bool crop_drop(const orc_point& p, const orc_detect_params& d) {
+  if (!finite3(p)) return true;  // defined behaviour for the reference's UB
+  // src/cone_detection.cpp:195-201, same order
+  if (static_cast<double>(p.z) < d.level_threshold) return true;
+  if (static_cast<double>(euclidan_dist0(p.x, p.y, p.z)) > d.distance_treshold_max) return true;
+  if (static_cast<double>(euclidan_dist0(p.x, p.y, p.z)) < d.distance_treshold_min) return true;
+  double a = static_cast<double>(oracle_atan2f(p.y, p.x));
+  if (-d.angle_threshold * M_PI / 180 >= a) return true;
+  if (a >= d.angle_threshold * M_PI / 180) return true;
+  return false;
+}
+
+// ---------------------------------------------------------------- clustering helpers
+struct Tol {
+  float tol_f;  // static_cast<float>(cluster_tolerance_)  (PCL extract)
+  float r2;     // (float)(radius*radius) in double          (PCL KdTreeFLANN::radiusSearch)
+};
+inline Tol tolerance(const orc_detect_params& d) {
+  // src/cone_detection.cpp:212 — pow(float,int) promotes to double
+  double tol = std::sqrt(std::pow(static_cast<double>(d.cone_height), 2) +
+                         std::pow(static_cast<double>(d.cone_width), 2));
+  Tol t;
+  t.tol_f = static_cast<float>(tol);
+  t.r2 = static_cast<float>(static_cast<double>(t.tol_f) * static_cast<double>(t.tol_f));
+  return t;
+}
+
+// FLANN L2_Simple<float>: diff = a - b; result += diff*diff, x then y then z, fp32,
+// no FMA (the Makefile builds with -ffp-contract=off and without -march flags).
+inline float l2_simple(const orc_point& a, const orc_point& b) {
+  const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+  float r = dx * dx;
+  r += dy * dy;
+  r += dz * dz;
+  return r;
+}
+
+struct CellKey {
+  int32_t x, y, z;
+  bool operator==(const CellKey& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct CellHash {
+  size_t operator()(const CellKey& k) const {
+    uint64_t h = static_cast<uint32_t>(k.x) * 0x9E3779B185EBCA87ull;
+    h ^= static_cast<uint32_t>(k.y) * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= static_cast<uint32_t>(k.z) * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    return static_cast<size_t>(h);
+  }
+};
+
+// canonical labelling: flood fill over a uniform grid of edge > tolerance, seeds in
+// ascending index order, so the first index of every component is its minimum.
+void label_grid(const orc_point* vox, uint32_t n, float r2, float tol_f, int32_t* labels) {
+  const double h = static_cast<double>(tol_f) * 1.001 + 1e-9;
+  std::unordered_map<CellKey, std::vector<uint32_t>, CellHash> grid;
+  grid.reserve(n);
+  auto cell = [&](const orc_point& p) {
+    return CellKey{static_cast<int32_t>(std::floor(p.x / h)), static_cast<int32_t>(std::floor(p.y / h)),
+                   static_cast<int32_t>(std::floor(p.z / h))};
+  };
+  for (uint32_t i = 0; i < n; ++i) grid[cell(vox[i])].push_back(i);
+  std::fill(labels, labels + n, -1);
+  std::vector<uint32_t> queue;
+  for (uint32_t s = 0; s < n; ++s) {
+    if (labels[s] >= 0) continue;
+    queue.clear();
+    queue.push_back(s);
+    labels[s] = static_cast<int32_t>(s);
+    for (size_t q = 0; q < queue.size(); ++q) {
+      const uint32_t i = queue[q];
+      const CellKey c = cell(vox[i]);
+      for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            auto it = grid.find(CellKey{c.x + dx, c.y + dy, c.z + dz});
+            if (it == grid.end()) continue;
+            for (uint32_t j : it->second) {
+              if (labels[j] >= 0) continue;
+              if (l2_simple(vox[i], vox[j]) < r2) {  // strict <  (FLANN RadiusResultSet)
+                labels[j] = static_cast<int32_t>(s);
+                queue.push_back(j);
+              }
+            }
+          }
+    }
+  }
+}
+
+// ---- a small kd-tree with FLANN KDTreeSingleIndex's shape (leaf size 15, reordered
+// points, exact radius search, results sorted by distance).  Only used in faithful mode.
+struct KdTree {
+  struct Node {
+    int32_t left = -1, right = -1;  // children; leaf when left < 0
+    uint32_t begin = 0, end = 0;    // range in idx
+    int dim = 0;
+    float split_lo = 0, split_hi = 0;
+  };
+  std::vector<Node> nodes;
+  std::vector<uint32_t> idx;
+  std::vector<float> pts;  // reordered xyz
+  const orc_point* src = nullptr;
+
+  void build(const orc_point* p, uint32_t n) {
+    src = p;
+    idx.resize(n);
+    std::iota(idx.begin(), idx.end(), 0u);
+    nodes.clear();
+    nodes.reserve(n / 4 + 4);
+    if (n) split(0, n);
+    pts.resize(3 * static_cast<size_t>(n));
+    for (uint32_t r = 0; r < n; ++r) {
+      pts[3 * r] = p[idx[r]].x;
+      pts[3 * r + 1] = p[idx[r]].y;
+      pts[3 * r + 2] = p[idx[r]].z;
+    }
+  }
+  float coord(uint32_t i, int d) const { return d == 0 ? src[i].x : (d == 1 ? src[i].y : src[i].z); }
+  int32_t split(uint32_t b, uint32_t e) {
+    const int32_t me = static_cast<int32_t>(nodes.size());
+    nodes.emplace_back();
+    nodes[me].begin = b;
+    nodes[me].end = e;
+    if (e - b <= 15) return me;
+    float lo[3], hi[3];
+    for (int d = 0; d < 3; ++d) lo[d] = std::numeric_limits<float>::max(), hi[d] = -lo[d];
+    for (uint32_t r = b; r < e; ++r)
+      for (int d = 0; d < 3; ++d) {
+        float c = coord(idx[r], d);
+        lo[d] = std::min(lo[d], c);
+        hi[d] = std::max(hi[d], c);
+      }
+    int dim = 0;
+    for (int d = 1; d < 3; ++d)
+      if (hi[d] - lo[d] > hi[dim] - lo[dim]) dim = d;
+    if (!(hi[dim] > lo[dim])) return me;  // all identical: keep as a (large) leaf
+    const float mid = 0.5f * (lo[dim] + hi[dim]);
+    auto it = std::partition(idx.begin() + b, idx.begin() + e,
+                             [&](uint32_t i) { return coord(i, dim) < mid; });
+    uint32_t m = static_cast<uint32_t>(it - idx.begin());
+    if (m == b || m == e) {  // degenerate: fall back to the median
+      m = b + (e - b) / 2;
+      std::nth_element(idx.begin() + b, idx.begin() + m, idx.begin() + e,
+                       [&](uint32_t a, uint32_t c) { return coord(a, dim) < coord(c, dim); });
+    }
+    float left_hi = -std::numeric_limits<float>::max(), right_lo = std::numeric_limits<float>::max();
+    for (uint32_t r = b; r < m; ++r) left_hi = std::max(left_hi, coord(idx[r], dim));
+    for (uint32_t r = m; r < e; ++r) right_lo = std::min(right_lo, coord(idx[r], dim));
+    nodes[me].dim = dim;
+    nodes[me].split_lo = left_hi;
+    nodes[me].split_hi = right_lo;
+    int32_t l = split(b, m);
+    int32_t r = split(m, e);
+    nodes[me].left = l;
+    nodes[me].right = r;
+    return me;
+  }
+  // exact radius search; pruning is done in double with a small slack so it can never
+  // reject a point the brute-force relation accepts.
+  void radius(const orc_point& q, float r2, std::vector<std::pair<float, uint32_t>>& out) const {
+    out.clear();
+    if (nodes.empty()) return;
+    const double rr = std::sqrt(static_cast<double>(r2)) * (1.0 + 1e-6) + 1e-12;
+    int32_t stack[128];
+    int sp = 0;
+    stack[sp++] = 0;
+    const float qc[3] = {q.x, q.y, q.z};
+    while (sp) {
+      const Node& nd = nodes[stack[--sp]];
+      if (nd.left < 0) {
+        for (uint32_t r = nd.begin; r < nd.end; ++r) {
+          orc_point b;
+          b.x = pts[3 * r];
+          b.y = pts[3 * r + 1];
+          b.z = pts[3 * r + 2];
+          float dist = l2_simple(q, b);
+          if (dist < r2) out.emplace_back(dist, idx[r]);
+        }
+        continue;
+      }
+      const double c = qc[nd.dim];
+      if (c - rr <= nd.split_lo) stack[sp++] = nd.left;
+      if (c + rr >= nd.split_hi) stack[sp++] = nd.right;
+    }
+    std::sort(out.begin(), out.end());  // pcl::search::KdTree default sorted_results_ = true
+  }
+};
+
+struct Cluster {
+  std::vector<int> indices;
+};
+
+// pcl::extractEuclideanClusters (indices overload) + EuclideanClusterExtraction::extract
+// restated: BFS flood fill with a `processed` vector, radius search per queue entry.
+void extract_faithful(const orc_point* vox, uint32_t n, const Tol& t, uint32_t min_sz, uint32_t max_sz,
+                      int32_t* labels, std::vector<Cluster>& clusters, uint32_t* n_components) {
+  KdTree tree_user;  // src/cone_detection.cpp:207-208 — the tree built by the node ...
+  tree_user.build(vox, n);
+  KdTree tree;       // ... is rebuilt inside extract() (tree_->setInputCloud(input_, indices_))
+  tree.build(vox, n);
+  std::vector<bool> processed(n, false);
+  std::vector<std::pair<float, uint32_t>> nn;
+  uint32_t comps = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (processed[i]) continue;
+    std::vector<int> seed_queue;
+    size_t sq = 0;
+    seed_queue.push_back(static_cast<int>(i));
+    processed[i] = true;
+    while (sq < seed_queue.size()) {
+      tree.radius(vox[seed_queue[sq]], t.r2, nn);
+      // PCL starts at result 1 when results are sorted (result 0 is the query itself,
+      // already processed); starting at 0 is equivalent and also safe with duplicates.
+      for (size_t j = 0; j < nn.size(); ++j) {
+        uint32_t k = nn[j].second;
+        if (processed[k]) continue;
+        seed_queue.push_back(static_cast<int>(k));
+        processed[k] = true;
+      }
+      ++sq;
+    }
+    ++comps;
+    for (int k : seed_queue) labels[k] = static_cast<int32_t>(i);
+    if (seed_queue.size() >= min_sz && seed_queue.size() <= max_sz) {
+      Cluster c;
+      c.indices = seed_queue;
+      std::sort(c.indices.begin(), c.indices.end());
+      c.indices.erase(std::unique(c.indices.begin(), c.indices.end()), c.indices.end());
+      clusters.push_back(std::move(c));
+    }
+  }
+  *n_components = comps;
+  // extract(): std::sort(clusters.rbegin(), clusters.rend(), comparePointClusters)
+  std::sort(clusters.rbegin(), clusters.rend(),
+            [](const Cluster& a, const Cluster& b) { return a.indices.size() < b.indices.size(); });
+}
+
+void extract_canonical(const orc_point* vox, uint32_t n, const Tol& t, uint32_t min_sz, uint32_t max_sz,
+                       int32_t* labels, std::vector<Cluster>& clusters, uint32_t* n_components) {
+  label_grid(vox, n, t.r2, t.tol_f, labels);
+  std::vector<uint32_t> size(n, 0);
+  for (uint32_t i = 0; i < n; ++i) size[labels[i]]++;
+  std::vector<int32_t> slot(n, -1);
+  uint32_t comps = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (labels[i] != static_cast<int32_t>(i)) continue;
+    ++comps;
+    if (size[i] >= min_sz && size[i] <= max_sz) {
+      slot[i] = static_cast<int32_t>(clusters.size());
+      clusters.emplace_back();
+      clusters.back().indices.reserve(size[i]);
+    }
+  }
+  for (uint32_t i = 0; i < n; ++i)
+    if (slot[labels[i]] >= 0) clusters[slot[labels[i]]].indices.push_back(static_cast<int>(i));
+  *n_components = comps;
+  // canonical order: size descending, ties by ascending minimum index (stable sort on
+  // a list that is already in ascending-min-index order)
+  std::stable_sort(clusters.begin(), clusters.end(),
+                   [](const Cluster& a, const Cluster& b) { return a.indices.size() > b.indices.size(); });
+}
+
+}  // namespace
+
+extern "C" {
+
+float orc_r2(const orc_detect_params* d) { return tolerance(*d).r2; }
+
+int orc_from_msg(const orc_view* v, orc_point* out) {
+  if (!v || v->off_x < 0 || v->off_y < 0 || v->off_z < 0 || v->is_bigendian) return 2;
+  const uint64_t n = static_cast<uint64_t>(v->width) * v->height;
+  for (uint32_t r = 0; r < v->height; ++r) {
+    const uint8_t* row = v->data + static_cast<size_t>(r) * v->row_step;
+    for (uint32_t c = 0; c < v->width; ++c) {
+      const uint8_t* src = row + static_cast<size_t>(c) * v->point_step;
+      orc_point p;
+      std::memset(&p, 0, sizeof(p));
+      p.pad = 1.0f;
+      std::memcpy(&p.x, src + v->off_x, 4);
+      std::memcpy(&p.y, src + v->off_y, 4);
+      std::memcpy(&p.z, src + v->off_z, 4);
+      if (v->off_intensity >= 0) std::memcpy(&p.intensity, src + v->off_intensity, 4);
+      out[static_cast<size_t>(r) * v->width + c] = p;
+    }
+  }
+  (void)n;
+  return 0;
+}
+
+int orc_sector_of(float x, float y) { return sector_of(x, y); }
+
+void orc_ground_minima(const orc_point* p, uint32_t n, float default_lowest, float* low) {
+  // src/ground_removal.cpp:58 — table initialised to default_lowest_point; Q2: 17 entries
+  for (int s = 0; s < ORC_NSECT; ++s) low[s] = default_lowest;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!finite3(p[i])) continue;
+    int s = sector_of(p[i].x, p[i].y);
+    if (low[s] > p[i].z) low[s] = p[i].z;  // :65-67
+  }
+}
+
+void orc_ground_mask(const orc_point* p, uint32_t n, const float* low, uint8_t* keep) {
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!finite3(p[i])) {
+      keep[i] = 0;
+      continue;
+    }
+    int s = sector_of(p[i].x, p[i].y);
+    // :75 — float + double literal => double compare
+    bool drop = static_cast<double>(p[i].z) < static_cast<double>(low[s]) + 0.1;
+    keep[i] = drop ? 0 : 1;
+  }
+}
+
+int orc_ground_node(const orc_view* v, const orc_ground_params* g, orc_point* out, uint32_t* n_kept,
+                    float* low_out, uint8_t* keep_out) {
+  const uint32_t n = v->width * v->height;
+  std::vector<orc_point> cloud(n);
+  int rc = orc_from_msg(v, cloud.data());
+  if (rc) return rc;
+  float low[ORC_NSECT];
+  orc_ground_minima(cloud.data(), n, g->default_lowest_point, low);
+  std::vector<uint8_t> keep(n);
+  orc_ground_mask(cloud.data(), n, low, keep.data());
+  uint32_t k = 0;
+  for (uint32_t i = 0; i < n; ++i)
+    if (keep[i]) out[k++] = cloud[i];
+  // :79 resize(cloud_size): value-initialised PointXYZI = (0,0,0,1) intensity 0
+  orc_point z;
+  std::memset(&z, 0, sizeof(z));
+  z.pad = 1.0f;
+  for (uint32_t i = k; i < n; ++i) out[i] = z;
+  if (n_kept) *n_kept = k;
+  if (low_out) std::memcpy(low_out, low, sizeof(low));
+  if (keep_out) std::memcpy(keep_out, keep.data(), n);
+  return 0;
+}
+
+void orc_crop_mask(const orc_point* p, uint32_t n, const orc_detect_params* d, uint8_t* keep) {
+  for (uint32_t i = 0; i < n; ++i) keep[i] = crop_drop(p[i], *d) ? 0 : 1;
+}
+
+int orc_voxel_grid(const orc_point* p, uint32_t n, const orc_detect_params* d, int mode,
+                   uint32_t* keys_sorted, uint32_t* order, orc_point* out_vox, uint32_t* n_vox,
+                   orc_counters* ctr) {
+  *n_vox = 0;
+  if (ctr) {
+    ctr->passthrough = 0;
+    ctr->key_bits = 0;
+    for (int k = 0; k < 3; ++k) ctr->min_b[k] = 0, ctr->div_b[k] = 0;
+  }
+  if (n == 0) return 0;  // defined: empty in, empty out
+  // VoxelGrid::setLeafSize(float,float,float): doubles narrowed at the call (:245)
+  const float leaf[3] = {static_cast<float>(d->voxel_filter_leaf_size_x),
+                         static_cast<float>(d->voxel_filter_leaf_size_y),
+                         static_cast<float>(d->voxel_filter_leaf_size_z)};
+  float inv[3];
+  for (int k = 0; k < 3; ++k) inv[k] = 1.0f / leaf[k];
+  // getMinMax3D over all points (is_dense path)
+  float mn[3] = {p[0].x, p[0].y, p[0].z}, mx[3] = {p[0].x, p[0].y, p[0].z};
+  for (uint32_t i = 1; i < n; ++i) {
+    const float c[3] = {p[i].x, p[i].y, p[i].z};
+    for (int k = 0; k < 3; ++k) {
+      mn[k] = std::min(mn[k], c[k]);
+      mx[k] = std::max(mx[k], c[k]);
+    }
+  }
+  int64_t dxyz[3];
+  for (int k = 0; k < 3; ++k) dxyz[k] = static_cast<int64_t>((mx[k] - mn[k]) * inv[k]) + 1;
+  if (dxyz[0] * dxyz[1] * dxyz[2] > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) {
+    // PCL warns and returns the input unchanged
+    for (uint32_t i = 0; i < n; ++i) {
+      out_vox[i] = p[i];
+      keys_sorted[i] = i;
+      order[i] = i;
+    }
+    *n_vox = n;
+    if (ctr) ctr->passthrough = 1;
+    return 0;
+  }
+  int32_t min_b[3], max_b[3], div_b[3];
+  for (int k = 0; k < 3; ++k) {
+    min_b[k] = static_cast<int32_t>(std::floor(mn[k] * inv[k]));
+    max_b[k] = static_cast<int32_t>(std::floor(mx[k] * inv[k]));
+    div_b[k] = max_b[k] - min_b[k] + 1;
+  }
+  const int32_t mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  struct Rec {
+    uint32_t idx, pt;
+  };
+  std::vector<Rec> recs(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    const float c[3] = {p[i].x, p[i].y, p[i].z};
+    int32_t ijk[3];
+    for (int k = 0; k < 3; ++k)
+      ijk[k] = static_cast<int32_t>(std::floor(c[k] * inv[k]) - static_cast<float>(min_b[k]));
+    int32_t idx = ijk[0] * mul[0] + ijk[1] * mul[1] + ijk[2] * mul[2];
+    recs[i].idx = static_cast<uint32_t>(idx);
+    recs[i].pt = i;
+  }
+  auto less_idx = [](const Rec& a, const Rec& b) { return a.idx < b.idx; };
+  if (mode == ORC_PCL_FAITHFUL)
+    std::sort(recs.begin(), recs.end(), less_idx);  // unstable, like PCL
+  else
+    std::stable_sort(recs.begin(), recs.end(), less_idx);
+  uint32_t v = 0;
+  for (uint32_t r = 0; r < n;) {
+    uint32_t e = r + 1;
+    while (e < n && recs[e].idx == recs[r].idx) ++e;
+    // CentroidPoint<PointXYZI>: AccumulatorXYZ (Vector3f sum, / n) + AccumulatorIntensity
+    float sx = 0, sy = 0, sz = 0, si = 0;
+    for (uint32_t k = r; k < e; ++k) {
+      const orc_point& q = p[recs[k].pt];
+      sx += q.x;
+      sy += q.y;
+      sz += q.z;
+      si += q.intensity;
+    }
+    const float cnt = static_cast<float>(e - r);
+    orc_point o;
+    std::memset(&o, 0, sizeof(o));
+    o.x = sx / cnt;
+    o.y = sy / cnt;
+    o.z = sz / cnt;
+    o.pad = 1.0f;
+    o.intensity = si / cnt;
+    out_vox[v++] = o;
+    r = e;
+  }
+  for (uint32_t r = 0; r < n; ++r) {
+    keys_sorted[r] = recs[r].idx;
+    order[r] = recs[r].pt;
+  }
+  *n_vox = v;
+  if (ctr) {
+    uint64_t cells = static_cast<uint64_t>(div_b[0]) * div_b[1] * div_b[2];
+    uint32_t bits = 0;
+    while ((1ull << bits) < cells) ++bits;
+    ctr->key_bits = bits;
+    for (int k = 0; k < 3; ++k) ctr->min_b[k] = min_b[k], ctr->div_b[k] = div_b[k];
+  }
+  return 0;
+}
+
+int orc_extract_clusters(const orc_point* vox, uint32_t n_vox, const orc_detect_params* d, int mode, int32_t* labels,
+                orc_cluster* clusters, uint32_t cap, uint32_t* n_clusters, uint32_t* n_components,
+                uint32_t* members) {
+  *n_clusters = 0;
+  if (n_components) *n_components = 0;
+  if (n_vox == 0) return 0;
+  const Tol t = tolerance(*d);
+  std::vector<Cluster> cl;
+  uint32_t comps = 0;
+  std::vector<int32_t> tmp;
+  if (!labels) {
+    tmp.resize(n_vox);
+    labels = tmp.data();
+  }
+  const uint32_t mn = d->min_cluster_size < 0 ? 0u : static_cast<uint32_t>(d->min_cluster_size);
+  const uint32_t mx = d->max_cluster_size < 0 ? 0u : static_cast<uint32_t>(d->max_cluster_size);
+  if (mode == ORC_PCL_FAITHFUL)
+    extract_faithful(vox, n_vox, t, mn, mx, labels, cl, &comps);
+  else
+    extract_canonical(vox, n_vox, t, mn, mx, labels, cl, &comps);
+  if (n_components) *n_components = comps;
+  if (cl.size() > cap) return 3;
+  size_t m = 0;
+  for (size_t k = 0; k < cl.size(); ++k) {
+    // src/cone_detection.cpp:261-273; Q1: x starts at 0 (the reference leaves it
+    // uninitialised for the first cluster)
+    float x = 0.0f, y = 0.0f;
+    int j = 0;
+    for (int idx : cl[k].indices) {
+      x += vox[idx].x;
+      y += vox[idx].y;
+      j++;
+      if (members) members[m++] = static_cast<uint32_t>(idx);
+    }
+    clusters[k].x = x / j;
+    clusters[k].y = y / j;
+    clusters[k].size = static_cast<uint32_t>(cl[k].indices.size());
+    clusters[k].min_index = static_cast<uint32_t>(cl[k].indices.front());
+  }
+  *n_clusters = static_cast<uint32_t>(cl.size());
+  return 0;
+}
+
+void orc_label_bruteforce(const orc_point* vox, uint32_t n, const orc_detect_params* d, int32_t* labels) {
+  const Tol t = tolerance(*d);
+  std::vector<int32_t> parent(n);
+  std::iota(parent.begin(), parent.end(), 0);
+  auto find = [&](int32_t a) {
+    while (parent[a] != a) a = parent[a] = parent[parent[a]];
+    return a;
+  };
+  for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t j = i + 1; j < n; ++j)
+      if (l2_simple(vox[i], vox[j]) < t.r2) {
+        int32_t a = find(static_cast<int32_t>(i)), b = find(static_cast<int32_t>(j));
+        if (a != b) parent[std::max(a, b)] = std::min(a, b);
+      }
+  for (uint32_t i = 0; i < n; ++i) labels[i] = find(static_cast<int32_t>(i));
+}
+
+void orc_extend(float* x, float* y, double extension_length) {
+  // src/cone_detection.cpp:276-278: p.z = 0; float vector_len; float divide, then
+  // float*double promotes: p.x = (float)((double)p.x + (double)(p.x / len) * ext)
+  float len = euclidan_dist0(*x, *y, 0.0f);
+  float nx = static_cast<float>(static_cast<double>(*x) + static_cast<double>(*x / len) * extension_length);
+  float ny = static_cast<float>(static_cast<double>(*y) + static_cast<double>(*y / len) * extension_length);
+  *x = nx;
+  *y = ny;
+}
+
+int orc_detect(const orc_view* v, const orc_detect_params* d, const orc_ground_params* g, int mode,
+               orc_cluster* clusters, uint32_t cap, uint32_t* n_clusters, orc_counters* ctr,
+               orc_timing* tm) {
+  orc_counters c;
+  std::memset(&c, 0, sizeof(c));
+  orc_timing t;
+  std::memset(&t, 0, sizeof(t));
+  const uint32_t n = v->width * v->height;
+  c.n_points = n;
+  auto t0 = clk::now();
+  std::vector<orc_point> cloud(n);
+  auto ta = clk::now();
+  if (g) {
+    // GroundRemover::cloud_handler: fromROSMsg, two passes, pad, (toROSMsg: memcpy-class)
+    uint32_t kept = 0;
+    int rc = orc_ground_node(v, g, cloud.data(), &kept, nullptr, nullptr);
+    if (rc) return rc;
+    c.n_ground_kept = kept;
+    auto tb = clk::now();
+    t.ground = secs(ta, tb);
+    // ConeDetector::cloud_handler then deserialises the padded 32-byte cloud again
+    std::vector<orc_point> again(n);
+    std::memcpy(again.data(), cloud.data(), sizeof(orc_point) * n);
+    cloud.swap(again);
+    t.from_msg = secs(tb, clk::now());
+  } else {
+    int rc = orc_from_msg(v, cloud.data());
+    if (rc) return rc;
+    c.n_ground_kept = n;
+    t.from_msg = secs(ta, clk::now());
+  }
+  // :158 copyPointCloud — full copy, only consumed by the colour path
+  auto tc0 = clk::now();
+  std::vector<orc_point> copy(cloud);
+  t.copy_cloud = secs(tc0, clk::now());
+  // :160 filter_points_position — erase(remove_if) in place
+  auto tc = clk::now();
+  {
+    auto e = std::remove_if(cloud.begin(), cloud.end(), [&](const orc_point& p) { return crop_drop(p, *d); });
+    cloud.erase(e, cloud.end());
+  }
+  c.n_cropped = static_cast<uint32_t>(cloud.size());
+  auto tv = clk::now();
+  t.crop = secs(tc, tv);
+  // :164 downsample
+  const uint32_t nc = c.n_cropped;
+  std::vector<uint32_t> keys(nc), order(nc);
+  std::vector<orc_point> vox(nc);
+  uint32_t nv = 0;
+  orc_voxel_grid(cloud.data(), nc, d, mode, keys.data(), order.data(), vox.data(), &nv, &c);
+  c.n_voxels = nv;
+  auto tk = clk::now();
+  t.voxel = secs(tv, tk);
+  // :167 euclidan_cluster (+ centroid loop :261-273, folded into orc_cluster's output)
+  uint32_t comps = 0;
+  int rc = orc_extract_clusters(vox.data(), nv, d, mode, nullptr, clusters, cap, n_clusters, &comps, nullptr);
+  c.n_components = comps;
+  c.n_clusters = *n_clusters;
+  auto te = clk::now();
+  t.cluster = secs(tk, te);
+  t.total = secs(t0, te);
+  if (ctr) *ctr = c;
+  if (tm) *tm = t;
+  volatile float sink = copy.empty() ? 0.0f : copy[copy.size() / 2].x;  // keep the copy alive
+  (void)sink;
+  return rc;
+}
+
+}  // extern "C"

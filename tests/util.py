@@ -1,0 +1,97 @@
+"""Shared helpers for the parity tests: run the oracle stage by stage and compare with the
+taps of libconesgpu."""
+from __future__ import annotations
+
+import numpy as np
+
+from cones_perception_b200 import api
+from cones_perception_b200.pointcloud2 import PointCloud2
+from oracle import oracle as O
+
+
+def oracle_stages(xyzi: np.ndarray, d, g=None, mode=O.CANONICAL):
+    """Reference pipeline on one frame, every intermediate kept (canonical mode by default)."""
+    pts = O.points32(xyzi)
+    n = len(pts)
+    out = {"n": n}
+    if g is not None:
+        low = O.ground_minima(pts, g.default_lowest_point)
+        gkeep = O.ground_mask(pts, low)
+        out["low"] = low
+        out["ground_keep"] = gkeep
+        # the ground node pads back to N with zero points (src/ground_removal.cpp:79)
+        kept = pts[gkeep.astype(bool)]
+        padded = np.zeros(n, dtype=O.POINT_DTYPE)
+        padded["pad"] = 1.0
+        padded[:len(kept)] = kept
+        src_index = np.concatenate([np.nonzero(gkeep)[0], np.full(n - len(kept), -1)])
+        stage_in = padded
+    else:
+        src_index = np.arange(n)
+        stage_in = pts
+    ckeep = O.crop_mask(stage_in, d).astype(bool)
+    cropped = stage_in[ckeep]
+    out["crop_index"] = src_index[ckeep]          # original input index (-1 for filler zeros)
+    out["cropped"] = cropped
+    keys, order, vox, ctr = O.voxel_grid(cropped, d, mode)
+    out.update(keys=keys, order=order, vox=vox, ctr=ctr)
+    labels, clusters, comps, members = O.extract_clusters(vox, d, mode)
+    out.update(labels=labels, clusters=clusters, n_components=comps, members=members)
+    return out
+
+
+def vox_xyzi(vox: np.ndarray) -> np.ndarray:
+    return np.stack([vox["x"], vox["y"], vox["z"], vox["intensity"]], 1)
+
+
+def bits(a: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_frame_parity(gpu: "api.ConesGpu", f: int, ora: dict, offs: dict, taps: dict, ctr, k_off, clusters):
+    """Bit-exact comparison of frame f of a batch run against its oracle stages."""
+    c0, c1 = offs["c_off"][f], offs["c_off"][f + 1]
+    v0, v1 = offs["v_off"][f], offs["v_off"][f + 1]
+    exp_idx = ora["crop_index"]
+    got_idx = taps["crop_index"][c0:c1].astype(np.int64)
+    got_idx[got_idx == 0xFFFFFFFF] = -1
+    # filler zeros: the GPU keeps ONE record with multiplicity; the oracle materialises them
+    n_fill = int((exp_idx < 0).sum())
+    exp_real = exp_idx[exp_idx >= 0]
+    got_real = got_idx[got_idx >= 0]
+    assert np.array_equal(got_real, exp_real), f"frame {f}: crop keep-mask differs"
+    assert (got_idx < 0).sum() == (1 if n_fill else 0)
+    assert ctr["n_cropped"][f] == len(got_idx)
+    if n_fill == 0:
+        assert np.array_equal(taps["voxel_keys"][c0:c1], ora["keys"]), f"frame {f}: voxel keys differ"
+        assert np.array_equal(taps["voxel_order"][c0:c1] - c0, ora["order"]), f"frame {f}: voxel order differs"
+    else:
+        assert np.array_equal(np.unique(taps["voxel_keys"][c0:c1]), np.unique(ora["keys"]))
+    exp_vox = vox_xyzi(ora["vox"])
+    got_vox = taps["voxel_cloud"][v0:v1]
+    assert got_vox.shape == exp_vox.shape, f"frame {f}: V {got_vox.shape} vs {exp_vox.shape}"
+    assert np.array_equal(bits(got_vox), bits(exp_vox)), f"frame {f}: voxel centroids not bit-exact"
+    assert np.array_equal(taps["labels"][v0:v1], ora["labels"]), f"frame {f}: cluster membership differs"
+    assert ctr["n_voxels"][f] == len(exp_vox)
+    assert ctr["n_components"][f] == ora["n_components"]
+    got_cl = clusters[k_off[f]:k_off[f + 1]]
+    exp_cl = ora["clusters"]
+    assert len(got_cl) == len(exp_cl), f"frame {f}: K {len(got_cl)} vs {len(exp_cl)}"
+    assert np.array_equal(got_cl["size"], exp_cl["size"])
+    assert np.array_equal(got_cl["min_index"], exp_cl["min_index"])
+    assert np.array_equal(bits(got_cl["x"]), bits(exp_cl["x"])), f"frame {f}: cluster x not bit-exact"
+    assert np.array_equal(bits(got_cl["y"]), bits(exp_cl["y"])), f"frame {f}: cluster y not bit-exact"
+
+
+def run_batch_with_taps(gpu: "api.ConesGpu", frames: list, d, g):
+    msgs = [PointCloud2.from_xyzi(a) for a in frames]
+    gpu.set_host_input(msgs)
+    gpu.run(d, g)
+    ctr, k_off, clusters = gpu.results()
+    offs = {"c_off": gpu.tap(api.TAP_CROP_OFFSETS), "v_off": gpu.tap(api.TAP_VOXEL_OFFSETS)}
+    taps = {"crop_index": gpu.tap(api.TAP_CROP_INDEX), "voxel_keys": gpu.tap(api.TAP_VOXEL_KEYS),
+            "voxel_order": gpu.tap(api.TAP_VOXEL_ORDER), "voxel_cloud": gpu.tap(api.TAP_VOXEL_CLOUD),
+            "labels": gpu.tap(api.TAP_LABELS)}
+    if g is not None:
+        taps["low"] = gpu.tap(api.TAP_SECTOR_LOW).reshape(-1, 17)
+    return ctr, k_off, clusters, offs, taps
