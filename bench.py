@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200: points/s (and frames/s, p50 frame
+latency) of the cones_perception hot path on 130k-point scans.
+
+    python bench.py --gpus N --steps K --warmup W            # ours (CUDA, libconesgpu.so)
+    python bench.py --impl reference --gpus N ...            # the CPU path on the host cores
+
+A step = one pass of the whole hot path (ground removal -> crop -> VoxelGrid -> Euclidean
+clustering -> centroids) over one batch of synthetic scans: BASELINE.json config 3, the
+64-beam 131 072-point scan with simulation params and ground removal on, FRAMES_PER_GPU
+frames per rank (weak scaling: 8 GPUs x 512 = the 4096-frame batch).  One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from cones_perception_b200 import scans  # noqa: E402
+
+METRIC = "points/sec at 130k-pt scans (frames/sec and p50 frame latency in extra keys)"
+UNIT = "points/s"
+CONE_CAP_PER_FRAME = 64
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU path (oracle)
+def cpu_frames_per_sec(frames: np.ndarray, cfg, threads: int, mode_faithful: bool = True):
+    """Times the CPU restatement (PCL cost profile) on `frames`; returns (seconds, per-stage ms)."""
+    from oracle import oracle as O
+
+    mode = O.PCL_FAITHFUL if mode_faithful else O.CANONICAL
+    O.lib()
+    stage = {"ground": 0.0, "from_msg": 0.0, "copy_cloud": 0.0, "crop": 0.0, "voxel": 0.0, "cluster": 0.0}
+    lock = threading.Lock()
+
+    def work(idx):
+        loc = dict.fromkeys(stage, 0.0)
+        for i in idx:
+            _, _, tm = O.detect(O.view_of_xyzi(frames[i]), cfg.detect, cfg.ground, mode)
+            for k in loc:
+                loc[k] += getattr(tm, k)
+        with lock:
+            for k in loc:
+                stage[k] += loc[k]
+
+    n = len(frames)
+    t0 = time.perf_counter()
+    if threads <= 1:
+        work(range(n))
+    else:
+        th = [threading.Thread(target=work, args=(range(t, n, threads),)) for t in range(threads)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    return dt, {k: 1e3 * v / n for k, v in stage.items()}
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return  # only rank 0 measures the CPU path
+    cfg = scans.config(3)
+    cores = os.cpu_count() or 1
+    sample = args.cpu_step_frames
+    frames = scans.generate(cfg, sample, base_seed=0)
+    n = cfg.points_per_frame
+    for _ in range(args.warmup):
+        cpu_frames_per_sec(frames[: max(cores, 8)], cfg, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_frames_per_sec(frames, cfg, cores)
+    dt = time.perf_counter() - t0
+    pts = args.steps * sample * n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": pts, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "frames_per_sec": pts / n,
+        "config": {"workload": "cfg3: 64-beam 131072-pt scans, simulation params, ground removal on",
+                   "frames_per_step": sample, "points_per_frame": n, "parallelism": f"{cores} host threads"},
+        "cpu_baseline": {"value": pts, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} frames/step of the same scans, oracle pcl_faithful mode, "
+                                   f"g++ -O2, frame-parallel over {cores} threads"},
+        "e2e": {"value": pts, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ ours
+class _DevArray:
+    """Zero-copy torch view of a raw device pointer (result buffers of the library)."""
+
+    def __init__(self, ptr: int, shape, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from cones_perception_b200 import api
+    from cones_perception_b200.pointcloud2 import PointCloud2, make_view, CCloudView
+    from cones_perception_b200.sharding import gather_cone_lists
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libconesgpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg = scans.config(3)
+    F, N = args.frames_per_gpu, cfg.points_per_frame
+    d, g = cfg.detect, cfg.ground
+
+    # ---- synthetic input: this rank's contiguous shard of the global batch, pinned
+    host = torch.empty((F, N, 4), dtype=torch.float32, pin_memory=True)
+    hnp = host.numpy()
+    scans.generate(cfg, F, base_seed=rank * F, out=hnp)
+    dev = host.to("cuda", non_blocking=False)
+
+    gpu = api.ConesGpu(max_points=F * N, max_frames=F, device=local, max_survivors=max(F * N // 8, 1 << 20),
+                       max_voxels=max(F * N // 16, 1 << 19))
+    ext = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", local))
+    frame_points = np.full(F, N, dtype=np.uint32)
+    gpu.set_device_input(dev.data_ptr(), frame_points, keep=dev)
+    cone_cap = F * CONE_CAP_PER_FRAME
+
+    def step_device():
+        gpu.run(d, g)
+        if world > 1:
+            d_cl, d_off, _ = gpu.device_results()
+            with torch.cuda.stream(ext):
+                off = torch.as_tensor(_DevArray(d_off, (F + 1,)), device="cuda")
+                cones = torch.as_tensor(_DevArray(d_cl, (cone_cap, 4)), device="cuda")
+                gather_cone_lists(off[1:] - off[:-1], cones, cone_cap)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    gpu.sync()
+    ctr, k_off, clusters = gpu.results()
+    launches_per_step = gpu.last_launch_count()
+
+    # ---- timed region: K steps, inputs resident in HBM (1 GiB per rank > 126 MB L2)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(ext)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    gpu.sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * F * N * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel roofline pass (events around each streaming kernel, same workload)
+    gpu.set_stage_timing(True)
+    k1, k2 = [], []
+    for _ in range(min(args.steps, 10)):
+        gpu.run(d, g)
+        gpu.sync()
+        k1.append(gpu.stage_ms(0))
+        k2.append(gpu.stage_ms(1))
+    gpu.set_stage_timing(False)
+    C_tot, V_tot, K_tot = int(ctr["n_cropped"].sum()), int(ctr["n_voxels"].sum()), int(ctr["n_clusters"].sum())
+    k1_ms, k2_ms = float(np.mean(k1)), float(np.mean(k2))
+    bytes_k1 = 16 * F * N
+    bytes_k2 = 16 * F * N + 24 * C_tot
+    dom = ("ground_sector_min_kernel", k1_ms, bytes_k1) if k1_ms >= k2_ms else \
+        ("mask_crop_compact_kernel", k2_ms, bytes_k2)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    achieved = dom[2] / (dom[1] * 1e-3) / 1e9
+    key_bits = int(ctr["key_bits"].max())
+    P = (key_bits + 7) // 8
+    b_alg_step = 32 * F * N + (72 + 16 * P) * C_tot + 104 * V_tot + 16 * K_tot
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom[0])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom[2], "kernel_ms": dom[1],
+                "kernels": {"ground_sector_min_kernel": {"ms": k1_ms, "GBps": bytes_k1 / (k1_ms * 1e-3) / 1e9},
+                            "mask_crop_compact_kernel": {"ms": k2_ms, "GBps": bytes_k2 / (k2_ms * 1e-3) / 1e9}},
+                "pipeline_algorithmic_bytes_per_step": b_alg_step,
+                "pipeline_GBps": b_alg_step / (ms_total * 1e-3 / args.steps) / 1e9,
+                "pipeline_frac": b_alg_step / (ms_total * 1e-3 / args.steps) / 1e9 / peak}
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + pipeline + D2H
+    msgs = [PointCloud2.from_xyzi(hnp[f]) for f in range(F)]
+    views = (CCloudView * F)(*[make_view(m, True) for m in msgs])
+    from cones_perception_b200.params import to_c_detect, to_c_ground
+    import ctypes as C
+    cd, cg = to_c_detect(d), to_c_ground(g)
+    o_ctr = np.zeros(F, dtype=api.COUNTER_DTYPE)
+    o_off = np.zeros(F + 1, dtype=np.uint32)
+    o_cl = np.zeros(cone_cap, dtype=api.CLUSTER_DTYPE)
+    total = C.c_uint64()
+
+    def step_e2e():
+        st = gpu.lib.cp_detect_batch(gpu._h, views, F, C.byref(cd), C.byref(cg), o_ctr.ctypes.data,
+                                     o_off.ctypes.data, o_cl.ctypes.data, cone_cap, C.byref(total))
+        if st != 0:
+            raise RuntimeError(gpu.lib.cp_last_error(gpu._h).decode())
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = world * F * N * e2e_steps / float(e2e_s.item())
+    assert total.value == K_tot and np.array_equal(o_cl[:K_tot].view(np.uint32), clusters.view(np.uint32)), \
+        "host-input and device-input runs disagree"
+    d2h = int(o_ctr.nbytes + o_off.nbytes + K_tot * 16 + 64)
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(F * N * 16), "d2h_bytes_per_step": d2h,
+           "frames_per_sec": e2e_val / N, "steps": e2e_steps,
+           "timer": "host wall clock around synchronous cp_detect_batch calls (pinned host clouds)"}
+
+    line = None
+    if rank == 0:
+        # ---- single-frame latency (config 2): host cloud in -> cone list out
+        cfg2 = scans.config(2)
+        f2 = scans.generate(cfg2, 1, base_seed=0)[0]
+        pin = torch.empty((N, 4), dtype=torch.float32, pin_memory=True)
+        pin.numpy()[:] = f2
+        lat_gpu = api.ConesGpu(max_points=N, max_frames=1, device=local)
+        m2 = PointCloud2.from_xyzi(pin.numpy())
+        for _ in range(5):
+            lat_gpu.detect(m2, cfg2.detect, cfg2.ground)
+        lat = []
+        for _ in range(args.latency_reps):
+            t = time.perf_counter()
+            lat_gpu.detect(m2, cfg2.detect, cfg2.ground)
+            lat.append(1e3 * (time.perf_counter() - t))
+        d2 = torch.from_numpy(f2).cuda()
+        lat_gpu.set_device_input(d2.data_ptr(), np.array([N], np.uint32), keep=d2)
+        lat_dev = []
+        for _ in range(args.latency_reps):
+            t = time.perf_counter()
+            lat_gpu.run(cfg2.detect, cfg2.ground)
+            lat_gpu.sync()
+            lat_dev.append(1e3 * (time.perf_counter() - t))
+        lat_gpu.close()
+
+        # ---- CPU baseline beside it (rank 0, N = 1 only): one core, bounded sample
+        cpu = None
+        if world == 1 and args.cpu_sample_frames > 0:
+            ns = min(args.cpu_sample_frames, F)
+            dt, stages = cpu_frames_per_sec(hnp[:ns], cfg, threads=1)
+            cpu = {"value": ns * N / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"first {ns} frames of the step's batch, oracle pcl_faithful mode (PCL cost profile), "
+                             f"g++ -O2, single thread like the reference's ros::spin nodes",
+                   "frames_per_sec": ns / dt, "ms_per_frame": 1e3 * dt / ns, "stage_ms_per_frame": stages,
+                   "host_cores_available": os.cpu_count()}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "frames_per_sec": value / N,
+            "p50_frame_latency_ms": float(np.percentile(lat, 50)), "p99_frame_latency_ms": float(np.percentile(lat, 99)),
+            "p50_frame_latency_device_resident_ms": float(np.percentile(lat_dev, 50)),
+            "config": {"workload": "cfg3: batch of 64-beam 131072-pt scans (simulation params, ground removal on), "
+                                   f"{F} frames per GPU, frame-sharded, cone lists gathered over NCCL when N>1",
+                       "frames_per_gpu": F, "points_per_frame": N, "global_frames": world * F,
+                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                       "cache": f"inputs larger than L2 ({F * N * 16 / 1e6:.0f} MB per rank vs 126 MB), no flush needed",
+                       "latency_workload": "cfg2 single frame, host cloud in -> cone list out"},
+            "per_step_counts": {"points": F * N, "cropped": C_tot, "voxels": V_tot, "clusters": K_tot},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks,
+        }
+    gpu.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--frames-per-gpu", type=int, default=512)
+    ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--cpu-sample-frames", type=int, default=512, help="frames timed on one core for cpu_baseline")
+    ap.add_argument("--cpu-step-frames", type=int, default=128, help="frames per step of --impl reference")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

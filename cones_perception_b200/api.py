@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "cp_strerror", "cp_last_error", "cp_abi_version", "cp_create_error", "cp_create", "cp_destroy",
     "cp_ground_remove", "cp_detect", "cp_batch_set_device_input", "cp_batch_set_host_input", "cp_batch_run",
     "cp_sync", "cp_batch_results", "cp_detect_batch", "cp_last_run_ms", "cp_last_launch_count", "cp_stream",
-    "cp_debug_tap", "cp_debug_sort",
+    "cp_debug_tap", "cp_debug_sort", "cp_set_stage_timing", "cp_stage_ms", "cp_device_results",
 ]
 
 CLUSTER_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.uint32), ("min_index", np.uint32)])
@@ -87,6 +87,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cp_stream.restype = vp
     lib.cp_debug_tap.argtypes = [vp, C.c_int, vp, u64, C.POINTER(u64)]
     lib.cp_debug_sort.argtypes = [vp, vp, vp, u32, u32]
+    lib.cp_set_stage_timing.argtypes = [vp, C.c_int]
+    lib.cp_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    lib.cp_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     if path is None:
         _lib = lib
     return lib
@@ -201,6 +204,20 @@ class ConesGpu:
         ms = C.c_float()
         self._ck(self.lib.cp_last_run_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def set_stage_timing(self, on: bool):
+        self._ck(self.lib.cp_set_stage_timing(self._h, 1 if on else 0))
+
+    def stage_ms(self, stage: int) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.cp_stage_ms(self._h, stage, C.byref(ms)))
+        return ms.value
+
+    def device_results(self):
+        """(d_clusters, d_cluster_offsets, d_n_clusters) raw device pointers of the last run."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.cp_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def last_launch_count(self) -> int:
         return int(self.lib.cp_last_launch_count(self._h))

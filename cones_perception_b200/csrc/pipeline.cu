@@ -41,10 +41,12 @@ struct cp_handle {
   int sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};  // around the two streaming kernels
+  bool stage_timing = false;
   std::string err = "";
   u32 launches = 0;
   bool batch_ready = false, ran = false;
-  bool taps = false, counted_ground = false;
+  bool taps = false, counted_ground = false, ran_ground = false;
 
   u64 cap_c = 0, cap_v = 0;
   u32 tiles_cap = 0, sort_tiles_cap = 0, hash_cap = 0;
@@ -483,7 +485,9 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   launch_init(h, ground ? ground->default_lowest_point : 0.0f);
   const u32 sgrid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, 8);
   if (ground) {
+    if (h->stage_timing) cudaEventRecord(h->ev_k[0], h->stream);
     launch_sector_min(h, g, sgrid);
+    if (h->stage_timing) cudaEventRecord(h->ev_k[1], h->stream);
     h->launches++;
   }
   CompactOut co;
@@ -497,8 +501,11 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   co.desc = h->d_desc_a;
   co.ctl = h->d_ctl;
   co.out32 = nullptr;
+  if (h->stage_timing) cudaEventRecord(h->ev_k[2], h->stream);
   launch_compact<false>(h, g, crop, gk, co, sgrid);
+  if (h->stage_timing) cudaEventRecord(h->ev_k[3], h->stream);
   h->launches++;
+  h->ran_ground = ground != nullptr;
 
   // ---- VoxelGrid
   const u32 fgrid = (F + 255) / 256;
@@ -749,7 +756,9 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&h->ev_k[0]) != cudaSuccess || cudaEventCreate(&h->ev_k[1]) != cudaSuccess ||
+      cudaEventCreate(&h->ev_k[2]) != cudaSuccess || cudaEventCreate(&h->ev_k[3]) != cudaSuccess) {
     h->err = "stream/event creation failed";
     return fail(CP_E_CUDA);
   }
@@ -840,6 +849,8 @@ void cp_destroy(cp_handle* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 2; ++i)
     if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1072,6 +1083,48 @@ cp_status cp_last_run_ms(cp_handle* h, float* ms) {
   }
   CK(cudaEventSynchronize(h->ev1));
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return CP_OK;
+}
+
+cp_status cp_set_stage_timing(cp_handle* h, int on) {
+  if (!h) return CP_E_PARAM;
+  h->stage_timing = on != 0;
+  return CP_OK;
+}
+
+cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms) {
+  if (!h || !ms) return CP_E_PARAM;
+  if (!h->ran || !h->stage_timing) {
+    h->err = "cp_stage_ms needs cp_set_stage_timing(1) before the run";
+    return CP_E_STATE;
+  }
+  if (stage == CP_STAGE_SECTOR_MIN) {
+    if (!h->ran_ground) {
+      h->err = "the last run had no ground removal";
+      return CP_E_STATE;
+    }
+    CK(cudaEventSynchronize(h->ev_k[1]));
+    CK(cudaEventElapsedTime(ms, h->ev_k[0], h->ev_k[1]));
+  } else if (stage == CP_STAGE_MASK_CROP_COMPACT) {
+    CK(cudaEventSynchronize(h->ev_k[3]));
+    CK(cudaEventElapsedTime(ms, h->ev_k[2], h->ev_k[3]));
+  } else {
+    h->err = "unknown stage";
+    return CP_E_PARAM;
+  }
+  return CP_OK;
+}
+
+cp_status cp_device_results(cp_handle* h, const void** d_clusters, const uint32_t** d_cluster_offsets,
+                            const uint32_t** d_n_clusters) {
+  if (!h) return CP_E_PARAM;
+  if (!h->ran) {
+    h->err = "cp_device_results before cp_batch_run";
+    return CP_E_STATE;
+  }
+  if (d_clusters) *d_clusters = h->d_clusters;
+  if (d_cluster_offsets) *d_cluster_offsets = h->d_k_off;
+  if (d_n_clusters) *d_n_clusters = &h->d_ctl->n_clusters;
   return CP_OK;
 }
 

@@ -137,8 +137,8 @@ def adversarial_points(d: DetectParams, seed: int = 0) -> np.ndarray:
     components of exactly max_cluster_size and max_cluster_size + 1 voxels."""
     rng = np.random.default_rng(seed)
     parts = []
-    # (ii) serpentine: rows along y, 0.30 m steps (< tol 0.397), rows 0.48 m apart (> tol), joined at alternating ends
-    step, gap = 0.30, 0.48
+    # (ii) serpentine: rows along y, 0.06 m steps (< tol 0.397), rows 0.48 m apart (> tol), joined at alternating ends
+    step, gap = 0.06, 0.48
     ys = np.arange(-4.5, 4.5 + 1e-6, step)
     z_layers = np.arange(1.2, 4.4, gap)
     xs = np.arange(1.8, 6.4, gap)
@@ -146,8 +146,10 @@ def adversarial_points(d: DetectParams, seed: int = 0) -> np.ndarray:
     flip = False
     for zi, z in enumerate(z_layers):
         xs_l = xs if zi % 2 == 0 else xs[::-1]
-        for x in xs_l:
+        for xi, x in enumerate(xs_l):
             row = ys[::-1] if flip else ys
+            if xi > 0:  # bridge point between consecutive rows (rows are > tol apart)
+                chain.append((0.5 * (x + xs_l[xi - 1]), row[0], z))
             chain.extend((x, y, z) for y in row)
             flip = not flip
         # bridge to the next layer at the last (x, y)
@@ -164,7 +166,7 @@ def adversarial_points(d: DetectParams, seed: int = 0) -> np.ndarray:
     for extra, (bx, by) in ((0, (60, 60)), (1, (60, -90))):
         n = d.max_cluster_size + extra
         idx = np.arange(n)
-        parts.append(_voxel_centres(bx + idx % 25, by + idx // 25, np.full(n, 20)))
+        parts.append(_voxel_centres(bx + idx % 25, by + idx // 25, np.full(n, 10)))
     pts = np.concatenate(parts)
     inten = rng.uniform(0, 100, len(pts)).astype(np.float32)
     return np.concatenate([pts, inten[:, None]], 1).astype(np.float32)

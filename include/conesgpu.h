@@ -157,6 +157,16 @@ cp_status cp_detect_batch(cp_handle* h, const cp_cloud_view* frames, uint32_t n_
 
 /* Device time of the last cp_batch_run (CUDA events on the handle's stream), ms. */
 cp_status cp_last_run_ms(cp_handle* h, float* ms);
+/* Per-kernel device times of the two streaming passes (CUDA events on the handle's stream
+ * around each launch).  Off by default; bench.py switches it on for the roofline pass. */
+typedef enum cp_stage { CP_STAGE_SECTOR_MIN = 0, CP_STAGE_MASK_CROP_COMPACT = 1 } cp_stage;
+cp_status cp_set_stage_timing(cp_handle* h, int on);
+cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms);
+/* Device pointers of the last run's results (valid until the next run on this handle):
+ * packed cp_cluster records, n_frames+1 cluster offsets, and the total cluster count.
+ * Lets a multi-GPU caller hand the cone lists to NCCL without a host round trip. */
+cp_status cp_device_results(cp_handle* h, const void** d_clusters, const uint32_t** d_cluster_offsets,
+                            const uint32_t** d_n_clusters);
 /* Kernel launches enqueued by the last cp_batch_run / cp_detect / cp_ground_remove. */
 uint32_t cp_last_launch_count(const cp_handle* h);
 /* The handle's stream as a cudaStream_t, for callers that time with their own events. */
