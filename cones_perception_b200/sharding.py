@@ -37,13 +37,14 @@ def gather_cone_lists(counts, cones, cap_cones: int, group=None, dst: int = 0):
     counts = counts.contiguous()
     cones = cones.contiguous()
     assert cones.shape == (cap_cones, CONE_WORDS)
-    counts_all = torch.empty((world,) + tuple(counts.shape), dtype=counts.dtype, device=counts.device)
-    cones_all = torch.empty((world, cap_cones, CONE_WORDS), dtype=cones.dtype, device=cones.device)
+    # outputs are the dim-0 concatenation of the inputs (the form both NCCL and gloo accept)
+    counts_all = torch.empty((world * counts.shape[0],), dtype=counts.dtype, device=counts.device)
+    cones_all = torch.empty((world * cap_cones, CONE_WORDS), dtype=cones.dtype, device=cones.device)
     dist.all_gather_into_tensor(counts_all, counts, group=group)
     dist.all_gather_into_tensor(cones_all, cones, group=group)
     if rank != dst:
         return None, None
-    return counts_all, cones_all
+    return counts_all.view(world, -1), cones_all.view(world, cap_cones, CONE_WORDS)
 
 
 def unpack_gathered(counts_all: np.ndarray, cones_all: np.ndarray):

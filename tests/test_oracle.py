@@ -1,0 +1,295 @@
+"""CPU tests of the oracle: known-answer tests derived from SURVEY.md Appendix A, cross-checks
+between its two modes and against independent implementations, and the committed goldens."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from cones_perception_b200 import scans
+from cones_perception_b200.params import PRESETS, DetectParams, GroundParams
+from oracle import oracle as O
+from tests.util import oracle_stages, vox_xyzi
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def f32(x):
+    return np.float32(x)
+
+
+def bits(x):
+    return int(np.array(x, np.float32).view(np.uint32))
+
+
+def cloud(rows):
+    a = np.zeros((len(rows), 4), np.float32)
+    a[:, :len(rows[0])] = np.array(rows, np.float32)
+    return a
+
+
+# ------------------------------------------------------------------ constants (Appendix A table)
+def test_constants_bit_patterns():
+    assert bits(0.325) == 0x3EA66666 and bits(0.228) == 0x3E6978D5
+    tol = np.sqrt(np.float64(np.float32(0.325)) ** 2 + np.float64(np.float32(0.228)) ** 2)
+    assert bits(tol) == 0x3ECB4395
+    assert bits(O.r2(PRESETS["our"])) == 0x3E216440
+    assert bits(np.float32(1.0) / np.float32(0.04)) == 0x41C80000          # inverse leaf = 25.0f exactly
+    assert bits((360 // 16) * np.pi / 180) == 0x3EC49809                    # 22 deg, not 22.5
+
+
+def test_sector_index_range_and_wrap():
+    L = O.lib()
+    assert L.orc_sector_of(1.0, 0.0) == 0
+    assert L.orc_sector_of(1.0, -1e-9) == 16          # angles just below 2*pi land in the 17th sector (Q2)
+    assert L.orc_sector_of(-1.0, 0.0) == int(np.floor(np.float32(np.pi) / np.float32(0.38397244)))
+    ang = np.linspace(-np.pi, np.pi, 20001)
+    s = [L.orc_sector_of(float(np.cos(a)), float(np.sin(a))) for a in ang]
+    assert min(s) == 0 and max(s) == 16
+    assert L.orc_sector_of(0.0, 0.0) == 0             # atan2(0, 0) = 0: the filler point
+
+
+# ------------------------------------------------------------------ ground removal (A.2)
+def test_ground_minima_and_mask():
+    g = GroundParams()
+    pts = O.points32(cloud([[5, 0.1, -0.60], [5, 0.2, -0.62], [5, 0.3, -0.51], [5, 0.4, -0.53],
+                            [-5, 0.1, 0.3], [0, 5, -0.05]]))
+    low = O.ground_minima(pts, g.default_lowest_point)
+    assert low[0] == f32(-0.62)
+    assert low[8] == f32(-0.1)                         # (-5, 0.1): z = 0.3 does not lower the default
+    assert low[4] == f32(-0.1)
+    keep = O.ground_mask(pts, low)
+    # drop iff (double)z < (double)low + 0.1 : low[0]+0.1 = -0.52 -> -0.53 dropped, -0.51 kept
+    # (0, 5, -0.05): low[4] stays at the default -0.1, threshold 0.0 -> dropped
+    assert keep.tolist() == [0, 0, 1, 0, 1, 0]
+
+
+def test_ground_node_pads_with_zero_points():
+    a = cloud([[5, 0.1, -0.6, 7], [5, 0.2, 0.5, 8], [4, -3, -0.6, 9], [4, -3.1, 0.4, 10]])
+    out, kept, low, keep = O.ground_node(O.view_of_xyzi(a), GroundParams())
+    assert kept == 2 and keep.tolist() == [0, 1, 0, 1]
+    assert out["x"].tolist() == [5, 4, 0, 0] and out["intensity"].tolist() == [8, 10, 0, 0]
+    assert out["pad"].tolist() == [1, 1, 1, 1]
+
+
+def test_all_ground_cloud_yields_nothing():
+    rng = np.random.default_rng(0)
+    a = np.zeros((2000, 4), np.float32)
+    a[:, 0] = rng.uniform(2, 6, 2000)
+    a[:, 1] = rng.uniform(-3, 3, 2000)
+    a[:, 2] = -0.6 + rng.normal(0, 0.002, 2000)
+    cl, ctr, _ = O.detect(O.view_of_xyzi(a), PRESETS["simulation"], GroundParams())
+    assert ctr.n_ground_kept == 0 and ctr.n_cropped == 0 and len(cl) == 0
+
+
+# ------------------------------------------------------------------ crop (A.3)
+def test_crop_thresholds():
+    d = PRESETS["our"]  # dmax 7, dmin 0.7, level -0.5, angle 90
+    rows = [[3, 0, 0], [3, 0, -0.5], [3, 0, np.nextafter(f32(-0.5), f32(-1))],      # level: < is strict
+            [7, 0, 0], [np.nextafter(f32(7), f32(8)), 0, 0],                          # d > dmax strict
+            [0.7, 0, 0], [np.nextafter(f32(0.7), f32(0)), 0, 0],                      # d < dmin strict
+            [1e-9, 3, 0], [0, 3, 0], [-1e-3, 3, 0], [1e-9, -3, 0], [0, -3, 0],        # |angle| < 90 deg
+            [np.nan, 1, 0], [1, np.inf, 0]]
+    keep = O.crop_mask(O.points32(cloud(rows)), d)
+    assert keep.tolist() == [1, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0] or \
+        keep.tolist() == [1, 1, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0]
+    # (float)0.7 = 0.69999999 < 0.7 (double): the d < dmin test drops it
+    assert keep[5] == 0
+    # atan2(3, 1e-9) rounds to float(pi/2) >= theta: dropped, like x = 0
+    assert keep[7] == 0
+
+
+def test_zero_point_is_cropped_by_shipped_presets():
+    z = O.points32(np.zeros((1, 4), np.float32))
+    for d in PRESETS.values():
+        assert O.crop_mask(z, d)[0] == 0
+
+
+# ------------------------------------------------------------------ VoxelGrid (A.4)
+def test_voxel_keys_and_centroids():
+    d = PRESETS["our"]
+    a = cloud([[1.00, 1.00, 0.00, 10], [1.01, 1.01, 0.01, 20], [1.039, 1.0, 0.0, 30],   # same voxel (25,25,0)
+               [1.041, 1.0, 0.0, 40],                                                   # next voxel in x
+               [1.0, 1.0, 0.041, 50]])                                                  # next voxel in z
+    keys, order, vox, ctr = O.voxel_grid(O.points32(a), d)
+    assert list(ctr.min_b) == [25, 25, 0] and list(ctr.div_b) == [2, 1, 2]
+    assert keys.tolist() == [0, 0, 0, 1, 2] and order.tolist() == [0, 1, 2, 3, 4]
+    assert len(vox) == 3
+    sx = (f32(1.00) + f32(1.01)) + f32(1.039)
+    assert vox["x"][0] == sx / f32(3) and vox["intensity"][0] == f32(20)
+    assert vox["x"][1] == f32(1.041) and vox["z"][2] == f32(0.041)
+
+
+def test_voxel_boundary_one_ulp():
+    d = PRESETS["our"]
+    edge = f32(0.08)                      # 2 * 0.04: floor(x * 25) switches from 1 to 2 around here
+    lo, hi = np.nextafter(edge, f32(0)), np.nextafter(edge, f32(1))
+    a = cloud([[0.0, 0, 0], [lo, 0, 0], [edge, 0, 0], [hi, 0, 0]])
+    keys, _, _, _ = O.voxel_grid(O.points32(a), d)
+    expect = [int(np.floor(f32(v) * f32(25.0))) for v in (0.0, lo, edge, hi)]
+    assert keys.tolist() == expect
+
+
+def test_voxel_empty_and_passthrough():
+    d = PRESETS["our"]
+    keys, order, vox, ctr = O.voxel_grid(O.points32(np.zeros((0, 4), np.float32)), d)
+    assert len(vox) == 0
+    # extents so large that dx*dy*dz overflows int32: PCL returns the input unchanged
+    a = cloud([[0, 0, 0], [1000, 1000, 1000], [1000, 1000, 1000.01]])
+    keys, order, vox, ctr = O.voxel_grid(O.points32(a), d)
+    assert ctr.passthrough == 1 and len(vox) == 3 and vox["x"].tolist() == [0, 1000, 1000]
+
+
+def test_canonical_vs_faithful_voxel_centroids_within_tolerance():
+    cfg = scans.config(2)
+    frame = scans.generate(cfg, 1, 11)[0]
+    a = oracle_stages(frame, cfg.detect, cfg.ground, O.CANONICAL)
+    b = oracle_stages(frame, cfg.detect, cfg.ground, O.PCL_FAITHFUL)
+    assert np.array_equal(a["keys"], b["keys"])
+    assert np.abs(vox_xyzi(a["vox"])[:, :3] - vox_xyzi(b["vox"])[:, :3]).max() <= 1e-5   # north_star tolerance
+    assert np.array_equal(a["labels"], b["labels"])                                       # membership exact
+    ca = np.sort(a["clusters"], order=["size", "min_index"])
+    cb = np.sort(b["clusters"], order=["size", "min_index"])
+    assert np.array_equal(ca["min_index"], cb["min_index"]) and np.array_equal(ca["size"], cb["size"])
+    assert np.abs(ca["x"] - cb["x"]).max() <= 1e-5 and np.abs(ca["y"] - cb["y"]).max() <= 1e-5
+
+
+# ------------------------------------------------------------------ clustering (A.5)
+def vox_from(rows):
+    return O.points32(cloud(rows))
+
+
+def test_pair_just_inside_and_outside_r2():
+    d = PRESETS["simulation"]
+    r2 = f32(O.r2(d))
+    r = np.sqrt(np.float64(r2))
+    inside = np.nextafter(f32(r), f32(0))
+    while f32(inside) * f32(inside) >= r2:
+        inside = np.nextafter(inside, f32(0))
+    outside = f32(r)
+    while f32(outside) * f32(outside) < r2:
+        outside = np.nextafter(outside, f32(1))
+    lab, cl, comps, _ = O.extract_clusters(vox_from([[0, 0, 0], [inside, 0, 0]]), d)
+    assert lab.tolist() == [0, 0] and comps == 1 and cl["size"].tolist() == [2]
+    lab, cl, comps, _ = O.extract_clusters(vox_from([[0, 0, 0], [outside, 0, 0]]), d)
+    assert lab.tolist() == [0, 1] and comps == 2 and len(cl) == 0      # singletons < min_cluster_size 2
+
+
+def test_chain_spacing():
+    d = PRESETS["simulation"]
+    k = 40
+    near = vox_from([[0.39 * i, 0, 0] for i in range(k)])
+    far = vox_from([[0.40 * i, 0, 0] for i in range(k)])
+    lab, cl, comps, _ = O.extract_clusters(near, d)
+    assert comps == 1 and cl["size"].tolist() == [k] and cl["min_index"].tolist() == [0]
+    lab, cl, comps, _ = O.extract_clusters(far, d)
+    assert comps == k and len(cl) == 0
+
+
+def test_max_cluster_size_kept_and_dropped_whole():
+    d = DetectParams(**{**PRESETS["our"].__dict__})
+    d.max_cluster_size = 50
+    line = lambda n, y: [[0.05 * i, y, 0] for i in range(n)]
+    vox = vox_from(line(50, 0.0) + line(51, 5.0) + line(2, 10.0) + line(3, 15.0))
+    lab, cl, comps, members = O.extract_clusters(vox, d)
+    assert comps == 4
+    assert cl["size"].tolist() == [50, 3] and cl["min_index"].tolist() == [0, 103]   # 51 dropped whole, 2 < min
+    assert members[:50].tolist() == list(range(50))
+
+
+def test_cluster_order_ties_by_min_index():
+    d = PRESETS["our"]
+    tri = lambda x: [[x, 0, 0], [x + 0.1, 0, 0], [x, 0.1, 0]]
+    vox = vox_from(tri(10) + tri(0) + tri(5) + [[20, 0, 0], [20.1, 0, 0], [20, 0.1, 0], [20.1, 0.1, 0]])
+    _, cl, _, _ = O.extract_clusters(vox, d)
+    assert cl["size"].tolist() == [4, 3, 3, 3] and cl["min_index"].tolist() == [9, 0, 3, 6]
+
+
+def test_labels_match_bruteforce_and_scipy():
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    cfg = scans.config(2)
+    frame = scans.generate(cfg, 1, 21)[0]
+    st = oracle_stages(frame, cfg.detect, cfg.ground)
+    vox, lab = st["vox"], st["labels"]
+    assert np.array_equal(lab, O.label_bruteforce(vox, cfg.detect))
+    xyz = np.stack([vox["x"], vox["y"], vox["z"]], 1).astype(np.float64)
+    r2 = O.r2(cfg.detect)
+    # guard band: no pair within 1e-6 of r2, so float/double disagreement cannot matter
+    tree = cKDTree(xyz)
+    pairs = tree.query_pairs(np.sqrt(r2) + 1e-3, output_type="ndarray")
+    d2 = ((xyz[pairs[:, 0]] - xyz[pairs[:, 1]]) ** 2).sum(1)
+    assert np.abs(d2 - r2).min() > 1e-6
+    edges = pairs[d2 < r2]
+    n = len(vox)
+    ncomp, sl = connected_components(coo_matrix((np.ones(len(edges)), (edges[:, 0], edges[:, 1])), shape=(n, n)),
+                                     directed=False)
+    first = np.full(ncomp, n)
+    np.minimum.at(first, sl, np.arange(n))
+    assert np.array_equal(first[sl], lab)
+
+
+def test_faithful_mode_on_adversarial_scene():
+    cfg = scans.config(5)
+    frame = scans.generate_config5(1, 0)[0]
+    a = oracle_stages(frame, cfg.detect, cfg.ground, O.CANONICAL)
+    b = oracle_stages(frame, cfg.detect, cfg.ground, O.PCL_FAITHFUL)
+    assert np.array_equal(a["labels"], b["labels"])
+    assert np.bincount(a["labels"]).max() >= 10_000          # the serpentine chain is one deep component
+    assert (a["clusters"]["size"] == cfg.detect.max_cluster_size).sum() == 1
+    assert not (a["clusters"]["size"] > cfg.detect.max_cluster_size).any()
+
+
+# ------------------------------------------------------------------ centroid + extension (A.6, A.7)
+def test_cluster_centroid_is_sequential_fp32():
+    d = PRESETS["our"]
+    rows = [[1.1, 2.1, 0], [1.2, 2.2, 0], [1.3, 2.3, 0.1]]
+    _, cl, _, _ = O.extract_clusters(vox_from(rows), d)
+    x = (f32(0) + f32(1.1) + f32(1.2)) + f32(1.3)
+    assert cl["x"][0] == x / f32(3)
+
+
+def test_radial_extension():
+    x, y = O.extend(3.0, 4.0, 0.05)
+    assert x == f32(np.float64(f32(3.0)) + np.float64(f32(3.0) / f32(5.0)) * 0.05)
+    assert y == f32(np.float64(f32(4.0)) + np.float64(f32(4.0) / f32(5.0)) * 0.05)
+
+
+# ------------------------------------------------------------------ fixtures
+def test_real_cone_crops_each_form_one_cluster():
+    """The 577 hand-labelled cone crops shipped with the reference (cones_clouds/cones.pkl):
+    every crop must voxelise and cluster into exactly one component."""
+    z = np.load(os.path.join(GOLD, "cone_crops.npz"))
+    pts, lens = z["points"], z["lengths"]
+    d = PRESETS["fsai"]
+    off = 0
+    single = 0
+    for n in lens:
+        crop = pts[off:off + n]
+        off += n
+        _, _, vox, _ = O.voxel_grid(O.points32(crop), d)
+        lab, _, comps, _ = O.extract_clusters(vox, d)
+        single += comps == 1
+    assert single == len(lens)
+
+
+@pytest.mark.parametrize("idx,seed", [(1, 0), (2, 0), (2, 7), (4, 0), (5, 0)])
+def test_oracle_matches_committed_goldens(idx, seed):
+    z = np.load(os.path.join(GOLD, f"cfg{idx}_seed{seed}_golden.npz"))
+    cfg = scans.config(idx)
+    frame = scans.generate_config5(1, seed)[0] if idx == 5 else scans.generate(cfg, 1, seed)[0]
+    assert hashlib.sha256(frame.tobytes()).hexdigest() == str(z["input_sha256"]), "scan generator drifted"
+    cl, ctr, _ = O.detect(O.view_of_xyzi(frame), cfg.detect, cfg.ground, O.CANONICAL)
+    assert np.array_equal(cl.view(np.uint32), z["clusters"].view(np.uint32))
+    got = [ctr.n_points, ctr.n_ground_kept, ctr.n_cropped, ctr.n_voxels, ctr.n_components, ctr.n_clusters,
+           ctr.key_bits]
+    assert got == z["counters"].tolist()
+
+
+def test_generator_is_thread_count_independent():
+    cfg = scans.config(3)
+    a = scans.generate(cfg, 3, 5, nthreads=1)
+    b = scans.generate(cfg, 3, 5, nthreads=3)
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a[0], a[1])
