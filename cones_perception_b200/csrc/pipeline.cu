@@ -75,6 +75,7 @@ struct cp_handle {
   u64* d_hkeys = nullptr;
   u32* d_hvals = nullptr;
   ClusterRec* d_clusters = nullptr;
+  u32 *d_mask = nullptr, *d_tile_count = nullptr, *d_tile_excl = nullptr;
   u64 *d_desc_a = nullptr, *d_desc_b = nullptr, *d_desc_c = nullptr, *d_desc_d = nullptr;
   u32 *d_tap_keys = nullptr, *d_tap_order = nullptr;
   i32* d_tap_labels = nullptr;
@@ -408,13 +409,38 @@ u32 grid_for(u64 work, u32 block, int sms, int per_sm) {
   return (u32)(b < cap ? b : cap);
 }
 
+// pass 2 of the front end: keep mask -> tile scan -> ordered gather (+bbox)
 template <bool OUT32>
-void launch_compact(cp_handle* h, const Geom& g, const CropK& c, const GroundK& gk, const CompactOut& o, u32 grid) {
+void launch_front_pass2(cp_handle* h, const Geom& g, const CropK& c, const GroundK& gk, u32 cap, uint8_t* out32,
+                        u32 grid) {
+  MaskOut mo;
+  mo.mask = h->d_mask;
+  mo.tile_count = h->d_tile_count;
+  mo.gcount = h->d_gcount;
+  GatherOut go;
+  go.pts = h->d_pts;
+  go.src = h->d_src;
+  go.frame = h->d_frame;
+  go.cap = cap;
+  go.bbox_key = h->d_bbox;
+  go.out32 = out32;
+  if (h->stage_timing) cudaEventRecord(h->ev_k[2], h->stream);
   switch (h->layout.mode) {
-    case 0: mask_crop_compact_kernel<0, OUT32><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, o); break;
-    case 1: mask_crop_compact_kernel<1, OUT32><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, o); break;
-    default: mask_crop_compact_kernel<2, OUT32><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, o); break;
+    case 0: keep_mask_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo); break;
+    case 1: keep_mask_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo); break;
+    default: keep_mask_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo); break;
   }
+  if (h->stage_timing) cudaEventRecord(h->ev_k[3], h->stream);
+  const u32 stiles = (g.n_tiles + kScanTile - 1) / kScanTile;
+  tile_scan_kernel<<<stiles < (u32)h->sms * 4 ? stiles : (u32)h->sms * 4, kScanThreads, 0, h->stream>>>(
+      g, h->d_tile_count, h->d_tile_excl, h->d_c_off, h->d_desc_a, h->d_ctl, cap);
+  const u32 ggrid = grid_for((u64)g.n_tiles * 32, 256, h->sms, 8);
+  switch (h->layout.mode) {
+    case 0: gather_survivors_kernel<0, OUT32><<<ggrid, 256, 0, h->stream>>>(h->in_ptr, h->layout, g, gk, h->d_mask, h->d_tile_count, h->d_tile_excl, go); break;
+    case 1: gather_survivors_kernel<1, OUT32><<<ggrid, 256, 0, h->stream>>>(h->in_ptr, h->layout, g, gk, h->d_mask, h->d_tile_count, h->d_tile_excl, go); break;
+    default: gather_survivors_kernel<2, OUT32><<<ggrid, 256, 0, h->stream>>>(h->in_ptr, h->layout, g, gk, h->d_mask, h->d_tile_count, h->d_tile_excl, go); break;
+  }
+  h->launches += 3;
 }
 void launch_sector_min(cp_handle* h, const Geom& g, u32 grid) {
   switch (h->layout.mode) {
@@ -490,21 +516,7 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
     if (h->stage_timing) cudaEventRecord(h->ev_k[1], h->stream);
     h->launches++;
   }
-  CompactOut co;
-  co.pts = h->d_pts;
-  co.src = h->d_src;
-  co.frame = h->d_frame;
-  co.cap = (u32)h->cap_c;
-  co.c_off = h->d_c_off;
-  co.bbox_key = h->d_bbox;
-  co.gcount = h->d_gcount;
-  co.desc = h->d_desc_a;
-  co.ctl = h->d_ctl;
-  co.out32 = nullptr;
-  if (h->stage_timing) cudaEventRecord(h->ev_k[2], h->stream);
-  launch_compact<false>(h, g, crop, gk, co, sgrid);
-  if (h->stage_timing) cudaEventRecord(h->ev_k[3], h->stream);
-  h->launches++;
+  launch_front_pass2<false>(h, g, crop, gk, (u32)h->cap_c, nullptr, sgrid);
   h->ran_ground = ground != nullptr;
 
   // ---- VoxelGrid
@@ -819,6 +831,9 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   A(dalloc(h, &h->d_hvals, h->hash_cap));
   A(dalloc(h, &h->d_clusters, h->cap_v));
   A(dalloc(h, &h->d_desc_a, h->tiles_cap));
+  A(dalloc(h, &h->d_mask, (size_t)h->tiles_cap * kTileWords));
+  A(dalloc(h, &h->d_tile_count, h->tiles_cap));
+  A(dalloc(h, &h->d_tile_excl, h->tiles_cap));
   const size_t nb = h->cap_c / kHeadTile + 2;
   A(dalloc(h, &h->d_desc_b, nb));
   A(dalloc(h, &h->d_desc_c, nb));
@@ -1051,18 +1066,9 @@ cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_groun
   gk.do_ground = 1;
   gk.want_count = 0;
   gk.pad_survives = 0;
-  CompactOut co;
-  memset(&co, 0, sizeof(co));
-  co.cap = n;
-  co.c_off = h->d_c_off;
-  co.bbox_key = h->d_bbox;
-  co.gcount = h->d_gcount;
-  co.desc = h->d_desc_a;
-  co.ctl = h->d_ctl;
-  co.out32 = h->d_out32;
-  launch_compact<true>(h, geo, crop, gk, co, sgrid);
+  launch_front_pass2<true>(h, geo, crop, gk, n, h->d_out32, sgrid);
   pad_zero_points_kernel<<<grid_for(n, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_out32, h->d_ctl, n);
-  h->launches += 3;
+  h->launches += 2;
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_xyzi32, h->d_out32, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
   if (low17) CK(cudaMemcpyAsync(h->h_frame_u32, h->d_low_key, sizeof(u32) * kNSect, cudaMemcpyDeviceToHost, h->stream));

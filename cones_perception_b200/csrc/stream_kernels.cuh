@@ -1,23 +1,31 @@
-// stream_kernels.cuh — the two streaming passes over the raw scan (16 B/point each):
+// stream_kernels.cuh — the streaming front end over the raw scan (16 B/point per pass):
 //
 //   ground_sector_min_kernel   pass 1 of GroundRemover::cloud_handler
 //                              (src/ground_removal.cpp:58-68): per-sector lowest z
-//   mask_crop_compact_kernel   pass 2 (:70-77) fused with filter_points_position
-//                              (src/cone_detection.cpp:189-204) and an order-preserving
-//                              compaction + bounding box of the survivors
+//   keep_mask_kernel           pass 2 (:70-77) fused with filter_points_position
+//                              (src/cone_detection.cpp:189-204): one keep bit per point
+//                              (warp ballots) + survivors per tile
+//   tile_scan_kernel           exclusive scan of the per-tile counts (decoupled look-back)
+//   gather_survivors_kernel    order-preserving compaction of the few survivors + bbox
 //
-// Both are HBM-bound streaming kernels: coalesced 128-bit loads (one float4 per point in
-// the compact layout), per-CTA shared-memory reduction, warp ballots for the masks.
-// Exactness: every predicate has a cheap fp32 test with a guard band; points that land in
-// a guard band (a few per million) re-evaluate the reference's double-precision formula.
+// The two heavy kernels are pure streaming maps with no inter-CTA dependency: coalesced
+// 128-bit loads (one float4 per point in the compact layout), shared-memory sector tables.
+// They are instruction-light because of two exact prefilters:
+//   pass 1: a point can only lower a sector minimum if z < max over sectors of the minima
+//           seen so far, so ground returns above that bound never need their sector;
+//   pass 2: a point with z < min over sectors of the thresholds is ground in every sector.
+// Exactness: every remaining predicate has a cheap fp32 test with a guard band; points in
+// a band (a few per 10^5) re-evaluate the reference's double-precision formula.
 #pragma once
 #include "common.cuh"
 
 namespace cp {
 
 constexpr int kStreamThreads = 256;
+constexpr int kStreamWarps = kStreamThreads / 32;
 constexpr int kStreamRows = 8;
 constexpr int kStreamTile = kStreamThreads * kStreamRows;  // 2048 points
+constexpr int kTileWords = kStreamTile / 32;               // 64 keep-mask words per tile
 
 struct Layout {
   u32 step;
@@ -53,19 +61,19 @@ struct GroundK {
 
 __device__ __forceinline__ void tile_lookup(const Geom& g, u32 tile, u32& frame, u32& local0, u32& count,
                                             u64& first_point) {
+  u32 n;
   if (g.uniform_n) {
     frame = tile / g.tpf;
     local0 = (tile - frame * g.tpf) * kStreamTile;
     first_point = (u64)frame * g.uniform_n;
-    const u32 n = g.uniform_n;
-    count = n - local0 < (u32)kStreamTile ? n - local0 : (u32)kStreamTile;
+    n = g.uniform_n;
   } else {
     frame = g.tile_frame[tile];
     local0 = (tile - g.frame_tile0[frame]) * kStreamTile;
     first_point = g.frame_off[frame];
-    const u32 n = g.frame_n[frame];
-    count = n - local0 < (u32)kStreamTile ? n - local0 : (u32)kStreamTile;
+    n = g.frame_n[frame];
   }
+  count = n - local0 < (u32)kStreamTile ? n - local0 : (u32)kStreamTile;
 }
 
 __device__ __forceinline__ float load_f32_bytes(const uint8_t* p) {
@@ -104,27 +112,56 @@ __device__ __noinline__ float atan2_exact(float y, float x) {
 // src/ground_removal.cpp:20 evaluated at survey time: float((360/16) * M_PI / 180)
 #define CP_SECTOR_ANGLE 0.38397244f
 #define CP_INV_SECTOR_ANGLE 2.6043537f
+#define CP_ANGLE_GUARD 1e-5f     // >= 3x the worst-case error of atan2_approx (3e-6 rad)
+#define CP_SECTOR_GUARD 4e-5f    // same bound scaled by 1/sector_angle, plus rounding of u
 
 // src/ground_removal.cpp:61-64 given the exact float angle
 __device__ __forceinline__ int sector_from_exact(float a) {
   const float ang = (a < 0.0f) ? (float)((double)a + 6.283185307179586) : a;
   return (int)floorf(__fdiv_rn(ang, CP_SECTOR_ANGLE));
 }
+__device__ __noinline__ int sector_exact(float x, float y) {
+  // common exact case first: +x axis (includes the all-zero filler point): atan2 = +-0
+  if (y == 0.0f && (x > 0.0f || (x == 0.0f && !signbit(x)))) return 0;
+  return sector_from_exact(atan2_exact(y, x));
+}
 
-// Fast sector from the fp32 atan2f (<= 2 ulp), exact re-evaluation inside guard bands.
-// `a_fast` must be atan2f(y, x).
-__device__ __forceinline__ int sector_of(float x, float y, float a_fast) {
-  const float ang = a_fast < 0.0f ? a_fast + 6.2831855f : a_fast;
+// Approximate atan2 for the fast paths: octant reduction + odd minimax polynomial
+// (degree 11, max error 1.74e-6 rad on [0,1]); total error incl. rounding < 3e-6 rad.
+// `ok` is false when the inputs are outside the range where that bound holds.
+__device__ __forceinline__ float atan2_approx(float y, float x, bool& ok) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  ok = (mx > 1e-30f) & (mx < 1e30f);
+  const float t = __fdividef(mn, mx);
+  const float s = t * t;
+  float p = -0.011719129f;
+  p = fmaf(p, s, 0.052647334f);
+  p = fmaf(p, s, -0.11642647f);
+  p = fmaf(p, s, 0.19354036f);
+  p = fmaf(p, s, -0.33262283f);
+  p = fmaf(p, s, 0.99997723f);
+  float r = p * t;
+  r = ay > ax ? 1.57079637f - r : r;
+  r = x < 0.0f ? 3.14159274f - r : r;
+  return copysignf(r, y);
+}
+
+// sector from the approximate angle; exact re-evaluation inside the guard bands
+__device__ __forceinline__ int sector_of(float x, float y, float a, bool ok) {
+  const float ang = a < 0.0f ? a + 6.2831855f : a;
   const float u = ang * CP_INV_SECTOR_ANGLE;
   const float fl = floorf(u);
   const float fr = u - fl;
-  const bool risky = (fr < 2e-5f) | (fr > 1.0f - 2e-5f) | (fabsf(a_fast) < 1e-5f);
-  if (risky) {
-    // common exact case first: +x axis (includes the all-zero filler point)
-    if (y == 0.0f && (x > 0.0f || (x == 0.0f && !signbit(x)))) return 0;
-    return sector_from_exact(atan2_exact(y, x));
-  }
+  const bool risky = !ok | (fr < CP_SECTOR_GUARD) | (fr > 1.0f - CP_SECTOR_GUARD) | (fabsf(a) < CP_ANGLE_GUARD);
+  if (risky) return sector_exact(x, y);
   return (int)fl;
+}
+
+__device__ __forceinline__ bool finite3(float x, float y, float z) {
+  // 0 * finite = 0; 0 * inf = NaN; 0 * NaN = NaN
+  const float t = fmaf(z, 0.0f, fmaf(y, 0.0f, x * 0.0f));
+  return t == 0.0f;
 }
 
 // ---- pass 1: per-sector minima ----------------------------------------------------------
@@ -132,79 +169,75 @@ template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads)
 ground_sector_min_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, u32* __restrict__ low_key) {
   __shared__ u32 smin[kSectStride];
-  const int lane = lane_id();
+  // prefilter bounds: max of smin over the sectors a quadrant can reach (0: all sectors);
+  // a point at or above its bound cannot lower any minimum
+  __shared__ u32 s_bound[5];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
   // contiguous chunk of tiles per CTA so the shared table is flushed once per frame change
   const u32 per = (g.n_tiles + gridDim.x - 1) / gridDim.x;
   const u32 t0 = blockIdx.x * per;
   const u32 t1 = t0 + per < g.n_tiles ? t0 + per : g.n_tiles;
-  if (threadIdx.x < kSectStride) smin[threadIdx.x] = 0xFFFFFFFFu;
-  __syncthreads();
   u32 cur_frame = 0xFFFFFFFFu;
   for (u32 tile = t0; tile < t1; ++tile) {
     u32 frame, local0, count;
     u64 first;
     tile_lookup(g, tile, frame, local0, count, first);
     if (frame != cur_frame) {
-      if (cur_frame != 0xFFFFFFFFu) {
-        __syncthreads();
-        if (threadIdx.x < kNSect && smin[threadIdx.x] != 0xFFFFFFFFu)
-          atomicMin(&low_key[cur_frame * kSectStride + threadIdx.x], smin[threadIdx.x]);
-        __syncthreads();
-        if (threadIdx.x < kSectStride) smin[threadIdx.x] = 0xFFFFFFFFu;
-        __syncthreads();
-      }
+      __syncthreads();
+      if (cur_frame != 0xFFFFFFFFu && threadIdx.x < kNSect)
+        atomicMin(&low_key[cur_frame * kSectStride + threadIdx.x], smin[threadIdx.x]);
+      // seed from the frame's global table: the default and whatever other CTAs found so far
+      if (threadIdx.x < kSectStride)
+        smin[threadIdx.x] = threadIdx.x < kNSect
+                                ? ((volatile u32*)low_key)[frame * kSectStride + threadIdx.x] : 0u;
       cur_frame = frame;
     }
+    __syncthreads();
+    if (warp == 0) {
+      // quadrant q = (x<0) | (y<0)<<1 reaches sectors {0..4}, {4..8}, {12..16}, {8..12}
+      const u32 v = lane < kNSect ? smin[lane] : 0u;
+      const u32 ball = __reduce_max_sync(kFull, v);
+      const u32 b0 = __reduce_max_sync(kFull, lane <= 4 ? v : 0u);
+      const u32 b1 = __reduce_max_sync(kFull, (lane >= 4 && lane <= 8) ? v : 0u);
+      const u32 b2 = __reduce_max_sync(kFull, (lane >= 12 && lane <= 16) ? v : 0u);
+      const u32 b3 = __reduce_max_sync(kFull, (lane >= 8 && lane <= 12) ? v : 0u);
+      if (lane == 0) {
+        s_bound[0] = ball; s_bound[1] = b0; s_bound[2] = b1; s_bound[3] = b2; s_bound[4] = b3;
+      }
+    }
+    __syncthreads();
+    const u32 wbase = warp * (32 * kStreamRows);
     float4 p[kStreamRows];
 #pragma unroll
     for (int r = 0; r < kStreamRows; ++r) {
-      const u32 i = r * kStreamThreads + threadIdx.x;
-      p[r] = (i < count) ? load_point<MODE>(in, first + local0 + i, L) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const u32 i = wbase + r * 32 + lane;
+      // out-of-range lanes get z = +inf: key above every bound, skipped by the prefilter
+      p[r] = (i < count) ? load_point<MODE>(in, first + local0 + i, L)
+                         : make_float4(0.f, 0.f, __int_as_float(0x7f800000), 0.f);
     }
 #pragma unroll
     for (int r = 0; r < kStreamRows; ++r) {
-      const u32 i = r * kStreamThreads + threadIdx.x;
-      const float x = p[r].x, y = p[r].y, z = p[r].z;
-      const bool ok = (i < count) && isfinite(x) && isfinite(y) && isfinite(z);
-      int s = 31;  // parking slot for invalid lanes
-      u32 zk = 0xFFFFFFFFu;
-      if (ok) {
-        s = sector_of(x, y, atan2f(y, x));
-        zk = f2ord(z);
-      }
-      // warp-level min per distinct sector (scan-ordered clouds: 1-2 sectors per warp)
-      u32 todo = __ballot_sync(kFull, ok);
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        const int s0 = __shfl_sync(kFull, s, src);
-        const bool mine = ok && (s == s0);
-        const u32 m = __reduce_min_sync(kFull, mine ? zk : 0xFFFFFFFFu);
-        if (lane == src) atomicMin(&smin[s0], m);
-        todo &= ~__ballot_sync(kFull, mine);
+      const u32 zk = f2ord(p[r].z);
+      const float x = p[r].x, y = p[r].y;
+      // points on an axis (or with a vanishing product) use the all-sector bound
+      const u32 q = (x * y == 0.0f) ? 0u : 1u + (x < 0.0f ? 1u : 0u) + (y < 0.0f ? 2u : 0u);
+      if (zk < s_bound[q]) {
+        if (finite3(x, y, p[r].z)) {
+          bool ok;
+          const float a = atan2_approx(y, x, ok);
+          const int s = sector_of(x, y, a, ok);
+          if (zk < smin[s]) atomicMin(&smin[s], zk);   // src/ground_removal.cpp:65-67
+        }
       }
     }
   }
   __syncthreads();
-  if (cur_frame != 0xFFFFFFFFu && threadIdx.x < kNSect && smin[threadIdx.x] != 0xFFFFFFFFu)
+  if (cur_frame != 0xFFFFFFFFu && threadIdx.x < kNSect)
     atomicMin(&low_key[cur_frame * kSectStride + threadIdx.x], smin[threadIdx.x]);
 }
 
-// ---- pass 2: ground mask + crop + ordered compaction ------------------------------------
-struct CompactOut {
-  float4* pts;       // [cap] surviving points
-  u32* src;          // [cap] frame-local input index
-  u32* frame;        // [cap] frame id
-  u32 cap;
-  u32* c_off;        // [F+1] survivor offsets per frame
-  u32* bbox_key;     // [F*8] ordered-int min xyz (0..2) / max xyz (4..6)
-  u32* gcount;       // [F] ground survivors (when want_count)
-  u64* desc;         // [n_tiles] look-back descriptors
-  Ctl* ctl;
-  uint8_t* out32;    // node-equivalent output (PCL 32-byte layout) or NULL
-};
-
-__device__ __forceinline__ bool crop_keep(const CropK& c, float x, float y, float z, bool& need_angle) {
-  need_angle = false;
+// ---- pass 2: keep mask ------------------------------------------------------------------
+__device__ __forceinline__ bool crop_keep(const CropK& c, float x, float y, float z) {
   if (z < c.zthr) return false;
   const float sf = fmaf(z, z, fmaf(y, y, x * x));
   bool exact = !(sf < 1e30f);
@@ -215,157 +248,270 @@ __device__ __forceinline__ bool crop_keep(const CropK& c, float x, float y, floa
     const double xd = x, yd = y, zd = z;
     double s = __dadd_rn(__dmul_rn(xd, xd), __dmul_rn(yd, yd));
     s = __dadd_rn(s, __dmul_rn(zd, zd));
-    if (s >= c.smax || s < c.smin) return false;
-  } else {
-    if (sf >= c.smax_hi || sf <= c.smin_lo) return false;
+    return !(s >= c.smax || s < c.smin);
   }
-  need_angle = true;
-  return true;
+  return !(sf >= c.smax_hi || sf <= c.smin_lo);
 }
 
-template <int MODE, bool OUT32>
+struct MaskOut {
+  u32* mask;        // [n_tiles * 64] keep bits, word (tile, w*8 + r) covers points w*256 + r*32 .. +31
+  u32* tile_count;  // [n_tiles] survivors per tile (+1 on a frame's last tile when pad_survives)
+  u32* gcount;      // [F] ground survivors (when want_count)
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads)
-mask_crop_compact_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, GroundK gk,
-                         const u32* __restrict__ low_key, CompactOut o) {
+keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, GroundK gk,
+                 const u32* __restrict__ low_key, MaskOut o) {
   __shared__ float thr[kSectStride];
-  __shared__ u32 wtot[kStreamThreads / 32];
-  __shared__ u32 s_tile, s_excl;
+  __shared__ float s_thr_min;
+  __shared__ u32 wtot[kStreamWarps];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  while (true) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(&o.ctl->ticket[0], 1u);
-    __syncthreads();
-    const u32 tile = s_tile;
-    if (tile >= g.n_tiles) break;
+  const u32 per = (g.n_tiles + gridDim.x - 1) / gridDim.x;
+  const u32 t0 = blockIdx.x * per;
+  const u32 t1 = t0 + per < g.n_tiles ? t0 + per : g.n_tiles;
+  u32 cur_frame = 0xFFFFFFFFu;
+  for (u32 tile = t0; tile < t1; ++tile) {
     u32 frame, local0, count;
     u64 first;
     tile_lookup(g, tile, frame, local0, count, first);
-    if (gk.do_ground && threadIdx.x < kNSect) {
-      // :75  p.z < low + 0.1 in double  <=>  z < roundup_to_float((double)low + 0.1)
-      const double t = (double)ord2f(low_key[frame * kSectStride + threadIdx.x]) + 0.1;
-      thr[threadIdx.x] = __double2float_ru(t);
+    if (gk.do_ground && frame != cur_frame) {
+      __syncthreads();
+      if (warp == 0) {
+        // :75  p.z < low + 0.1 in double  <=>  z < roundup_to_float((double)low + 0.1)
+        float t = __int_as_float(0x7f800000);
+        if (lane < kNSect) {
+          t = __double2float_ru((double)ord2f(low_key[frame * kSectStride + lane]) + 0.1);
+          thr[lane] = t;
+        }
+#pragma unroll
+        for (int o2 = 16; o2; o2 >>= 1) t = fminf(t, __shfl_xor_sync(kFull, t, o2));
+        if (lane == 0) s_thr_min = t;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-
-    float4 p[kStreamRows];
-    u32 bal[kStreamRows];
-    u32 gkept = 0;
+    cur_frame = frame;
+    const float thr_min = gk.do_ground ? s_thr_min : -__int_as_float(0x7f800000);
     const u32 wbase = warp * (32 * kStreamRows);
+    float4 p[kStreamRows];
 #pragma unroll
     for (int r = 0; r < kStreamRows; ++r) {
       const u32 i = wbase + r * 32 + lane;
-      p[r] = (i < count) ? load_point<MODE>(in, first + local0 + i, L) : make_float4(0.f, 0.f, 0.f, 0.f);
+      p[r] = (i < count) ? load_point<MODE>(in, first + local0 + i, L)
+                         : make_float4(0.f, 0.f, -__int_as_float(0x7f800000), 0.f);  // z = -inf: dropped
     }
+    u32 wcount = 0, gkept = 0, myword = 0;
 #pragma unroll
     for (int r = 0; r < kStreamRows; ++r) {
       const u32 i = wbase + r * 32 + lane;
       const float x = p[r].x, y = p[r].y, z = p[r].z;
-      bool keep = (i < count) && isfinite(x) && isfinite(y) && isfinite(z);
-      bool need_angle = false;
-      if (keep && c.do_crop) keep = crop_keep(c, x, y, z, need_angle);
-      const bool need_sector = gk.do_ground && (keep || gk.want_count) && (i < count) &&
-                               isfinite(x) && isfinite(y) && isfinite(z);
-      if ((keep && need_angle) || need_sector) {
-        const float a_fast = atan2f(y, x);
-        if (keep && need_angle) {
-          const float aa = fabsf(a_fast);
-          if (aa > c.f_lo_guard) {
-            if (aa >= c.f_hi_guard) keep = false;
-            else keep = fabsf(atan2_exact(y, x)) < c.f_hi;  // src/cone_detection.cpp:200-201
+      bool keep = false;
+      // ground prefilter: below the lowest threshold of any sector => ground everywhere
+      // (without the per-frame count, points failing the crop need no ground verdict either)
+      if ((i < count) && !(z < thr_min) && finite3(x, y, z)) {
+        keep = !c.do_crop || crop_keep(c, x, y, z);
+        if (keep || gk.want_count) {
+          bool ok;
+          const float a = atan2_approx(y, x, ok);
+          if (keep && c.do_crop) {
+            const float aa = fabsf(a);
+            if (!ok | (aa > c.f_lo_guard)) {
+              if (ok & (aa >= c.f_hi_guard)) keep = false;
+              else keep = fabsf(atan2_exact(y, x)) < c.f_hi;  // src/cone_detection.cpp:200-201
+            }
+          }
+          if (gk.do_ground && (keep || gk.want_count)) {
+            const int s = sector_of(x, y, a, ok);
+            const bool gkeep = !(z < thr[s]);
+            if (gkeep) gkept++;
+            keep = keep && gkeep;
           }
         }
-        if (need_sector) {
-          const int s = sector_of(x, y, a_fast);
-          const bool gkeep = !(z < thr[s]);
-          if (gk.want_count && gkeep) gkept++;
-          keep = keep && gkeep;
-        }
       }
-      bal[r] = __ballot_sync(kFull, keep);
+      const u32 bal = __ballot_sync(kFull, keep);
+      wcount += __popc(bal);
+      if (lane == r) myword = bal;
     }
-    // ---- ranks: warp-contiguous rows => rank order == point order
-    u32 wcount = 0;
-    u32 rowoff[kStreamRows];
-#pragma unroll
-    for (int r = 0; r < kStreamRows; ++r) {
-      rowoff[r] = wcount;
-      wcount += __popc(bal[r]);
-    }
+    if (lane < kStreamRows) o.mask[(u64)tile * kTileWords + warp * kStreamRows + lane] = myword;
     if (lane == 0) wtot[warp] = wcount;
-    __syncthreads();
-    u32 wexcl = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kStreamThreads / 32; ++w) {
-      const u32 t = wtot[w];
-      if (w < warp) wexcl += t;
-      total += t;
-    }
-    const bool last_of_frame = (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]);
-    const u32 pad_rec = (gk.pad_survives && last_of_frame) ? 1u : 0u;
-    if (warp == 0) {
-      const u32 e = lookback_exclusive(o.desc, tile, total + pad_rec);
-      if (lane == 0) s_excl = e;
-    }
     if (gk.want_count) {
       const u32 gsum = __reduce_add_sync(kFull, gkept);
       if (lane == 0 && gsum) atomicAdd(&o.gcount[frame], gsum);
     }
     __syncthreads();
-    const u32 excl = s_excl;
     if (threadIdx.x == 0) {
-      if (last_of_frame) o.c_off[frame + 1] = excl + total + pad_rec;
-      if (tile == g.n_tiles - 1) o.ctl->n_surv = min(excl + total + pad_rec, o.cap);
-      if ((u64)excl + total + pad_rec > o.cap) atomicOr(&o.ctl->error, kErrSurvivors);
-    }
-    if (wcount) {
-      u32 mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0, mxy = 0, mxz = 0;
+      u32 total = 0;
 #pragma unroll
-      for (int r = 0; r < kStreamRows; ++r) {
-        if ((bal[r] >> lane) & 1u) {
-          const u32 pos = excl + wexcl + rowoff[r] + __popc(bal[r] & lanemask_lt());
-          const u32 i = wbase + r * 32 + lane;
-          if (pos < o.cap) {
-            if (OUT32) {
-              float4* dst = reinterpret_cast<float4*>(o.out32 + (u64)pos * 32);
-              dst[0] = make_float4(p[r].x, p[r].y, p[r].z, 1.0f);
-              dst[1] = make_float4(p[r].w, 0.f, 0.f, 0.f);
-            } else {
-              o.pts[pos] = p[r];
-              o.src[pos] = local0 + i;
-              o.frame[pos] = frame;
-            }
-          }
-          const u32 kx = f2ord(p[r].x), ky = f2ord(p[r].y), kz = f2ord(p[r].z);
-          mnx = min(mnx, kx); mxx = max(mxx, kx);
-          mny = min(mny, ky); mxy = max(mxy, ky);
-          mnz = min(mnz, kz); mxz = max(mxz, kz);
-        }
-      }
-      if (!OUT32) {
-        mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny);
-        mnz = __reduce_min_sync(kFull, mnz); mxx = __reduce_max_sync(kFull, mxx);
-        mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
-        if (lane == 0) {
-          u32* bb = o.bbox_key + frame * 8;
-          atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny); atomicMin(bb + 2, mnz);
-          atomicMax(bb + 4, mxx); atomicMax(bb + 5, mxy); atomicMax(bb + 6, mxz);
-        }
-      }
-    }
-    if (!OUT32 && pad_rec && threadIdx.x == 0) {
-      // one record stands for the N-G zero points appended by src/ground_removal.cpp:79;
-      // its multiplicity is applied when the voxel mean is taken
-      const u32 pos = excl + total;
-      if (pos < o.cap) {
-        o.pts[pos] = make_float4(0.f, 0.f, 0.f, 0.f);
-        o.src[pos] = 0xFFFFFFFFu;
-        o.frame[pos] = frame;
-      }
-      const u32 kz = f2ord(0.0f);
-      u32* bb = o.bbox_key + frame * 8;
-      atomicMin(bb + 0, kz); atomicMin(bb + 1, kz); atomicMin(bb + 2, kz);
-      atomicMax(bb + 4, kz); atomicMax(bb + 5, kz); atomicMax(bb + 6, kz);
+      for (int w = 0; w < kStreamWarps; ++w) total += wtot[w];
+      const bool last_of_frame = (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]);
+      o.tile_count[tile] = total + ((gk.pad_survives && last_of_frame) ? 1u : 0u);
     }
     __syncthreads();
+  }
+}
+
+// ---- exclusive scan of the tile counts ------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads)
+tile_scan_kernel(Geom g, const u32* __restrict__ tile_count, u32* __restrict__ tile_excl,
+                 u32* __restrict__ c_off, u64* desc, Ctl* ctl, u32 cap) {
+  __shared__ u32 wsum[kScanThreads / 32];
+  __shared__ u32 s_tile, s_excl;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const u32 stiles = (g.n_tiles + kScanTile - 1) / kScanTile;
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->ticket[0], 1u);
+    __syncthreads();
+    const u32 st = s_tile;
+    if (st >= stiles) break;
+    const u32 i0 = st * kScanTile + threadIdx.x * kScanItems;
+    u32 v[kScanItems], cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      v[j] = (i0 + j < g.n_tiles) ? tile_count[i0 + j] : 0u;
+      cnt += v[j];
+    }
+    u32 inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    u32 woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+      const u32 t = wsum[w];
+      if (w < warp) woff += t;
+      total += t;
+    }
+    if (warp == 0) {
+      const u32 e = lookback_exclusive(desc, st, total);
+      if (lane == 0) s_excl = e;
+    }
+    __syncthreads();
+    u32 run = s_excl + woff + inc - cnt;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      const u32 t = i0 + j;
+      if (t < g.n_tiles) {
+        tile_excl[t] = run;
+        run += v[j];
+        // a frame's last tile publishes the frame's end offset
+        u32 frame, nt;
+        if (g.uniform_n) {
+          frame = t / g.tpf;
+          nt = (t + 1 == (frame + 1) * g.tpf);
+        } else {
+          frame = g.tile_frame[t];
+          nt = (t + 1 == g.n_tiles) || (g.tile_frame[t + 1] != frame);
+        }
+        if (nt) c_off[frame + 1] = run;
+        if (t + 1 == g.n_tiles) {
+          ctl->n_surv = run < cap ? run : cap;
+          if (run > cap) atomicOr(&ctl->error, kErrSurvivors);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- ordered gather of the survivors --------------------------------------------------------
+struct GatherOut {
+  float4* pts;       // [cap] surviving points
+  u32* src;          // [cap] frame-local input index
+  u32* frame;        // [cap] frame id
+  u32 cap;
+  u32* bbox_key;     // [F*8] ordered-int min xyz (0..2) / max xyz (4..6)
+  uint8_t* out32;    // node-equivalent output (PCL 32-byte layout) or NULL
+};
+
+// one warp per tile: lane l owns keep words l and l+32 of the tile
+template <int MODE, bool OUT32>
+__global__ void __launch_bounds__(256)
+gather_survivors_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, GroundK gk,
+                        const u32* __restrict__ mask, const u32* __restrict__ tile_count,
+                        const u32* __restrict__ tile_excl, GatherOut o) {
+  const int lane = lane_id();
+  const u32 warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < g.n_tiles; tile += warps) {
+    const u32 tc = tile_count[tile];
+    if (tc == 0) continue;
+    u32 frame, local0, count;
+    u64 first;
+    tile_lookup(g, tile, frame, local0, count, first);
+    const u32 excl = tile_excl[tile];
+    const u32 w0 = mask[(u64)tile * kTileWords + lane], w1 = mask[(u64)tile * kTileWords + 32 + lane];
+    const u32 c0 = __popc(w0), c1 = __popc(w1);
+    u32 i0 = c0, i1 = c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 a = __shfl_up_sync(kFull, i0, d), b = __shfl_up_sync(kFull, i1, d);
+      if (lane >= d) {
+        i0 += a;
+        i1 += b;
+      }
+    }
+    const u32 tot0 = __shfl_sync(kFull, i0, 31), tot1 = __shfl_sync(kFull, i1, 31);
+    u32 mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0, mxy = 0, mxz = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      u32 w = half ? w1 : w0;
+      u32 pos = excl + (half ? tot0 + i1 - c1 : i0 - c0);
+      const u32 pbase = (half ? 32 + lane : lane) * 32;  // first point of this word within the tile
+      while (w) {
+        const int b = __ffs(w) - 1;
+        w &= w - 1;
+        const u32 i = pbase + b;
+        const float4 p = load_point<MODE>(in, first + local0 + i, L);
+        if (pos < o.cap) {
+          if (OUT32) {
+            float4* dst = reinterpret_cast<float4*>(o.out32 + (u64)pos * 32);
+            dst[0] = make_float4(p.x, p.y, p.z, 1.0f);
+            dst[1] = make_float4(p.w, 0.f, 0.f, 0.f);
+          } else {
+            o.pts[pos] = p;
+            o.src[pos] = local0 + i;
+            o.frame[pos] = frame;
+          }
+        }
+        ++pos;
+        const u32 kx = f2ord(p.x), ky = f2ord(p.y), kz = f2ord(p.z);
+        mnx = min(mnx, kx); mxx = max(mxx, kx);
+        mny = min(mny, ky); mxy = max(mxy, ky);
+        mnz = min(mnz, kz); mxz = max(mxz, kz);
+      }
+    }
+    if (!OUT32) {
+      const bool last_of_frame = (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]);
+      if (gk.pad_survives && last_of_frame && lane == 0) {
+        // one record stands for the N-G zero points appended by src/ground_removal.cpp:79;
+        // its multiplicity is applied when the voxel mean is taken
+        const u32 pos = excl + tot0 + tot1;
+        if (pos < o.cap) {
+          o.pts[pos] = make_float4(0.f, 0.f, 0.f, 0.f);
+          o.src[pos] = 0xFFFFFFFFu;
+          o.frame[pos] = frame;
+        }
+        const u32 kz = f2ord(0.0f);
+        mnx = min(mnx, kz); mxx = max(mxx, kz);
+        mny = min(mny, kz); mxy = max(mxy, kz);
+        mnz = min(mnz, kz); mxz = max(mxz, kz);
+      }
+      mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny);
+      mnz = __reduce_min_sync(kFull, mnz); mxx = __reduce_max_sync(kFull, mxx);
+      mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
+      if (lane == 0) {
+        u32* bb = o.bbox_key + frame * 8;
+        atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny); atomicMin(bb + 2, mnz);
+        atomicMax(bb + 4, mxx); atomicMax(bb + 5, mxy); atomicMax(bb + 6, mxz);
+      }
+    }
   }
 }
 

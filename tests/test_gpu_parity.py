@@ -6,7 +6,7 @@ from cones_perception_b200 import api, scans
 from cones_perception_b200.params import PRESETS, GroundParams
 from cones_perception_b200.pointcloud2 import PointCloud2
 from oracle import oracle as O
-from tests.util import assert_frame_parity, oracle_stages, run_batch_with_taps
+from tests.util import assert_frame_parity, boundary_cloud, oracle_stages, run_batch_with_taps
 
 pytestmark = pytest.mark.gpu
 
@@ -104,3 +104,33 @@ def test_adversarial_config5(gpu):
     assert sizes.max() > 5000, "the serpentine chain should form one deep component"
     assert (clusters["size"] == cfg.detect.max_cluster_size).any(), "the exactly-max component must be kept"
     assert not (clusters["size"] > cfg.detect.max_cluster_size).any()
+
+
+@pytest.mark.parametrize("preset", ["our", "fsai", "simulation"])
+@pytest.mark.parametrize("ground", [False, True])
+def test_threshold_boundary_points_bit_exact(gpu, preset, ground):
+    """Every guard-band fallback: points on / within ulps of each threshold must get the oracle's verdict."""
+    d = PRESETS[preset]
+    g = GroundParams() if ground else None
+    frame = boundary_cloud(d, seed={"our": 1, "fsai": 2, "simulation": 3}[preset])
+    ora = oracle_stages(frame, d, g)
+    ctr, k_off, clusters, offs, taps = run_batch_with_taps(gpu, [frame], d, g)
+    if ground:
+        assert np.array_equal(taps["low"][0].view(np.uint32), ora["low"].view(np.uint32)), "sector minima differ"
+    assert_frame_parity(gpu, 0, ora, offs, taps, ctr, k_off, clusters)
+
+
+def test_golden_fixtures_on_gpu(gpu):
+    import hashlib
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    for idx, seed in ((1, 0), (2, 0), (2, 7), (4, 0), (5, 0)):
+        z = np.load(os.path.join(gold, f"cfg{idx}_seed{seed}_golden.npz"))
+        cfg = scans.config(idx)
+        frame = scans.generate_config5(1, seed)[0] if idx == 5 else scans.generate(cfg, 1, seed)[0]
+        assert hashlib.sha256(frame.tobytes()).hexdigest() == str(z["input_sha256"])
+        with api.ConesGpu(max_points=len(frame), max_frames=1) as h:
+            cl, ctr = h.detect(PointCloud2.from_xyzi(frame), cfg.detect, cfg.ground, cap=1 << 16)
+        assert np.array_equal(cl.view(np.uint32), z["clusters"].view(np.uint32)), f"cfg{idx} seed {seed}"
+        assert [int(ctr["n_cropped"]), int(ctr["n_voxels"]), int(ctr["n_components"]), int(ctr["n_clusters"]),
+                int(ctr["key_bits"])] == z["counters"].tolist()[2:]

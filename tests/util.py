@@ -95,3 +95,53 @@ def run_batch_with_taps(gpu: "api.ConesGpu", frames: list, d, g):
     if g is not None:
         taps["low"] = gpu.tap(api.TAP_SECTOR_LOW).reshape(-1, 17)
     return ctr, k_off, clusters, offs, taps
+
+
+def boundary_cloud(d, seed: int = 0, n_random: int = 20000) -> np.ndarray:
+    """Points placed on and within a few ulp of every threshold of the path: sector boundaries,
+    +-angle_threshold, the +-x / +-y axes, distance_treshold_min/max, level_threshold, plus signed
+    zeros, denormals, huge and non-finite values.  Used to prove the guard-band fallbacks exact."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    sa = np.float32((360 // 16) * np.pi / 180)
+    theta = d.angle_threshold * np.pi / 180
+    angles = [k * float(sa) for k in range(0, 18)] + [theta, -theta, np.pi, -np.pi, np.pi / 2, -np.pi / 2, 0.0,
+                                                        2 * np.pi - 1e-7]
+    for a in angles:
+        for eps in (0.0, 1e-8, -1e-8, 1e-7, -1e-7, 5e-7, -5e-7, 2e-6, -2e-6, 9e-6, -9e-6, 3e-5, -3e-5):
+            for r in (0.9, 1.7, 3.3, 6.9, 9.7):
+                z = rng.choice([-0.6, -0.601, -0.5, -0.45, 0.0, 0.3])
+                rows.append([r * np.cos(a + eps), r * np.sin(a + eps), z])
+    # exact axis points and signed zeros
+    for x, y in [(1, 0.0), (1, -0.0), (-1, 0.0), (-1, -0.0), (0.0, 1), (-0.0, 1), (0.0, -1), (-0.0, -1), (0.0, 0.0),
+                 (-0.0, 0.0), (0.0, -0.0), (-0.0, -0.0), (1e-40, 1e-40), (-1e-40, 2e-39), (3, 1e-42), (3, -1e-42),
+                 (1e-20, 5), (-1e-20, 5), (2, 1e-9), (2, -1e-9), (-2, 1e-9), (-2, -1e-9)]:
+        for z in (-0.7, -0.2, 0.1):
+            rows.append([x * 2.5, y * 2.5, z])
+    # distances within a few ulp of dmin / dmax along assorted directions
+    for dist in (d.distance_treshold_min, d.distance_treshold_max):
+        for _ in range(400):
+            v = rng.normal(size=3)
+            v[2] = abs(v[2]) * 0.2
+            v /= np.linalg.norm(v)
+            for k in (-3, -2, -1, 0, 1, 2, 3):
+                rows.append(list(v * dist * (1.0 + k * 2.0 ** -24)))
+    # level threshold +- ulps
+    lv = np.float32(d.level_threshold)
+    for zz in (lv, np.nextafter(lv, np.float32(-100)), np.nextafter(lv, np.float32(100))):
+        for _ in range(20):
+            rows.append([rng.uniform(1.5, 5), rng.uniform(-2, 2), zz])
+    # extreme magnitudes and non-finite values
+    rows += [[1e30, 1.0, 0.0], [3e38, 3e38, 0.0], [1e-30, 1e-30, 0.1], [np.inf, 1, 0], [1, -np.inf, 0], [1, 1, np.inf],
+             [np.nan, 1, 0], [1, np.nan, 0], [1, 1, np.nan], [1, 1, -np.inf], [-np.nan, 2, -0.7]]
+    a = np.array(rows, np.float64)
+    # random background incl. a ground sheet so every sector has a low minimum
+    bg = np.stack([rng.uniform(-9, 9, n_random), rng.uniform(-9, 9, n_random),
+                   np.where(rng.random(n_random) < 0.7, -0.6 + rng.normal(0, 0.002, n_random),
+                            rng.uniform(-0.55, 1.0, n_random))], 1)
+    a = np.concatenate([a, bg])
+    rng.shuffle(a)
+    out = np.zeros((len(a), 4), np.float32)
+    out[:, :3] = a.astype(np.float32)
+    out[:, 3] = rng.uniform(0, 100, len(a))
+    return out
