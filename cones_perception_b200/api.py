@@ -99,17 +99,20 @@ class ConesGpu:
     """Owner of one cp_handle (one CUDA device, one stream, used by one thread at a time)."""
 
     def __init__(self, max_points: int, max_frames: int = 1, device: int = 0, max_point_step: int = 16,
-                 max_survivors: int = 0, max_voxels: int = 0, taps: bool = False):
+                 max_survivors: int = 0, max_voxels: int = 0, taps: bool = False, back_mode: int | None = None):
         self.lib = load_library()
         self._h = C.c_void_p()
         if taps:
             os.environ["CONESGPU_TAPS"] = "1"
+        if back_mode is not None:   # tests: 0/1 shared-memory back half, 2 general global-memory path
+            os.environ["CONESGPU_BACK_MODE"] = str(back_mode)
         try:
             cfg = CConfig(device, max_points, max_frames, max_point_step, max_survivors, max_voxels)
             st = self.lib.cp_create(C.byref(self._h), C.byref(cfg))
         finally:
             if taps:
                 os.environ.pop("CONESGPU_TAPS", None)
+            os.environ.pop("CONESGPU_BACK_MODE", None)
         if st != CP_OK:
             raise ConesGpuError(st, self.lib.cp_create_error().decode())
         self.max_points, self.max_frames = max_points, max_frames

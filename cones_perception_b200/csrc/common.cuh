@@ -29,6 +29,10 @@ struct Ctl {
   u32 hash_mask;       // live hash capacity - 1
   u32 error;           // sticky capacity / internal error bits
   u32 ticket[4];       // dynamic tile tickets
+  u32 fast_overflow;   // frames the shared-memory back half could not hold
+  u32 fast_max_c;      // largest per-frame survivor count seen by it
+  u32 fast_max_v;      // largest per-frame voxel count seen by it
+  u32 pad0;
 };
 
 enum : u32 { kErrSurvivors = 1u, kErrVoxels = 2u, kErrHash = 4u, kErrInternal = 8u };

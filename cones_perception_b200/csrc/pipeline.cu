@@ -14,6 +14,7 @@
 
 #include "cluster_kernels.cuh"
 #include "common.cuh"
+#include "frame_kernels.cuh"
 #include "radix_sort.cuh"
 #include "stream_kernels.cuh"
 #include "voxel_kernels.cuh"
@@ -36,6 +37,15 @@ struct HostGeom {
 
 }  // namespace
 
+// parameters of the run in flight (kept so cp_sync can re-run the back half in another mode)
+struct RunParams {
+  cp_detect_params d;
+  VoxelK vk;
+  ClusterK ck;
+  GroundK gk;
+  u32 csort_bits, osort_bits;
+};
+
 struct cp_handle {
   cp_config cfg{};
   int sms = 148;
@@ -47,6 +57,10 @@ struct cp_handle {
   u32 launches = 0;
   bool batch_ready = false, ran = false;
   bool taps = false, counted_ground = false, ran_ground = false;
+  int back_mode = 0;  // 0: fast (2048/1024 per frame), 1: fast (4096/2048), 2: general
+  RunParams rp{};
+  u64 *d_desc_fv = nullptr, *d_desc_fk = nullptr;
+  u32* d_frame_ticket = nullptr;
 
   u64 cap_c = 0, cap_v = 0;
   u32 tiles_cap = 0, sort_tiles_cap = 0, hash_cap = 0;
@@ -455,6 +469,8 @@ void launch_init(cp_handle* h, float default_low) {
   init_kernel<<<h->sms * 2, 256, 0, h->stream>>>(h->d_ctl, h->hg.n_frames, default_low, h->d_low_key, h->d_bbox,
                                                  h->d_c_off, h->d_gcount, h->d_ncomp_f, h->d_kcount_f,
                                                  h->d_desc_a, h->hg.n_tiles, h->d_desc_b, h->d_desc_c, h->d_desc_d, nb);
+  cudaMemsetAsync(h->d_desc_fv, 0, sizeof(u64) * h->hg.n_frames, h->stream);
+  cudaMemsetAsync(h->d_desc_fk, 0, sizeof(u64) * h->hg.n_frames, h->stream);
   h->launches++;
 }
 
@@ -472,53 +488,27 @@ SortArgs sort_args(cp_handle* h, bool order_sort, const u32* d_n, const u32* d_b
   return a;
 }
 
-cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_ground_params* ground) {
-  if (!d) {
-    h->err = "NULL detect params";
-    return CP_E_PARAM;
+__global__ void back_reset_kernel(Ctl* ctl, u32 n_frames, u32* ncomp_f, u32* kcount_f) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) {
+    ctl->n_vox = ctl->n_cells = ctl->n_comp = ctl->n_clusters = 0;
+    ctl->voxel_key_bits = 0;
+    ctl->fast_overflow = 0;
+    ctl->error &= kErrSurvivors;
   }
-  if (!h->batch_ready) {
-    h->err = "no batch input set";
-    return CP_E_STATE;
+  for (u32 i = t; i < n_frames; i += gridDim.x * blockDim.x) {
+    ncomp_f[i] = 0;
+    kcount_f[i] = 0;
   }
-  const float leaf[3] = {(float)d->voxel_filter_leaf_size_x, (float)d->voxel_filter_leaf_size_y,
-                         (float)d->voxel_filter_leaf_size_z};
-  for (int a = 0; a < 3; ++a)
-    if (!(leaf[a] > 0.0f) || !isfinite(leaf[a])) {
-      h->err = "voxel_filter_leaf_size_* must be positive and finite";
-      return CP_E_PARAM;
-    }
-  CropK crop;
-  cp_status st = make_crop(h, d, &crop);
-  if (st) return st;
-  ClusterK ck;
-  u32 csort_bits = 0, osort_bits = 0;
-  st = make_cluster(h, d, h->hg.n_frames, &ck, &csort_bits, &osort_bits);
-  if (st) return st;
-  GroundK gk;
-  gk.do_ground = ground ? 1 : 0;
-  gk.pad_survives = (ground && zero_point_survives(d)) ? 1 : 0;
-  gk.want_count = gk.pad_survives;
-  h->counted_ground = gk.want_count != 0;
-  VoxelK vk;
-  for (int a = 0; a < 3; ++a) vk.inv[a] = 1.0f / leaf[a];
-  vk.frame_bits = ceil_log2_host(h->hg.n_frames);
+}
 
-  const Geom g = device_geom(h);
+// general back half: global-memory kernels, any frame size
+void enqueue_back_general(cp_handle* h, const RunParams& rp) {
+  const cp_detect_params* d = &rp.d;
+  const VoxelK& vk = rp.vk;
+  const ClusterK& ck = rp.ck;
+  const u32 csort_bits = rp.csort_bits, osort_bits = rp.osort_bits;
   const u32 F = h->hg.n_frames;
-  h->launches = 0;
-  cudaEventRecord(h->ev0, h->stream);
-  launch_init(h, ground ? ground->default_lowest_point : 0.0f);
-  const u32 sgrid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, 8);
-  if (ground) {
-    if (h->stage_timing) cudaEventRecord(h->ev_k[0], h->stream);
-    launch_sector_min(h, g, sgrid);
-    if (h->stage_timing) cudaEventRecord(h->ev_k[1], h->stream);
-    h->launches++;
-  }
-  launch_front_pass2<false>(h, g, crop, gk, (u32)h->cap_c, nullptr, sgrid);
-  h->ran_ground = ground != nullptr;
-
   // ---- VoxelGrid
   const u32 fgrid = (F + 255) / 256;
   voxel_setup_kernel<<<fgrid, 256, 0, h->stream>>>(F, vk, h->d_bbox, h->d_c_off, h->d_vf, h->d_ctl);
@@ -639,9 +629,123 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
                                                       h->d_tap_labels);
     h->launches++;
   }
+}
+
+// fast back half: one CTA per frame in shared memory (frame_kernels.cuh)
+template <int CMAX, int VMAX>
+void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
+  FrameArgs fa;
+  fa.n_frames = h->hg.n_frames;
+  fa.c_off = h->d_c_off;
+  fa.pts = h->d_pts;
+  fa.src = h->d_src;
+  fa.bbox_key = h->d_bbox;
+  fa.frame_n = h->d_frame_n;
+  fa.uniform_n = h->hg.uniform_n;
+  fa.gcount = h->d_gcount;
+  fa.pad_survives = rp.gk.pad_survives;
+  fa.vk = rp.vk;
+  fa.ck = rp.ck;
+  fa.vf = h->d_vf;
+  fa.v_off = h->d_v_off;
+  fa.k_off = h->d_k_off;
+  fa.ncomp_f = h->d_ncomp_f;
+  fa.kcount_f = h->d_kcount_f;
+  fa.clusters = h->d_clusters;
+  fa.clusters_cap = (u32)h->cap_v;
+  fa.desc_v = h->d_desc_fv;
+  fa.desc_k = h->d_desc_fk;
+  fa.ctl = h->d_ctl;
+  fa.ticket = h->d_frame_ticket;
+  cudaMemsetAsync(h->d_frame_ticket, 0, sizeof(u32), h->stream);
+  fa.tap_vox = h->taps ? h->d_vox : nullptr;
+  fa.tap_vox_cap = (u32)h->cap_v;
+  fa.tap_keys = h->taps ? h->d_tap_keys : nullptr;
+  fa.tap_order = h->taps ? h->d_tap_order : nullptr;
+  fa.tap_labels = h->taps ? h->d_tap_labels : nullptr;
+  const size_t smem = sizeof(FrameSmem<CMAX, VMAX>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(frame_backend_kernel<CMAX, VMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const u32 per_sm = (u32)std::max<size_t>(1, std::min<size_t>(4, (220u << 10) / (smem + 1024)));
+  const u32 grid = std::min<u32>(fa.n_frames, (u32)h->sms * per_sm);
+  frame_backend_kernel<CMAX, VMAX><<<grid, kFrameThreads, smem, h->stream>>>(fa);
+  h->launches++;
+}
+
+cp_status enqueue_back(cp_handle* h, bool retry) {
+  const RunParams& rp = h->rp;
+  if (retry) {
+    back_reset_kernel<<<h->sms, 256, 0, h->stream>>>(h->d_ctl, h->hg.n_frames, h->d_ncomp_f, h->d_kcount_f);
+    CK(cudaMemsetAsync(h->d_desc_fv, 0, sizeof(u64) * h->hg.n_frames, h->stream));
+    CK(cudaMemsetAsync(h->d_desc_fk, 0, sizeof(u64) * h->hg.n_frames, h->stream));
+    h->launches++;
+  }
+  if (h->back_mode == 0) enqueue_back_fast<2048, 1024>(h, rp);
+  else if (h->back_mode == 1) enqueue_back_fast<4096, 2048>(h, rp);
+  else enqueue_back_general(h, rp);
   cudaEventRecord(h->ev1, h->stream);
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaGetLastError());
+  return CP_OK;
+}
+
+cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_ground_params* ground) {
+  if (!d) {
+    h->err = "NULL detect params";
+    return CP_E_PARAM;
+  }
+  if (!h->batch_ready) {
+    h->err = "no batch input set";
+    return CP_E_STATE;
+  }
+  const float leaf[3] = {(float)d->voxel_filter_leaf_size_x, (float)d->voxel_filter_leaf_size_y,
+                         (float)d->voxel_filter_leaf_size_z};
+  for (int a = 0; a < 3; ++a)
+    if (!(leaf[a] > 0.0f) || !isfinite(leaf[a])) {
+      h->err = "voxel_filter_leaf_size_* must be positive and finite";
+      return CP_E_PARAM;
+    }
+  CropK crop;
+  cp_status st = make_crop(h, d, &crop);
+  if (st) return st;
+  ClusterK ck;
+  u32 csort_bits = 0, osort_bits = 0;
+  st = make_cluster(h, d, h->hg.n_frames, &ck, &csort_bits, &osort_bits);
+  if (st) return st;
+  GroundK gk;
+  gk.do_ground = ground ? 1 : 0;
+  gk.pad_survives = (ground && zero_point_survives(d)) ? 1 : 0;
+  gk.want_count = gk.pad_survives;
+  h->counted_ground = gk.want_count != 0;
+  VoxelK vk;
+  for (int a = 0; a < 3; ++a) vk.inv[a] = 1.0f / leaf[a];
+  vk.frame_bits = ceil_log2_host(h->hg.n_frames);
+
+  const Geom g = device_geom(h);
+  const u32 F = h->hg.n_frames;
+  h->launches = 0;
+  cudaEventRecord(h->ev0, h->stream);
+  launch_init(h, ground ? ground->default_lowest_point : 0.0f);
+  const u32 sgrid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, 8);
+  if (ground) {
+    if (h->stage_timing) cudaEventRecord(h->ev_k[0], h->stream);
+    launch_sector_min(h, g, sgrid);
+    if (h->stage_timing) cudaEventRecord(h->ev_k[1], h->stream);
+    h->launches++;
+  }
+  launch_front_pass2<false>(h, g, crop, gk, (u32)h->cap_c, nullptr, sgrid);
+  h->ran_ground = ground != nullptr;
+  h->rp.d = *d;
+  h->rp.vk = vk;
+  h->rp.ck = ck;
+  h->rp.gk = gk;
+  h->rp.csort_bits = csort_bits;
+  h->rp.osort_bits = osort_bits;
+  st = enqueue_back(h, false);
+  if (st) return st;
   h->ran = true;
   return CP_OK;
 }
@@ -776,6 +880,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   }
   const char* tap_env = getenv("CONESGPU_TAPS");
   h->taps = tap_env && tap_env[0] == '1';
+  const char* mode_env = getenv("CONESGPU_BACK_MODE");  // tests: force the back-half variant
+  if (mode_env && mode_env[0] >= '0' && mode_env[0] <= '2') h->back_mode = mode_env[0] - '0';
   const u64 P = cfg->max_points;
   const u32 F = cfg->max_frames;
   h->cap_c = cfg->max_survivors ? std::min<u64>(cfg->max_survivors, P + F) : P + F;
@@ -831,6 +937,9 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   A(dalloc(h, &h->d_hvals, h->hash_cap));
   A(dalloc(h, &h->d_clusters, h->cap_v));
   A(dalloc(h, &h->d_desc_a, h->tiles_cap));
+  A(dalloc(h, &h->d_frame_ticket, 1));
+  A(dalloc(h, &h->d_desc_fv, F));
+  A(dalloc(h, &h->d_desc_fk, F));
   A(dalloc(h, &h->d_mask, (size_t)h->tiles_cap * kTileWords));
   A(dalloc(h, &h->d_tile_count, h->tiles_cap));
   A(dalloc(h, &h->d_tile_excl, h->tiles_cap));
@@ -957,8 +1066,17 @@ cp_status cp_sync(cp_handle* h) {
   if (!h) return CP_E_PARAM;
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  if (h->ran) return device_errors(h);
-  return CP_OK;
+  if (!h->ran) return CP_OK;
+  // the shared-memory back half reports frames it could not hold: pick the next variant
+  // (bigger shared-memory budget, then the general global-memory path) and redo the back half
+  while (h->back_mode < 2 && h->h_ctl->fast_overflow != 0 && !(h->h_ctl->error & kErrSurvivors)) {
+    h->back_mode = (h->back_mode == 0 && h->h_ctl->fast_max_c <= 4096 && h->h_ctl->fast_max_v <= 2048) ? 1 : 2;
+    cp_status st = enqueue_back(h, true);
+    if (st) return st;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+  }
+  return device_errors(h);
 }
 
 cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* cluster_offsets, cp_cluster* out,

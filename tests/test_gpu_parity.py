@@ -11,9 +11,11 @@ from tests.util import assert_frame_parity, boundary_cloud, oracle_stages, run_b
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def gpu():
-    g = api.ConesGpu(max_points=1 << 22, max_frames=64, taps=True)
+@pytest.fixture(scope="module", params=["fast", "general"])
+def gpu(request):
+    """Both back-half variants: the per-frame shared-memory kernel (which falls back to the
+    general path on frames it cannot hold) and the general global-memory path forced on."""
+    g = api.ConesGpu(max_points=1 << 22, max_frames=64, taps=True, back_mode=0 if request.param == "fast" else 2)
     yield g
     g.close()
 
