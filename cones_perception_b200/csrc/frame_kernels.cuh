@@ -274,11 +274,20 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
         }
       }
       __syncthreads();
-      // ---- S5: connected components of "L2_Simple(i,j) < r2" — all pairs, warp per row
+      // ---- S5: connected components of "L2_Simple(i,j) < r2" — all pairs, warp per row.
+      // A warp resolves a row cooperatively: roots of all hits, one warp-wide minimum, and a
+      // CAS only for roots that still differ (rare once a component has formed).
       for (u32 i = warp + 1; i < V; i += kFrameThreads / 32) {
         const float xi = s.vx[i], yi = s.vy[i], zi = s.vz[i];
-        for (u32 j = lane; j < i; j += 32) {
-          if (l2_simple(xi, yi, zi, s.vx[j], s.vy[j], s.vz[j]) < a.ck.r2) smem_union(s.parent, i, j);
+        for (u32 base = 0; base < i; base += 32) {
+          const u32 j = base + lane;
+          const bool hit = j < i && l2_simple(xi, yi, zi, s.vx[j], s.vy[j], s.vz[j]) < a.ck.r2;
+          if (!__any_sync(kFull, hit)) continue;
+          const u32 rj = hit ? smem_find(s.parent, j) : 0xFFFFFFFFu;
+          const u32 ri = smem_find(s.parent, i);
+          const u32 m = min(__reduce_min_sync(kFull, rj), ri);
+          if (hit && rj != m && atomicCAS(&s.parent[rj], rj, m) != rj) smem_union(s.parent, rj, m);
+          if (lane == 0 && ri != m && atomicCAS(&s.parent[ri], ri, m) != ri) smem_union(s.parent, ri, m);
         }
       }
       __syncthreads();
@@ -333,33 +342,42 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
       }
     }
     __syncthreads();
-    // ---- S8/S9: centroid (src/cone_detection.cpp:261-273) and canonical rank per kept cluster
+    // ---- S8/S9: centroid (src/cone_detection.cpp:261-273) and canonical rank, warp per cluster.
+    // Lanes find the members 32 voxels at a time; the fp32 sums stay sequential in ascending
+    // voxel index (every lane carries the same running sum).
     if (K > 0) {
       const u32 k_excl = s.k_excl;
-      for (u32 k = tid; k < K; k += kFrameThreads) {
+      for (u32 k = warp; k < K; k += kFrameThreads / 32) {
         const u32 root = s.vstart[k];
         const u32 size = s.csize[root];
         float x = 0.0f, y = 0.0f;
         u32 seen = 0;
-        for (u32 v = root; v < V && seen < size; ++v) {
-          if (s.label[v] == root) {
-            x = __fadd_rn(x, s.vx[v]);
-            y = __fadd_rn(y, s.vy[v]);
-            ++seen;
+        for (u32 base = root; base < V && seen < size; base += 32) {
+          const u32 v = base + lane;
+          u32 members = __ballot_sync(kFull, v < V && s.label[v] == root);
+          seen += __popc(members);
+          while (members) {
+            const u32 m = base + (u32)__ffs(members) - 1u;
+            members &= members - 1;
+            x = __fadd_rn(x, s.vx[m]);
+            y = __fadd_rn(y, s.vy[m]);
           }
         }
         u32 rank = 0;  // size descending, then min index ascending (kept roots are ascending)
-        for (u32 q = 0; q < K; ++q) {
+        for (u32 q = lane; q < K; q += 32) {
           const u32 sq = s.csize[s.vstart[q]];
           rank += (sq > size || (sq == size && q < k)) ? 1u : 0u;
         }
-        const float cnt = (float)(i32)size;
-        ClusterRec o;
-        o.x = __fdiv_rn(x, cnt);
-        o.y = __fdiv_rn(y, cnt);
-        o.size = size;
-        o.min_index = root;
-        if (k_excl + rank < a.clusters_cap) a.clusters[k_excl + rank] = o;
+        rank = __reduce_add_sync(kFull, rank);
+        if (lane == 0) {
+          const float cnt = (float)(i32)size;
+          ClusterRec o;
+          o.x = __fdiv_rn(x, cnt);
+          o.y = __fdiv_rn(y, cnt);
+          o.size = size;
+          o.min_index = root;
+          if (k_excl + rank < a.clusters_cap) a.clusters[k_excl + rank] = o;
+        }
       }
     }
   }
