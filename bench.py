@@ -167,9 +167,13 @@ def run_ours(args):
 
     from cones_perception_b200 import api
     from cones_perception_b200.pointcloud2 import PointCloud2, make_view, CCloudView
-    from cones_perception_b200.sharding import gather_cone_lists
+    from cones_perception_b200.sharding import gather_cone_lists, pack_words
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # exactly one line may reach stdout (the JSON): park stdout on stderr while libraries (NCCL
+    # version banners, torchrun notices) are chatty, print the line on the real stdout at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
@@ -196,14 +200,37 @@ def run_ours(args):
     gpu.set_device_input(dev.data_ptr(), frame_points, keep=dev)
     cone_cap = F * CONE_CAP_PER_FRAME
 
+    # result path when N > 1: the rank's packed cone list (offsets + records, one device block)
+    # is copied to a staging buffer on the compute stream and gathered to rank 0 with ONE
+    # all_gather on a side stream, overlapping the next step's kernels (KB-scale, latency-bound)
+    words = pack_words(F, cone_cap)
+    comm = torch.cuda.Stream() if world > 1 else None
+    stage = [torch.empty(words, dtype=torch.int32, device="cuda") for _ in range(2)] if world > 1 else None
+    stage_free = [None, None]
+    gathered = [None]
+    step_no = [0]
+
     def step_device():
         gpu.run(d, g)
         if world > 1:
-            d_cl, d_off, _ = gpu.device_results()
+            i = step_no[0] & 1
+            step_no[0] += 1
+            _, d_off, _ = gpu.device_results()
+            if stage_free[i] is not None:
+                ext.wait_event(stage_free[i])       # the gather that last used this buffer is done
             with torch.cuda.stream(ext):
-                off = torch.as_tensor(_DevArray(d_off, (F + 1,)), device="cuda")
-                cones = torch.as_tensor(_DevArray(d_cl, (cone_cap, 4)), device="cuda")
-                gather_cone_lists(off[1:] - off[:-1], cones, cone_cap)
+                stage[i].copy_(torch.as_tensor(_DevArray(d_off, (words,)), device="cuda"))
+            ready = torch.cuda.Event()
+            ready.record(ext)
+            comm.wait_event(ready)
+            with torch.cuda.stream(comm):
+                gathered[0] = gather_cone_lists(stage[i])
+                stage_free[i] = torch.cuda.Event()
+                stage_free[i].record(comm)
+
+    def drain():
+        if world > 1:
+            ext.wait_stream(comm)
 
     def barrier():
         if world > 1:
@@ -212,7 +239,9 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_device()
+    drain()
     gpu.sync()
+    torch.cuda.synchronize()
     ctr, k_off, clusters = gpu.results()
     launches_per_step = gpu.last_launch_count()
 
@@ -225,10 +254,19 @@ def run_ours(args):
     e0.record(ext)
     for _ in range(args.steps):
         step_device()
+    drain()
     e1.record(ext)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     gpu.sync()
+    if world > 1 and rank == 0:
+        # the gathered list must hold every rank's frames; rank 0's block must equal its own results
+        from cones_perception_b200.sharding import unpack_gathered
+        per_frame = unpack_gathered(gathered[0].cpu().numpy(), F)
+        assert len(per_frame) == world * F
+        mine = np.concatenate(per_frame[:F]) if int(ctr["n_clusters"].sum()) else np.zeros(0, api.CLUSTER_DTYPE)
+        assert np.array_equal(mine.view(np.uint32), clusters.view(np.uint32)), "gathered cone list is wrong"
+        assert all(sum(len(c) for c in per_frame[r * F:(r + 1) * F]) > 0 for r in range(world))
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -369,6 +407,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if line is not None:
         print(json.dumps(line), flush=True)
 

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(HERE)
 LIB_DIR = os.path.join(HERE, "_lib")
 GPU_LIB = os.path.join(LIB_DIR, "libconesgpu.so")
 SCAN_LIB = os.path.join(HERE, "scangen", "libconesscan.so")
+HOST_LIB = os.path.join(LIB_DIR, "libconeshost.so")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -54,12 +55,26 @@ def build_scangen(force: bool = False) -> str:
     return SCAN_LIB
 
 
+def build_host(force: bool = False) -> str:
+    """C++ host mirror of the reference node classes (host/nodes.hpp) behind a C test surface."""
+    hdir = os.path.join(HERE, "host")
+    srcs = [os.path.join(hdir, f) for f in sorted(os.listdir(hdir))] + [os.path.join(ROOT, "include", "conesgpu.h")]
+    if not force and _fresh(HOST_LIB, srcs + [GPU_LIB]):
+        return HOST_LIB
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB,
+                    os.path.join(hdir, "host_c_api.cpp"), "-L" + LIB_DIR, "-lconesgpu", "-Wl,-rpath,$ORIGIN"],
+                   check=True)
+    return HOST_LIB
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_gpu(force, verbose)
     build_scangen(force)
+    build_host(force)
 
 
 if __name__ == "__main__":
     build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(GPU_LIB)
     print(SCAN_LIB)
+    print(HOST_LIB)

@@ -910,7 +910,6 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   A(dalloc(h, &h->d_v_off, F + 1));
   A(dalloc(h, &h->d_ncomp_f, F));
   A(dalloc(h, &h->d_kcount_f, F));
-  A(dalloc(h, &h->d_k_off, F + 1));
   A(dalloc(h, &h->d_vf, F));
   A(dalloc(h, &h->d_pts, h->cap_c));
   A(dalloc(h, &h->d_src, h->cap_c));
@@ -935,7 +934,15 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   A(dalloc(h, &h->d_label, h->cap_v));
   A(dalloc(h, &h->d_hkeys, h->hash_cap));
   A(dalloc(h, &h->d_hvals, h->hash_cap));
-  A(dalloc(h, &h->d_clusters, h->cap_v));
+  {
+    // results live in ONE block — cluster offsets [round_up(F+1, 4) words] then the packed records —
+    // so a multi-GPU caller can hand the whole cone list to a single collective
+    const size_t off_words = ((size_t)F + 1 + 3) / 4 * 4;
+    u32* block = nullptr;
+    A(dalloc(h, &block, off_words + (size_t)h->cap_v * 4));
+    h->d_k_off = block;
+    h->d_clusters = reinterpret_cast<ClusterRec*>(block + off_words);
+  }
   A(dalloc(h, &h->d_desc_a, h->tiles_cap));
   A(dalloc(h, &h->d_frame_ticket, 1));
   A(dalloc(h, &h->d_desc_fv, F));

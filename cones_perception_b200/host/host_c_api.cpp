@@ -1,0 +1,155 @@
+// host_c_api.cpp — a small C surface over the C++ host classes (nodes.hpp) so that pytest can
+// drive them through ctypes.  Not part of the drop-in boundary (that is include/conesgpu.h).
+#include <cstdio>
+#include <string>
+
+#include "nodes.hpp"
+
+using namespace cones_host;
+
+namespace {
+std::string g_err;
+
+PointCloud2 make_msg(const float* xyzi, uint32_t n, int with_intensity_field, uint32_t sec, uint32_t nsec) {
+  PointCloud2 m;
+  m.header.seq = 7;
+  m.header.stamp_sec = sec;
+  m.header.stamp_nsec = nsec;
+  m.header.frame_id = "cloud";
+  m.height = 1;
+  m.width = n;
+  m.point_step = 16;
+  m.row_step = 16 * n;
+  m.fields.resize(with_intensity_field ? 4 : 3);
+  const char* names[4] = {"x", "y", "z", "intensity"};
+  for (size_t i = 0; i < m.fields.size(); ++i) {
+    m.fields[i].name = names[i];
+    m.fields[i].offset = static_cast<uint32_t>(4 * i);
+  }
+  m.data.resize(static_cast<size_t>(n) * 16);
+  if (n) std::memcpy(m.data.data(), xyzi, static_cast<size_t>(n) * 16);
+  return m;
+}
+}  // namespace
+
+extern "C" {
+
+const char* ch_last_error(void) { return g_err.c_str(); }
+
+// ---- ConeTracker (no GPU needed) ---------------------------------------------------------
+void* ch_tracker_create(int classify_colors, int use_points_buffer, double match_dist, double extension) {
+  auto* t = new ConeTracker();
+  t->classify_colors = classify_colors != 0;
+  t->use_points_buffer = use_points_buffer != 0;
+  t->cones_matching_dist_theshold = match_dist;
+  t->cone_position_extension_length = extension;
+  return t;
+}
+void ch_tracker_destroy(void* t) { delete static_cast<ConeTracker*>(t); }
+
+// forced_color >= 0: the colour "service" answers with that colour for every crop
+int ch_tracker_update(void* tp, const float* xy, uint32_t n, int forced_color, float* out_xy, uint32_t* counts,
+                      uint32_t cap) {
+  auto* t = static_cast<ConeTracker*>(tp);
+  std::vector<std::pair<float, float>> c(n);
+  for (uint32_t i = 0; i < n; ++i) c[i] = {xy[2 * i], xy[2 * i + 1]};
+  if (forced_color >= 0)
+    t->get_colors = [forced_color](const std::vector<std::vector<Point>>& crops) {
+      return std::vector<Color>(crops.size(), static_cast<Color>(forced_color));
+    };
+  std::vector<Point> whole;
+  auto clouds = t->update(c, &whole);
+  for (int k = 0; k < kNumberOfColors; ++k) {
+    counts[k] = static_cast<uint32_t>(clouds[k].size());
+    if (clouds[k].size() > cap) return 3;
+    for (size_t i = 0; i < clouds[k].size(); ++i) {
+      out_xy[(static_cast<size_t>(k) * cap + i) * 2] = clouds[k][i].x;
+      out_xy[(static_cast<size_t>(k) * cap + i) * 2 + 1] = clouds[k][i].y;
+    }
+  }
+  return 0;
+}
+
+// ---- ConeDetector / GroundRemover (GPU) -----------------------------------------------------
+void* ch_detector_create(uint64_t max_points, int device, const cp_detect_params* d, int classify_colors,
+                         int use_points_buffer, int fused_ground) {
+  try {
+    auto* det = new ConeDetector(max_points, device, 32);
+    det->distance_treshold_max = d->distance_treshold_max;
+    det->distance_treshold_min = d->distance_treshold_min;
+    det->level_threshold = d->level_threshold;
+    det->angle_threshold = d->angle_threshold;
+    det->voxel_filter_leaf_size_x = d->voxel_filter_leaf_size_x;
+    det->voxel_filter_leaf_size_y = d->voxel_filter_leaf_size_y;
+    det->voxel_filter_leaf_size_z = d->voxel_filter_leaf_size_z;
+    det->min_cluster_size = d->min_cluster_size;
+    det->max_cluster_size = d->max_cluster_size;
+    det->classify_colors = classify_colors != 0;
+    det->use_points_buffer = use_points_buffer != 0;
+    det->fused_ground_removal = fused_ground != 0;
+    return det;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void ch_detector_destroy(void* d) { delete static_cast<ConeDetector*>(d); }
+
+// one callback: compact xyzi cloud in, the four published clouds out (x, y per cone) plus the
+// layout facts of the published messages
+int ch_detector_handle(void* dp, const float* xyzi, uint32_t n, int with_intensity_field, float* out_xy,
+                       uint32_t* counts, uint32_t cap, uint32_t* out_point_step, uint32_t* out_n_fields,
+                       uint32_t* out_stamp_nsec) {
+  try {
+    auto* det = static_cast<ConeDetector*>(dp);
+    PointCloud2 msg = make_msg(xyzi, n, with_intensity_field, 100, 123456789);
+    auto clouds = det->cloud_handler(msg);
+    for (int k = 0; k < kNumberOfColors; ++k) {
+      counts[k] = clouds[k].width;
+      if (clouds[k].width > cap) return 3;
+      for (uint32_t i = 0; i < clouds[k].width; ++i) {
+        float xy[2];
+        std::memcpy(xy, clouds[k].data.data() + static_cast<size_t>(i) * clouds[k].point_step, 8);
+        out_xy[(static_cast<size_t>(k) * cap + i) * 2] = xy[0];
+        out_xy[(static_cast<size_t>(k) * cap + i) * 2 + 1] = xy[1];
+      }
+    }
+    *out_point_step = clouds[0].point_step;
+    *out_n_fields = static_cast<uint32_t>(clouds[0].fields.size());
+    *out_stamp_nsec = clouds[0].header.stamp_nsec;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 4;
+  }
+}
+
+void* ch_ground_create(uint64_t max_points, int device) {
+  try {
+    return new GroundRemover(max_points, device, 32);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void ch_ground_destroy(void* g) { delete static_cast<GroundRemover*>(g); }
+
+int ch_ground_handle(void* gp, const float* xyzi, uint32_t n, int with_intensity_field, void* out32,
+                     uint32_t* kept, uint32_t* out_point_step, uint32_t* out_stamp_nsec, uint32_t* out_n_fields) {
+  try {
+    auto* gr = static_cast<GroundRemover*>(gp);
+    PointCloud2 msg = make_msg(xyzi, n, with_intensity_field, 100, 123456789);
+    PointCloud2 out = gr->cloud_handler(msg);
+    std::memcpy(out32, out.data.data(), out.data.size());
+    *kept = gr->last_kept();
+    *out_point_step = out.point_step;
+    *out_stamp_nsec = out.header.stamp_nsec;
+    *out_n_fields = static_cast<uint32_t>(out.fields.size());
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 4;
+  }
+}
+
+}  // extern "C"

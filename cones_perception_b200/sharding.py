@@ -20,44 +20,48 @@ def shard_frames(n_frames: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_cone_lists(counts, cones, cap_cones: int, group=None, dst: int = 0):
-    """Gather per-frame cone counts and packed cone records to rank `dst`.
+def offset_words(frames_per_rank: int) -> int:
+    """Words reserved for the cluster offsets in the packed result (F+1 rounded up to 4, the layout
+    of libconesgpu's result block, see cp_device_results)."""
+    return (frames_per_rank + 1 + 3) // 4 * 4
 
-    counts: int32 tensor [frames_per_rank] (cones per local frame), on the collective's device
-    cones:  int32 tensor [cap_cones, 4] (bit patterns of cp_cluster records, first sum(counts) valid)
-    Returns on dst: (counts_all [world, frames_per_rank], cones_all [world, cap_cones, 4]);
-    elsewhere (None, None).  Fixed-capacity all_gather keeps it to two collectives of KB-size
-    messages: latency-bound, not bandwidth-bound.
+
+def pack_words(frames_per_rank: int, cap_cones: int) -> int:
+    """int32 words of one rank's packed result: cluster offsets then cap_cones records."""
+    return offset_words(frames_per_rank) + cap_cones * CONE_WORDS
+
+
+def gather_cone_lists(packed, group=None, dst: int = 0):
+    """Gather every rank's packed cone list to rank `dst` with ONE fixed-capacity all_gather.
+
+    packed: int32 tensor [pack_words(F, cap)] on the collective's device: the rank's cluster offsets
+            (cp_batch_results' cluster_offsets / cp_device_results) followed by the bit patterns of
+            its cp_cluster records (the first offsets[-1] are valid).
+    Returns on dst a tensor [world, F+1 + cap*4]; elsewhere None.  The message is KB-scale:
+    latency-bound, not bandwidth-bound, so one collective beats a count exchange + gatherv.
     """
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    counts = counts.contiguous()
-    cones = cones.contiguous()
-    assert cones.shape == (cap_cones, CONE_WORDS)
-    # outputs are the dim-0 concatenation of the inputs (the form both NCCL and gloo accept)
-    counts_all = torch.empty((world * counts.shape[0],), dtype=counts.dtype, device=counts.device)
-    cones_all = torch.empty((world * cap_cones, CONE_WORDS), dtype=cones.dtype, device=cones.device)
-    dist.all_gather_into_tensor(counts_all, counts, group=group)
-    dist.all_gather_into_tensor(cones_all, cones, group=group)
+    packed = packed.contiguous()
+    out = torch.empty((world * packed.shape[0],), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
     if rank != dst:
-        return None, None
-    return counts_all.view(world, -1), cones_all.view(world, cap_cones, CONE_WORDS)
+        return None
+    return out.view(world, -1)
 
 
-def unpack_gathered(counts_all: np.ndarray, cones_all: np.ndarray):
-    """Host-side view of a gather: list over global frames of structured cone arrays."""
+def unpack_gathered(gathered: np.ndarray, frames_per_rank: int):
+    """Host-side view of a gather: list over global frames (rank-major) of structured cone arrays."""
     from .api import CLUSTER_DTYPE
 
     out = []
-    world = counts_all.shape[0]
-    for r in range(world):
-        recs = np.ascontiguousarray(cones_all[r]).view(np.uint32).reshape(-1, CONE_WORDS)
-        off = 0
-        for c in counts_all[r]:
-            c = int(c)
-            out.append(recs[off:off + c].copy().view(CLUSTER_DTYPE).reshape(-1))
-            off += c
+    g = np.ascontiguousarray(gathered).view(np.int32)
+    for r in range(g.shape[0]):
+        off = g[r, :frames_per_rank + 1].astype(np.int64)
+        recs = g[r, offset_words(frames_per_rank):].view(np.uint32).reshape(-1, CONE_WORDS)
+        for f in range(frames_per_rank):
+            out.append(recs[off[f]:off[f + 1]].copy().view(CLUSTER_DTYPE).reshape(-1))
     return out

@@ -164,7 +164,9 @@ cp_status cp_set_stage_timing(cp_handle* h, int on);
 cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms);
 /* Device pointers of the last run's results (valid until the next run on this handle):
  * packed cp_cluster records, n_frames+1 cluster offsets, and the total cluster count.
- * Lets a multi-GPU caller hand the cone lists to NCCL without a host round trip. */
+ * Lets a multi-GPU caller hand the cone lists to NCCL without a host round trip: offsets and
+ * records are one allocation, d_clusters == d_cluster_offsets + round_up(n_frames_max + 1, 4)
+ * 32-bit words (n_frames_max = cp_config.max_frames), so one collective can move both. */
 cp_status cp_device_results(cp_handle* h, const void** d_clusters, const uint32_t** d_cluster_offsets,
                             const uint32_t** d_n_clusters);
 /* Kernel launches enqueued by the last cp_batch_run / cp_detect / cp_ground_remove. */

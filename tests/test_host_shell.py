@@ -1,0 +1,125 @@
+"""The C++ host mirror of the reference node classes (cones_perception_b200/host/nodes.hpp):
+CPU tests of the stateful tracker, GPU tests of the full cloud_handlers."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from cones_perception_b200 import scans
+from cones_perception_b200.build import HOST_LIB
+from cones_perception_b200.params import PRESETS, GroundParams, to_c_detect
+from oracle import oracle as O
+from tests.util import TrackerReference
+
+CAP = 256
+
+
+@pytest.fixture(scope="module")
+def host():
+    lib = C.CDLL(HOST_LIB)
+    lib.ch_last_error.restype = C.c_char_p
+    lib.ch_tracker_create.restype = C.c_void_p
+    lib.ch_tracker_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
+    lib.ch_tracker_destroy.argtypes = [C.c_void_p]
+    lib.ch_tracker_update.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.ch_detector_create.restype = C.c_void_p
+    lib.ch_detector_create.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.ch_detector_destroy.argtypes = [C.c_void_p]
+    lib.ch_detector_handle.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ch_ground_create.restype = C.c_void_p
+    lib.ch_ground_create.argtypes = [C.c_uint64, C.c_int]
+    lib.ch_ground_destroy.argtypes = [C.c_void_p]
+    lib.ch_ground_handle.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    return lib
+
+
+def tracker_update(lib, t, xy, forced=-1):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.zeros((4, CAP, 2), np.float32)
+    counts = np.zeros(4, np.uint32)
+    rc = lib.ch_tracker_update(t, xy.ctypes.data, len(xy), forced, out.ctypes.data, counts.ctypes.data, CAP)
+    assert rc == 0
+    return [out[k, :counts[k]].copy() for k in range(4)]
+
+
+def as_arrays(clouds):
+    return [np.array([(p[0], p[1]) for p in c], np.float32).reshape(-1, 2) for c in clouds]
+
+
+@pytest.mark.parametrize("classify,buffer", [(False, False), (False, True), (True, True), (True, False)])
+def test_tracker_matches_reference_semantics(host, classify, buffer):
+    rng = np.random.default_rng(3)
+    t = host.ch_tracker_create(int(classify), int(buffer), 0.5, 0.05)
+    ref = TrackerReference(classify, buffer, 0.5, 0.05, forced_color=2)
+    base = rng.uniform(1, 9, (12, 2)).astype(np.float32)
+    for frame in range(8):
+        # cones drift slowly, some appear / disappear, one frame is empty
+        pts = base + rng.normal(0, 0.05 if frame % 3 else 0.4, base.shape).astype(np.float32)
+        pts = pts[rng.random(len(pts)) > 0.2]
+        if frame == 5:
+            pts = pts[:0]
+        got = tracker_update(host, t, pts, forced=2 if classify else -1)
+        exp = as_arrays(ref.update([tuple(p) for p in pts]))
+        for k in range(4):
+            assert got[k].shape == exp[k].shape, (frame, k)
+            assert np.array_equal(got[k].view(np.uint32), exp[k].view(np.uint32)), (frame, k)
+        if frame == 0:
+            assert sum(len(g) for g in got) == 0      # nothing is published on the first frame (Q8)
+        if frame == 6 and not buffer and not classify:
+            assert len(got[0]) == 0                   # previous frame detected nothing: gate stays shut
+    host.ch_tracker_destroy(t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused_ground,with_intensity", [(False, True), (True, True), (True, False)])
+def test_cone_detector_cloud_handler_sequence(host, fused_ground, with_intensity):
+    cfg = scans.config(3)
+    frames = scans.generate(cfg, 4, base_seed=40)
+    d = cfg.detect
+    cd = to_c_detect(d)
+    det = host.ch_detector_create(cfg.points_per_frame, 0, C.byref(cd), 0, 1, int(fused_ground))
+    assert det, host.ch_last_error()
+    ref = TrackerReference(False, True, d.cones_matching_dist_theshold, d.cone_position_extension_length)
+    published = 0
+    for f in frames:
+        out = np.zeros((4, CAP, 2), np.float32)
+        counts = np.zeros(4, np.uint32)
+        step, nf, nsec = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        rc = host.ch_detector_handle(det, f.ctypes.data, len(f), int(with_intensity), out.ctypes.data,
+                                     counts.ctypes.data, CAP, C.byref(step), C.byref(nf), C.byref(nsec))
+        assert rc == 0, host.ch_last_error()
+        view = O.view_of_xyzi(f, with_intensity=True)
+        if not with_intensity:
+            view.off_intensity = 0                      # the faked field aliases x (src/cone_detection.cpp:142-151)
+        cl, _, _ = O.detect(view, d, GroundParams() if fused_ground else None, O.CANONICAL)
+        exp = as_arrays(ref.update([(c["x"], c["y"]) for c in cl]))
+        for k in range(4):
+            assert counts[k] == len(exp[k])
+            assert np.array_equal(out[k, :counts[k]].view(np.uint32), exp[k].view(np.uint32))
+        published += int(counts.sum())
+        assert step.value == 32 and nf.value == (4 if with_intensity else 3)   # Q6: input fields, PCL data
+        assert nsec.value == 123456789                                         # header copied verbatim
+    assert published > 0
+    host.ch_detector_destroy(det)
+
+
+@pytest.mark.gpu
+def test_ground_remover_cloud_handler(host):
+    cfg = scans.config(2)
+    f = scans.generate(cfg, 1, base_seed=41)[0]
+    gr = host.ch_ground_create(cfg.points_per_frame, 0)
+    assert gr, host.ch_last_error()
+    out = np.zeros((len(f), 8), np.float32)
+    kept, step, nsec, nf = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = host.ch_ground_handle(gr, f.ctypes.data, len(f), 1, out.ctypes.data, C.byref(kept), C.byref(step),
+                               C.byref(nsec), C.byref(nf))
+    assert rc == 0, host.ch_last_error()
+    exp, ekept, _, _ = O.ground_node(O.view_of_xyzi(f), GroundParams())
+    e = np.stack([exp[n] for n in ("x", "y", "z", "pad", "intensity", "c1", "c2", "c3")], 1)
+    assert kept.value == ekept and np.array_equal(out.view(np.uint32), e.view(np.uint32))
+    assert step.value == 32 and nf.value == 4
+    assert nsec.value == 123456000           # stamp survives the PCL round trip at microsecond resolution (Q5)
+    host.ch_ground_destroy(gr)

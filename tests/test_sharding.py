@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
     from cones_perception_b200.api import CLUSTER_DTYPE
-    from cones_perception_b200.sharding import gather_cone_lists
+    from cones_perception_b200.sharding import gather_cone_lists, offset_words, pack_words
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     frames_per_rank, cap = 3, 16
@@ -42,12 +42,14 @@ def _worker(rank, world, port, q):
     recs["y"][:k] = -1.5
     recs["size"][:k] = 3 + np.arange(k)
     recs["min_index"][:k] = np.arange(k)
-    cones = torch.from_numpy(recs.view(np.int32).reshape(cap, 4).copy())
-    c_all, k_all = gather_cone_lists(torch.from_numpy(counts), cones, cap)
+    packed = np.zeros(pack_words(frames_per_rank, cap), np.int32)
+    packed[1:frames_per_rank + 1] = np.cumsum(counts)
+    packed[offset_words(frames_per_rank):] = recs.view(np.int32)
+    got = gather_cone_lists(torch.from_numpy(packed))
     if rank == 0:
-        q.put((c_all.numpy(), k_all.numpy()))
+        q.put(got.numpy())
     else:
-        assert c_all is None and k_all is None
+        assert got is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -59,11 +61,11 @@ def test_gather_cone_lists_gloo_world2():
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
-    counts_all, cones_all = q.get(timeout=120)
+    gathered = q.get(timeout=120)
     [p.join(timeout=120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    assert counts_all.tolist() == [[1, 0, 2], [2, 0, 4]]
-    frames = unpack_gathered(counts_all, cones_all)
+    assert gathered.shape == (2, 4 + 16 * 4)  # offsets padded to 4 words + 16 records
+    frames = unpack_gathered(gathered, 3)
     assert [len(f) for f in frames] == [1, 0, 2, 2, 0, 4]
     assert frames[0]["x"].tolist() == [0.0] and frames[2]["x"].tolist() == [1.0, 2.0]
     assert frames[3]["x"].tolist() == [100.0, 101.0] and frames[5]["size"].tolist() == [5, 6, 7, 8]

@@ -145,3 +145,57 @@ def boundary_cloud(d, seed: int = 0, n_random: int = 20000) -> np.ndarray:
     out[:, :3] = a.astype(np.float32)
     out[:, 3] = rng.uniform(0, 100, len(a))
     return out
+
+
+# ---- the stateful tail of ConeDetector::get_centroid_clouds restated in Python (test oracle) ----
+class TrackerReference:
+    """src/cone_detection.cpp:276-340 (radial extension, temporal gate / points buffer, colour
+    routing) on numpy float32 scalars with the reference's float/double promotion rules."""
+
+    def __init__(self, classify_colors=False, use_points_buffer=False, match=0.5, ext=0.05, forced_color=0):
+        self.classify_colors, self.use_points_buffer = classify_colors, use_points_buffer
+        self.match, self.ext, self.forced_color = match, ext, forced_color
+        self.prev = None                      # prev_detected_cones (NULL before the first frame)
+        self.prev_col = [None] * 4            # prev_centroid_clouds
+
+    @staticmethod
+    def dist(a, b):                           # perception_handling::euclidan_dist, utils.cpp:32-34
+        f32, f64 = np.float32, np.float64
+        s = f64(f32(a[0]) - f32(b[0])) ** 2 + f64(f32(a[1]) - f32(b[1])) ** 2 + f64(f32(a[2]) - f32(b[2])) ** 2
+        return f32(np.sqrt(s))
+
+    def update(self, centroids):
+        f32, f64 = np.float32, np.float64
+        clouds = [[] for _ in range(4)]
+        current, need = [], []
+        for cx, cy in centroids:
+            px, py, pz = f32(cx), f32(cy), f32(0.0)
+            ln = self.dist((px, py, pz), (0, 0, 0))                                    # :276
+            px, py = f32(f64(px) + f64(f32(px / ln)) * self.ext), f32(f64(py) + f64(f32(py / ln)) * self.ext)
+            p = (px, py, pz)
+            current.append(p)
+            if self.prev is not None:                                                  # :282
+                for q in self.prev:
+                    if (not self.use_points_buffer) or f64(self.dist(p, q)) < self.match:   # :286
+                        if self.classify_colors:
+                            need_color = True
+                            for i in range(1, 4):                                      # :291-306
+                                if self.prev_col[i] is not None:
+                                    for c in self.prev_col[i]:
+                                        if f64(self.dist(p, c)) < self.match:
+                                            need_color = False
+                                            clouds[i].append(p)
+                                            break
+                                    if not need_color:
+                                        break
+                            if need_color:
+                                need.append(p)
+                        else:
+                            clouds[0].append(p)                                        # :315
+                        break                                                          # :317
+        if self.classify_colors:
+            for p in need:                                                             # :326-333
+                clouds[self.forced_color].append(p)
+        self.prev_col = [list(c) for c in clouds]                                      # :335-337
+        self.prev = current                                                            # :339
+        return clouds
