@@ -11,9 +11,14 @@
 // cluster_kernels.cuh; frames that exceed the shared-memory capacity (or trip VoxelGrid's
 // int32 overflow guard) raise Ctl::fast_overflow and the host re-runs the back half through
 // the general path.
+//
+// The kernel also gathers its frame's survivors straight from the keep mask (ordered, by word
+// popcounts) and reduces their bounding box in shared memory, so the fast path needs neither
+// the tile scan nor the global gather pass nor the survivor arrays.
 #pragma once
 #include "cluster_kernels.cuh"
 #include "common.cuh"
+#include "stream_kernels.cuh"
 #include "voxel_kernels.cuh"
 
 namespace cp {
@@ -22,12 +27,11 @@ constexpr int kFrameThreads = 512;
 
 struct FrameArgs {
   u32 n_frames;
-  const u32* c_off;          // [F+1]
-  const float4* pts;         // survivors
-  const u32* src;
-  const u32* bbox_key;
-  const u32* frame_n;
-  u32 uniform_n;
+  const uint8_t* in;         // raw input points (the kernel gathers its frame's survivors itself)
+  Layout layout;
+  Geom geom;
+  const u32* mask;           // keep bits written by keep_mask_kernel
+  const u32* c_off;          // [F+1] survivor offsets — only with taps (NULL otherwise)
   const u32* gcount;
   int pad_survives;
   VoxelK vk;
@@ -38,6 +42,7 @@ struct FrameArgs {
   u32* k_off;                // [F+1]
   u32* ncomp_f;              // [F]
   u32* kcount_f;             // [F]
+  u32* ncrop_f;              // [F] survivors per frame
   ClusterRec* clusters;      // packed, canonical order per frame
   u32 clusters_cap;
   u64* desc_v;               // frame descriptors for the voxel offsets
@@ -55,15 +60,29 @@ struct FrameArgs {
 template <int CMAX, int VMAX>
 struct FrameSmem {
   float px[CMAX], py[CMAX], pz[CMAX], pw[CMAX];
-  u64 key[CMAX];             // (voxel idx << 32) | survivor position
-  float vx[VMAX], vy[VMAX], vz[VMAX];
-  u32 vstart[VMAX + 1];      // voxel -> first sorted record; later: kept roots / ranks
-  u32 parent[VMAX];
-  u32 label[VMAX];
-  u32 csize[VMAX];
+  u32 k0[CMAX], k1[CMAX];              // voxel idx, ping-pong buffers of the radix sort
+  unsigned short v0[CMAX], v1[CMAX];   // survivor position, ping-pong
+  union {
+    struct {                           // scratch of the radix sort (dead before the voxel arrays live)
+      u32 whist[kFrameThreads / 32][256];
+      u32 gbase[256];
+    } sort;
+    struct {
+      float vx[VMAX], vy[VMAX], vz[VMAX];
+      u32 parent[VMAX];
+      u32 label[VMAX];                 // also: per-cell fill counters of the sweep
+      u32 csize[VMAX];
+      unsigned short vcell[VMAX];      // sweep cell of each voxel
+      unsigned short perm[VMAX];       // voxels ordered by sweep cell
+    } vox;
+  } u;
+  u32 vstart[VMAX + 1];                // voxel -> first sorted record; then sweep cell starts; then kept roots
   u32 wsum[kFrameThreads / 32];
   VoxelFrame vfr;
-  u32 frame, slow, n_vox, v_excl, k_excl, n_kept, n_comp;
+  u32 frame, slow, n_vox, v_excl, k_excl, n_kept, n_comp, n_surv;
+  u32 bbox[8];
+  u32 sw_axis, sw_ncell;
+  float sw_min, sw_inv;
 };
 
 __device__ __forceinline__ u32 smem_find(volatile u32* parent, u32 x) {
@@ -113,7 +132,7 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* wsum, u32& total) {
   return woff + inc - v;
 }
 
-template <int CMAX, int VMAX>
+template <int CMAX, int VMAX, int MODE>
 __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FrameSmem<CMAX, VMAX>& s = *reinterpret_cast<FrameSmem<CMAX, VMAX>*>(smem_raw);
@@ -126,10 +145,88 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
     __syncthreads();
     const u32 f = s.frame;
     if (f >= a.n_frames) break;
-    const u32 c0 = a.c_off[f];
-    const u32 C = a.c_off[f + 1] - c0;
+    // frame geometry: tiles [tile0, tile0 + ntiles), points [first, first + n)
+    u32 tile0, ntiles, npts;
+    u64 first;
+    if (a.geom.uniform_n) {
+      tile0 = f * a.geom.tpf;
+      ntiles = a.geom.tpf;
+      npts = a.geom.uniform_n;
+      first = (u64)f * a.geom.uniform_n;
+    } else {
+      tile0 = a.geom.frame_tile0[f];
+      ntiles = (f + 1 < a.n_frames ? a.geom.frame_tile0[f + 1] : a.geom.n_tiles) - tile0;
+      npts = a.geom.frame_n[f];
+      first = a.geom.frame_off[f];
+    }
+    const u32 c0 = a.c_off ? a.c_off[f] : 0u;
 
-    // ---- S0: VoxelGrid setup from the survivors' bounding box (thread 0)
+    // ---- S0: ordered gather of the frame's survivors from the keep mask (8 words = 256
+    // points per thread and round) + bounding box
+    if (tid < 8) s.bbox[tid] = tid < 4 ? 0xFFFFFFFFu : 0u;
+    if (tid == 0) s.slow = 0;
+    __syncthreads();
+    u32 C = 0;
+    {
+      const u32 nwords = ntiles * kTileWords;
+      u32 mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0, mxy = 0, mxz = 0;
+      for (u32 w0 = 0; w0 < nwords; w0 += kFrameThreads * 8) {
+        const u32 wb = w0 + tid * 8;
+        u32 w[8];
+        u32 cnt = 0;
+        if (wb < nwords) {
+          const uint4* mp = reinterpret_cast<const uint4*>(a.mask + (u64)tile0 * kTileWords + wb);
+          const uint4 m0 = mp[0], m1 = mp[1];
+          w[0] = m0.x; w[1] = m0.y; w[2] = m0.z; w[3] = m0.w;
+          w[4] = m1.x; w[5] = m1.y; w[6] = m1.z; w[7] = m1.w;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cnt += __popc(w[k]);
+        }
+        u32 total;
+        u32 pos = C + block_excl_scan(cnt, s.wsum, total);
+        if (cnt && C + total <= (u32)CMAX) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            u32 bits = w[k];
+            while (bits) {
+              const u32 b = (u32)__ffs(bits) - 1u;
+              bits &= bits - 1;
+              const float4 p = load_point<MODE>(a.in, first + (u64)(wb + k) * 32 + b, a.layout);
+              s.px[pos] = p.x; s.py[pos] = p.y; s.pz[pos] = p.z; s.pw[pos] = p.w;
+              ++pos;
+              const u32 kx = f2ord(p.x), ky = f2ord(p.y), kz = f2ord(p.z);
+              mnx = min(mnx, kx); mxx = max(mxx, kx);
+              mny = min(mny, ky); mxy = max(mxy, ky);
+              mnz = min(mnz, kz); mxz = max(mxz, kz);
+            }
+          }
+        }
+        C += total;
+      }
+      (void)npts;
+      mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny);
+      mnz = __reduce_min_sync(kFull, mnz); mxx = __reduce_max_sync(kFull, mxx);
+      mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
+      if (lane == 0 && mxx >= mnx) {
+        atomicMin(&s.bbox[0], mnx); atomicMin(&s.bbox[1], mny); atomicMin(&s.bbox[2], mnz);
+        atomicMax(&s.bbox[4], mxx); atomicMax(&s.bbox[5], mxy); atomicMax(&s.bbox[6], mxz);
+      }
+    }
+    // the zero points the ground node pads with (src/ground_removal.cpp:79) as ONE record
+    // with multiplicity, appended after the real survivors
+    const u32 pad_idx = a.pad_survives ? C : 0xFFFFFFFFu;
+    if (a.pad_survives) {
+      if (tid == 0 && C < (u32)CMAX) {
+        s.px[C] = s.py[C] = s.pz[C] = s.pw[C] = 0.0f;
+        const u32 kz = f2ord(0.0f);
+        atomicMin(&s.bbox[0], kz); atomicMin(&s.bbox[1], kz); atomicMin(&s.bbox[2], kz);
+        atomicMax(&s.bbox[4], kz); atomicMax(&s.bbox[5], kz); atomicMax(&s.bbox[6], kz);
+      }
+      ++C;
+    }
+    __syncthreads();
+
+    // ---- S0b: VoxelGrid setup from the survivors' bounding box (thread 0)
     if (tid == 0) {
       VoxelFrame v;
       v.pad = 0;
@@ -143,7 +240,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
         i32 div_b[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const float mn = ord2f(a.bbox_key[f * 8 + k]), mx = ord2f(a.bbox_key[f * 8 + 4 + k]);
+          const float mn = ord2f(s.bbox[k]), mx = ord2f(s.bbox[4 + k]);
           d[k] = (long long)__fmul_rn(__fsub_rn(mx, mn), a.vk.inv[k]) + 1;
           v.min_b[k] = (i32)floorf(__fmul_rn(mn, a.vk.inv[k]));
           const i32 max_b = (i32)floorf(__fmul_rn(mx, a.vk.inv[k]));
@@ -163,6 +260,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
       s.vfr = v;
       s.slow = slow;
       a.vf[f] = v;
+      a.ncrop_f[f] = C;
       atomicMax(&a.ctl->fast_max_c, C);
     }
     __syncthreads();
@@ -170,52 +268,88 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
     const bool slow0 = s.slow != 0;
 
     if (!slow0) {
-      // ---- S1: load survivors, voxel keys
-      u32 P2 = 32;
-      while (P2 < C) P2 <<= 1;
+      // ---- S1: voxel keys (PCL idx) with the survivor position as the value
       const VoxelFrame vfr = s.vfr;
-      for (u32 i = tid; i < P2; i += kFrameThreads) {
-        u64 k = 0xFFFFFFFFFFFFFFFFull;
-        if (i < C) {
-          const float4 p = a.pts[c0 + i];
-          s.px[i] = p.x; s.py[i] = p.y; s.pz[i] = p.z; s.pw[i] = p.w;
-          const i32 i0 = (i32)__fsub_rn(floorf(__fmul_rn(p.x, a.vk.inv[0])), (float)vfr.min_b[0]);
-          const i32 i1 = (i32)__fsub_rn(floorf(__fmul_rn(p.y, a.vk.inv[1])), (float)vfr.min_b[1]);
-          const i32 i2 = (i32)__fsub_rn(floorf(__fmul_rn(p.z, a.vk.inv[2])), (float)vfr.min_b[2]);
-          const u32 idx = (u32)i0 + (u32)i1 * vfr.mul1 + (u32)i2 * vfr.mul2;
-          k = ((u64)idx << 32) | (u64)i;
-        }
-        s.key[i] = k;
+      for (u32 i = tid; i < C; i += kFrameThreads) {
+        const i32 i0 = (i32)__fsub_rn(floorf(__fmul_rn(s.px[i], a.vk.inv[0])), (float)vfr.min_b[0]);
+        const i32 i1 = (i32)__fsub_rn(floorf(__fmul_rn(s.py[i], a.vk.inv[1])), (float)vfr.min_b[1]);
+        const i32 i2 = (i32)__fsub_rn(floorf(__fmul_rn(s.pz[i], a.vk.inv[2])), (float)vfr.min_b[2]);
+        s.k0[i] = (u32)i0 + (u32)i1 * vfr.mul1 + (u32)i2 * vfr.mul2;
+        s.v0[i] = (unsigned short)i;
       }
-      __syncthreads();
-      // ---- S2: bitonic sort of (voxel idx, position): ascending idx, ascending position inside
-      for (u32 k = 2; k <= P2; k <<= 1) {
-        for (u32 j = k >> 1; j > 0; j >>= 1) {
-          for (u32 t = tid; t < (P2 >> 1); t += kFrameThreads) {
-            const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
-            const u32 ixj = i | j;
-            const u64 x = s.key[i], y = s.key[ixj];
-            const bool up = (i & k) == 0;
-            if ((x > y) == up) {
-              s.key[i] = y;
-              s.key[ixj] = x;
-            }
+      // ---- S2: stable LSD radix sort in shared memory, 8-bit digits, only the live key bits.
+      // Warp w owns a contiguous chunk and walks it 32 items at a time, so ranks keep the
+      // input (= point) order inside a voxel.
+      constexpr int kWarps = kFrameThreads / 32;
+      constexpr int kMaxRounds = CMAX / kFrameThreads;
+      const u32 passes = (vfr.bits + 7u) >> 3;
+      const u32 chunk = ((C + kFrameThreads - 1) / kFrameThreads) * 32;
+      for (u32 pass = 0; pass < passes; ++pass) {
+        const u32* ksrc = (pass & 1) ? s.k1 : s.k0;
+        u32* kdst = (pass & 1) ? s.k0 : s.k1;
+        const unsigned short* vsrc = (pass & 1) ? s.v1 : s.v0;
+        unsigned short* vdst = (pass & 1) ? s.v0 : s.v1;
+        const u32 shift = pass * 8;
+        for (u32 q = tid; q < kWarps * 256; q += kFrameThreads) (&s.u.sort.whist[0][0])[q] = 0;
+        __syncthreads();
+        u32 key[kMaxRounds], off[kMaxRounds], vmask = 0;
+        unsigned short val[kMaxRounds];
+#pragma unroll
+        for (int r = 0; r < kMaxRounds; ++r) {
+          const u32 i = warp * chunk + r * 32 + lane;
+          const bool valid = ((u32)r * 32 < chunk) && i < C;
+          key[r] = valid ? ksrc[i] : 0u;
+          val[r] = valid ? vsrc[i] : (unsigned short)0;
+          const u32 d = valid ? ((key[r] >> shift) & 0xFFu) : 0x100u;
+          const u32 peers = __match_any_sync(kFull, d);
+          const int leader = __ffs(peers) - 1;
+          u32 old = 0;
+          if (valid && lane == leader) {
+            old = s.u.sort.whist[warp][d];
+            s.u.sort.whist[warp][d] = old + __popc(peers);
           }
-          __syncthreads();
+          old = __shfl_sync(kFull, old, leader);
+          off[r] = old + __popc(peers & lanemask_lt());
+          vmask |= valid ? (1u << r) : 0u;
+          __syncwarp();
         }
+        __syncthreads();
+        u32 run = 0;
+        if (tid < 256) {
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) {
+            const u32 t = s.u.sort.whist[w][tid];
+            s.u.sort.whist[w][tid] = run;
+            run += t;
+          }
+        }
+        u32 tot;
+        const u32 gb = block_excl_scan(run, s.wsum, tot);
+        if (tid < 256) s.u.sort.gbase[tid] = gb;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kMaxRounds; ++r) {
+          if (vmask & (1u << r)) {
+            const u32 d = (key[r] >> shift) & 0xFFu;
+            const u32 pos = s.u.sort.gbase[d] + s.u.sort.whist[warp][d] + off[r];
+            kdst[pos] = key[r];
+            vdst[pos] = val[r];
+          }
+        }
+        __syncthreads();
       }
+      const u32* ks = (passes & 1) ? s.k1 : s.k0;
       // ---- S3: segment heads -> voxel ids
       const u32 per = (C + kFrameThreads - 1) / kFrameThreads;
       const u32 r0 = tid * per, r1 = min(r0 + per, C);
       u32 cnt = 0;
-      for (u32 r = r0; r < r1; ++r)
-        cnt += (r == 0 || (u32)(s.key[r] >> 32) != (u32)(s.key[r - 1] >> 32)) ? 1u : 0u;
+      for (u32 r = r0; r < r1; ++r) cnt += (r == 0 || ks[r] != ks[r - 1]) ? 1u : 0u;
       u32 total;
       u32 vid = block_excl_scan(cnt, s.wsum, total);
       V = total;
       if (V <= (u32)VMAX) {
         for (u32 r = r0; r < r1; ++r)
-          if (r == 0 || (u32)(s.key[r] >> 32) != (u32)(s.key[r - 1] >> 32)) s.vstart[vid++] = r;
+          if (r == 0 || ks[r] != ks[r - 1]) s.vstart[vid++] = r;
         if (tid == 0) s.vstart[V] = C;
       } else if (tid == 0) {
         s.slow = 1;
@@ -245,58 +379,116 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
     u32 K = 0;
     if (!slow && V > 0) {
       // ---- S4: voxel centroids — sequential fp32 sums in record (= point) order
+      const u32 passes4 = (s.vfr.bits + 7u) >> 3;
+      const u32* ks = (passes4 & 1) ? s.k1 : s.k0;
+      const unsigned short* vs = (passes4 & 1) ? s.v1 : s.v0;
+      // NOTE: the voxel arrays alias the sort scratch; the sort is complete (barrier above)
+      float mxv = 0.f, myv = 0.f, mzv = 0.f;
       for (u32 v = tid; v < V; v += kFrameThreads) {
         const u32 b = s.vstart[v], e = s.vstart[v + 1];
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
         u32 cnt = e - b;
         for (u32 r = b; r < e; ++r) {
-          const u32 i = (u32)s.key[r];
+          const u32 i = vs[r];
           sx = __fadd_rn(sx, s.px[i]);
           sy = __fadd_rn(sy, s.py[i]);
           sz = __fadd_rn(sz, s.pz[i]);
           si = __fadd_rn(si, s.pw[i]);
-          if (a.pad_survives && a.src[c0 + i] == 0xFFFFFFFFu) {
-            const u32 nf = a.uniform_n ? a.uniform_n : a.frame_n[f];
-            cnt += (nf - a.gcount[f]) - 1u;
-          }
+          if (i == pad_idx) cnt += (npts - a.gcount[f]) - 1u;
         }
         const float c = (float)cnt;
-        const float mx = __fdiv_rn(sx, c), my = __fdiv_rn(sy, c), mz = __fdiv_rn(sz, c);
-        s.vx[v] = mx; s.vy[v] = my; s.vz[v] = mz;
-        s.parent[v] = v;
-        s.csize[v] = 0;
-        if (a.tap_vox && v_excl + v < a.tap_vox_cap) a.tap_vox[v_excl + v] = make_float4(mx, my, mz, __fdiv_rn(si, c));
+        mxv = __fdiv_rn(sx, c); myv = __fdiv_rn(sy, c); mzv = __fdiv_rn(sz, c);
+        s.u.vox.vx[v] = mxv; s.u.vox.vy[v] = myv; s.u.vox.vz[v] = mzv;
+        s.u.vox.parent[v] = v;
+        s.u.vox.csize[v] = 0;
+        if (a.tap_vox && v_excl + v < a.tap_vox_cap)
+          a.tap_vox[v_excl + v] = make_float4(mxv, myv, mzv, __fdiv_rn(si, c));
       }
       if (a.tap_keys) {
         for (u32 r = tid; r < C; r += kFrameThreads) {
-          a.tap_keys[c0 + r] = (u32)(s.key[r] >> 32);
-          a.tap_order[c0 + r] = c0 + (u32)s.key[r];
+          a.tap_keys[c0 + r] = ks[r];
+          a.tap_order[c0 + r] = c0 + vs[r];
         }
       }
+      // ---- S5: connected components of "L2_Simple(i,j) < r2".
+      // Sweep: voxels are binned along the longer horizontal axis of the bounding box into
+      // cells of edge >= 1.01 * tolerance (counting sort), so a voxel only meets the voxels of
+      // its own and the previous cell.  A warp resolves a row cooperatively: roots of all hits,
+      // one warp-wide minimum, and a CAS only for roots that still differ.
+      if (tid == 0) {
+        const float ex = __fsub_rn(ord2f(s.bbox[4]), ord2f(s.bbox[0]));
+        const float ey = __fsub_rn(ord2f(s.bbox[5]), ord2f(s.bbox[1]));
+        const u32 axis = ey > ex ? 1u : 0u;
+        const float ext = axis ? ey : ex;
+        float inv = a.ck.inv_h;
+        u32 ncell = (u32)(ext * inv) + 2u;
+        if (ncell > (u32)VMAX) {             // very long scene: widen the cells, still >= tolerance
+          inv = (float)(VMAX - 2) / ext;
+          ncell = (u32)VMAX;
+        }
+        s.sw_axis = axis;
+        s.sw_ncell = ncell;
+        s.sw_min = ord2f(s.bbox[axis]);
+        s.sw_inv = inv;
+      }
       __syncthreads();
-      // ---- S5: connected components of "L2_Simple(i,j) < r2" — all pairs, warp per row.
-      // A warp resolves a row cooperatively: roots of all hits, one warp-wide minimum, and a
-      // CAS only for roots that still differ (rare once a component has formed).
-      for (u32 i = warp + 1; i < V; i += kFrameThreads / 32) {
-        const float xi = s.vx[i], yi = s.vy[i], zi = s.vz[i];
-        for (u32 base = 0; base < i; base += 32) {
-          const u32 j = base + lane;
-          const bool hit = j < i && l2_simple(xi, yi, zi, s.vx[j], s.vy[j], s.vz[j]) < a.ck.r2;
+      const u32 ncell = s.sw_ncell;
+      for (u32 c = tid; c <= ncell; c += kFrameThreads) s.vstart[c] = 0;
+      for (u32 c = tid; c < ncell; c += kFrameThreads) s.u.vox.label[c] = 0;
+      __syncthreads();
+      for (u32 v = tid; v < V; v += kFrameThreads) {
+        const float coord = s.sw_axis ? s.u.vox.vy[v] : s.u.vox.vx[v];
+        i32 c = (i32)floorf((coord - s.sw_min) * s.sw_inv);
+        c = c < 0 ? 0 : (c >= (i32)ncell ? (i32)ncell - 1 : c);
+        s.u.vox.vcell[v] = (unsigned short)c;
+        atomicAdd(&s.vstart[c], 1u);
+      }
+      __syncthreads();
+      {
+        const u32 perc = (ncell + kFrameThreads - 1) / kFrameThreads;
+        const u32 q0 = tid * perc, q1 = min(q0 + perc, ncell);
+        u32 sum = 0;
+        for (u32 q = q0; q < q1; ++q) sum += s.vstart[q];
+        u32 tot;
+        u32 run = block_excl_scan(sum, s.wsum, tot);
+        for (u32 q = q0; q < q1; ++q) {
+          const u32 t = s.vstart[q];
+          s.vstart[q] = run;
+          run += t;
+        }
+        if (tid == 0) s.vstart[ncell] = V;
+      }
+      __syncthreads();
+      for (u32 v = tid; v < V; v += kFrameThreads) {
+        const u32 c = s.u.vox.vcell[v];
+        s.u.vox.perm[s.vstart[c] + atomicAdd(&s.u.vox.label[c], 1u)] = (unsigned short)v;
+      }
+      __syncthreads();
+      for (u32 r = warp; r < V; r += kFrameThreads / 32) {
+        const u32 i = s.u.vox.perm[r];
+        const u32 ci = s.u.vox.vcell[i];
+        const u32 lo = s.vstart[ci ? ci - 1 : 0];
+        const float xi = s.u.vox.vx[i], yi = s.u.vox.vy[i], zi = s.u.vox.vz[i];
+        for (u32 base = lo; base < r; base += 32) {
+          const u32 jp = base + lane;
+          const u32 j = jp < r ? s.u.vox.perm[jp] : 0u;
+          const bool hit = jp < r &&
+                           l2_simple(xi, yi, zi, s.u.vox.vx[j], s.u.vox.vy[j], s.u.vox.vz[j]) < a.ck.r2;
           if (!__any_sync(kFull, hit)) continue;
-          const u32 rj = hit ? smem_find(s.parent, j) : 0xFFFFFFFFu;
-          const u32 ri = smem_find(s.parent, i);
+          const u32 rj = hit ? smem_find(s.u.vox.parent, j) : 0xFFFFFFFFu;
+          const u32 ri = smem_find(s.u.vox.parent, i);
           const u32 m = min(__reduce_min_sync(kFull, rj), ri);
-          if (hit && rj != m && atomicCAS(&s.parent[rj], rj, m) != rj) smem_union(s.parent, rj, m);
-          if (lane == 0 && ri != m && atomicCAS(&s.parent[ri], ri, m) != ri) smem_union(s.parent, ri, m);
+          if (hit && rj != m && atomicCAS(&s.u.vox.parent[rj], rj, m) != rj) smem_union(s.u.vox.parent, rj, m);
+          if (lane == 0 && ri != m && atomicCAS(&s.u.vox.parent[ri], ri, m) != ri) smem_union(s.u.vox.parent, ri, m);
         }
       }
       __syncthreads();
       // ---- S6: labels (root = min voxel index of the component) and component sizes
-      for (u32 v = tid; v < V; v += kFrameThreads) s.label[v] = smem_find(s.parent, v);
+      for (u32 v = tid; v < V; v += kFrameThreads) s.u.vox.label[v] = smem_find(s.u.vox.parent, v);
       __syncthreads();
       for (u32 v = tid; v < V; v += kFrameThreads) {
-        atomicAdd(&s.csize[s.label[v]], 1u);
-        if (a.tap_labels) a.tap_labels[v_excl + v] = (i32)s.label[v];
+        atomicAdd(&s.u.vox.csize[s.u.vox.label[v]], 1u);
+        if (a.tap_labels) a.tap_labels[v_excl + v] = (i32)s.u.vox.label[v];
       }
       __syncthreads();
       // ---- S7: kept roots in ascending order (ordered compaction over v)
@@ -304,9 +496,9 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
       const u32 v0 = tid * perv, v1 = min(v0 + perv, V);
       u32 kc = 0, cc = 0;
       for (u32 v = v0; v < v1; ++v) {
-        if (s.label[v] == v) {
+        if (s.u.vox.label[v] == v) {
           ++cc;
-          const u32 sz = s.csize[v];
+          const u32 sz = s.u.vox.csize[v];
           if (sz >= a.ck.min_size && sz <= a.ck.max_size) ++kc;
         }
       }
@@ -315,8 +507,8 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
       block_excl_scan(cc, s.wsum, ctotal);
       K = ktotal;
       for (u32 v = v0; v < v1; ++v) {
-        if (s.label[v] == v) {
-          const u32 sz = s.csize[v];
+        if (s.u.vox.label[v] == v) {
+          const u32 sz = s.u.vox.csize[v];
           if (sz >= a.ck.min_size && sz <= a.ck.max_size) s.vstart[kpos++] = v;  // vstart is free now
         }
       }
@@ -349,23 +541,23 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
       const u32 k_excl = s.k_excl;
       for (u32 k = warp; k < K; k += kFrameThreads / 32) {
         const u32 root = s.vstart[k];
-        const u32 size = s.csize[root];
+        const u32 size = s.u.vox.csize[root];
         float x = 0.0f, y = 0.0f;
         u32 seen = 0;
         for (u32 base = root; base < V && seen < size; base += 32) {
           const u32 v = base + lane;
-          u32 members = __ballot_sync(kFull, v < V && s.label[v] == root);
+          u32 members = __ballot_sync(kFull, v < V && s.u.vox.label[v] == root);
           seen += __popc(members);
           while (members) {
             const u32 m = base + (u32)__ffs(members) - 1u;
             members &= members - 1;
-            x = __fadd_rn(x, s.vx[m]);
-            y = __fadd_rn(y, s.vy[m]);
+            x = __fadd_rn(x, s.u.vox.vx[m]);
+            y = __fadd_rn(y, s.u.vox.vy[m]);
           }
         }
         u32 rank = 0;  // size descending, then min index ascending (kept roots are ascending)
         for (u32 q = lane; q < K; q += 32) {
-          const u32 sq = s.csize[s.vstart[q]];
+          const u32 sq = s.u.vox.csize[s.vstart[q]];
           rank += (sq > size || (sq == size && q < k)) ? 1u : 0u;
         }
         rank = __reduce_add_sync(kFull, rank);

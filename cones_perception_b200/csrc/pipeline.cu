@@ -61,6 +61,8 @@ struct cp_handle {
   RunParams rp{};
   u64 *d_desc_fv = nullptr, *d_desc_fk = nullptr;
   u32* d_frame_ticket = nullptr;
+  u32* d_ncrop_f = nullptr;
+  bool gathered = false;  // the global scan + gather of the current run has been enqueued
 
   u64 cap_c = 0, cap_v = 0;
   u32 tiles_cap = 0, sort_tiles_cap = 0, hash_cap = 0;
@@ -423,21 +425,12 @@ u32 grid_for(u64 work, u32 block, int sms, int per_sm) {
   return (u32)(b < cap ? b : cap);
 }
 
-// pass 2 of the front end: keep mask -> tile scan -> ordered gather (+bbox)
-template <bool OUT32>
-void launch_front_pass2(cp_handle* h, const Geom& g, const CropK& c, const GroundK& gk, u32 cap, uint8_t* out32,
-                        u32 grid) {
+// pass 2 of the front end, part 1: keep mask + survivors per tile
+void launch_keep_mask(cp_handle* h, const Geom& g, const CropK& c, const GroundK& gk, u32 grid) {
   MaskOut mo;
   mo.mask = h->d_mask;
   mo.tile_count = h->d_tile_count;
   mo.gcount = h->d_gcount;
-  GatherOut go;
-  go.pts = h->d_pts;
-  go.src = h->d_src;
-  go.frame = h->d_frame;
-  go.cap = cap;
-  go.bbox_key = h->d_bbox;
-  go.out32 = out32;
   if (h->stage_timing) cudaEventRecord(h->ev_k[2], h->stream);
   switch (h->layout.mode) {
     case 0: keep_mask_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo); break;
@@ -445,6 +438,20 @@ void launch_front_pass2(cp_handle* h, const Geom& g, const CropK& c, const Groun
     default: keep_mask_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo); break;
   }
   if (h->stage_timing) cudaEventRecord(h->ev_k[3], h->stream);
+  h->launches++;
+}
+
+// part 2: tile scan -> ordered gather (+bbox) into the global survivor arrays
+// (general back half, node-equivalent ground removal, parity taps)
+template <bool OUT32>
+void launch_scan_gather(cp_handle* h, const Geom& g, const GroundK& gk, u32 cap, uint8_t* out32) {
+  GatherOut go;
+  go.pts = h->d_pts;
+  go.src = h->d_src;
+  go.frame = h->d_frame;
+  go.cap = cap;
+  go.bbox_key = h->d_bbox;
+  go.out32 = out32;
   const u32 stiles = (g.n_tiles + kScanTile - 1) / kScanTile;
   tile_scan_kernel<<<stiles < (u32)h->sms * 4 ? stiles : (u32)h->sms * 4, kScanThreads, 0, h->stream>>>(
       g, h->d_tile_count, h->d_tile_excl, h->d_c_off, h->d_desc_a, h->d_ctl, cap);
@@ -454,7 +461,8 @@ void launch_front_pass2(cp_handle* h, const Geom& g, const CropK& c, const Groun
     case 1: gather_survivors_kernel<1, OUT32><<<ggrid, 256, 0, h->stream>>>(h->in_ptr, h->layout, g, gk, h->d_mask, h->d_tile_count, h->d_tile_excl, go); break;
     default: gather_survivors_kernel<2, OUT32><<<ggrid, 256, 0, h->stream>>>(h->in_ptr, h->layout, g, gk, h->d_mask, h->d_tile_count, h->d_tile_excl, go); break;
   }
-  h->launches += 3;
+  h->launches += 2;
+  h->gathered = true;
 }
 void launch_sector_min(cp_handle* h, const Geom& g, u32 grid) {
   switch (h->layout.mode) {
@@ -632,16 +640,30 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
 }
 
 // fast back half: one CTA per frame in shared memory (frame_kernels.cuh)
+template <int CMAX, int VMAX, int MODE>
+void launch_frame_kernel(cp_handle* h, const FrameArgs& fa) {
+  const size_t smem = sizeof(FrameSmem<CMAX, VMAX>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(frame_backend_kernel<CMAX, VMAX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const u32 per_sm = (u32)std::max<size_t>(1, std::min<size_t>(4, (220u << 10) / (smem + 1024)));
+  const u32 grid = std::min<u32>(fa.n_frames, (u32)h->sms * per_sm);
+  frame_backend_kernel<CMAX, VMAX, MODE><<<grid, kFrameThreads, smem, h->stream>>>(fa);
+  h->launches++;
+}
+
+// fast back half: one CTA per frame in shared memory (frame_kernels.cuh)
 template <int CMAX, int VMAX>
 void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   FrameArgs fa;
   fa.n_frames = h->hg.n_frames;
-  fa.c_off = h->d_c_off;
-  fa.pts = h->d_pts;
-  fa.src = h->d_src;
-  fa.bbox_key = h->d_bbox;
-  fa.frame_n = h->d_frame_n;
-  fa.uniform_n = h->hg.uniform_n;
+  fa.in = h->in_ptr;
+  fa.layout = h->layout;
+  fa.geom = device_geom(h);
+  fa.mask = h->d_mask;
+  fa.c_off = h->taps ? h->d_c_off : nullptr;
   fa.gcount = h->d_gcount;
   fa.pad_survives = rp.gk.pad_survives;
   fa.vk = rp.vk;
@@ -651,6 +673,7 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   fa.k_off = h->d_k_off;
   fa.ncomp_f = h->d_ncomp_f;
   fa.kcount_f = h->d_kcount_f;
+  fa.ncrop_f = h->d_ncrop_f;
   fa.clusters = h->d_clusters;
   fa.clusters_cap = (u32)h->cap_v;
   fa.desc_v = h->d_desc_fv;
@@ -663,16 +686,13 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   fa.tap_keys = h->taps ? h->d_tap_keys : nullptr;
   fa.tap_order = h->taps ? h->d_tap_order : nullptr;
   fa.tap_labels = h->taps ? h->d_tap_labels : nullptr;
-  const size_t smem = sizeof(FrameSmem<CMAX, VMAX>);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(frame_backend_kernel<CMAX, VMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+  // the crop taps (survivor arrays, offsets) come from the global gather
+  if (h->taps && !h->gathered) launch_scan_gather<false>(h, fa.geom, rp.gk, (u32)h->cap_c, nullptr);
+  switch (h->layout.mode) {
+    case 0: launch_frame_kernel<CMAX, VMAX, 0>(h, fa); break;
+    case 1: launch_frame_kernel<CMAX, VMAX, 1>(h, fa); break;
+    default: launch_frame_kernel<CMAX, VMAX, 2>(h, fa); break;
   }
-  const u32 per_sm = (u32)std::max<size_t>(1, std::min<size_t>(4, (220u << 10) / (smem + 1024)));
-  const u32 grid = std::min<u32>(fa.n_frames, (u32)h->sms * per_sm);
-  frame_backend_kernel<CMAX, VMAX><<<grid, kFrameThreads, smem, h->stream>>>(fa);
-  h->launches++;
 }
 
 cp_status enqueue_back(cp_handle* h, bool retry) {
@@ -685,7 +705,10 @@ cp_status enqueue_back(cp_handle* h, bool retry) {
   }
   if (h->back_mode == 0) enqueue_back_fast<2048, 1024>(h, rp);
   else if (h->back_mode == 1) enqueue_back_fast<4096, 2048>(h, rp);
-  else enqueue_back_general(h, rp);
+  else {
+    if (!h->gathered) launch_scan_gather<false>(h, device_geom(h), rp.gk, (u32)h->cap_c, nullptr);
+    enqueue_back_general(h, rp);
+  }
   cudaEventRecord(h->ev1, h->stream);
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaGetLastError());
@@ -736,7 +759,8 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
     if (h->stage_timing) cudaEventRecord(h->ev_k[1], h->stream);
     h->launches++;
   }
-  launch_front_pass2<false>(h, g, crop, gk, (u32)h->cap_c, nullptr, sgrid);
+  launch_keep_mask(h, g, crop, gk, sgrid);
+  h->gathered = false;
   h->ran_ground = ground != nullptr;
   h->rp.d = *d;
   h->rp.vk = vk;
@@ -945,6 +969,7 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   }
   A(dalloc(h, &h->d_desc_a, h->tiles_cap));
   A(dalloc(h, &h->d_frame_ticket, 1));
+  A(dalloc(h, &h->d_ncrop_f, F));
   A(dalloc(h, &h->d_desc_fv, F));
   A(dalloc(h, &h->d_desc_fk, F));
   A(dalloc(h, &h->d_mask, (size_t)h->tiles_cap * kTileWords));
@@ -1050,10 +1075,31 @@ cp_status cp_batch_set_host_input(cp_handle* h, const cp_cloud_view* frames, uin
   if (st) return st;
   size_t off = 0;
   int ring = 0;
-  for (u32 f = 0; f < n_frames; ++f) {
-    st = stage_view(h, &frames[f], off, &ring);
+  // frames that sit back to back in host memory (a replay buffer, a pinned batch tensor) are
+  // copied as one run: few large cudaMemcpyAsync calls instead of one per frame
+  for (u32 f = 0; f < n_frames;) {
+    const cp_cloud_view& v0 = frames[f];
+    const size_t step = v0.point_step;
+    auto packed = [&](const cp_cloud_view& v) { return v.height <= 1 || v.row_step == (size_t)v.width * v.point_step; };
+    size_t run_bytes = (size_t)fp[f] * step;
+    u32 e = f + 1;
+    if (packed(v0))
+      while (e < n_frames && packed(frames[e]) && frames[e].data == v0.data + run_bytes) {
+        run_bytes += (size_t)fp[e] * step;
+        ++e;
+      }
+    if (e == f + 1) {
+      st = stage_view(h, &v0, off, &ring);
+    } else {
+      cp_cloud_view run = v0;
+      run.height = 1;
+      run.width = (u32)(run_bytes / step);
+      run.row_step = (u32)std::min<size_t>(run_bytes, 0xFFFFFFFFu);
+      st = (run_bytes / step < (1ull << 32)) ? stage_view(h, &run, off, &ring) : CP_E_CAPACITY;
+    }
     if (st) return st;
-    off += (size_t)fp[f] * frames[f].point_step;
+    off += run_bytes;
+    f = e;
   }
   h->layout = make_layout(frames[0].point_step, frames[0].off_x, frames[0].off_y, frames[0].off_z,
                           frames[0].off_intensity);
@@ -1106,12 +1152,13 @@ cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* 
     memcpy(cluster_offsets, s, sizeof(u32) * (F + 1));
   }
   if (counters) {
-    std::vector<u32> c_off(F + 1), v_off(F + 1), ncomp(F), kc(F), gc(F);
+    std::vector<u32> c_off(F + 1), v_off(F + 1), ncomp(F), kc(F), gc(F), nc(F);
     std::vector<VoxelFrame> vf(F);
     CK(cudaMemcpyAsync(c_off.data(), h->d_c_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(v_off.data(), h->d_v_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(ncomp.data(), h->d_ncomp_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(kc.data(), h->d_kcount_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(nc.data(), h->d_ncrop_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(gc.data(), h->d_gcount, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(vf.data(), h->d_vf, sizeof(VoxelFrame) * F, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1119,7 +1166,7 @@ cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* 
       cp_frame_counters& c = counters[f];
       c.n_points = h->hg.frame_n[f];
       c.n_ground_kept = h->counted_ground ? gc[f] : 0xFFFFFFFFu;  // only counted when the filler point matters
-      c.n_cropped = c_off[f + 1] - c_off[f];
+      c.n_cropped = h->gathered ? c_off[f + 1] - c_off[f] : nc[f];
       c.n_voxels = v_off[f + 1] - v_off[f];
       c.n_components = ncomp[f];
       c.n_clusters = kc[f];
@@ -1191,9 +1238,10 @@ cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_groun
   gk.do_ground = 1;
   gk.want_count = 0;
   gk.pad_survives = 0;
-  launch_front_pass2<true>(h, geo, crop, gk, n, h->d_out32, sgrid);
+  launch_keep_mask(h, geo, crop, gk, sgrid);
+  launch_scan_gather<true>(h, geo, gk, n, h->d_out32);
   pad_zero_points_kernel<<<grid_for(n, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_out32, h->d_ctl, n);
-  h->launches += 2;
+  h->launches += 1;
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_xyzi32, h->d_out32, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
   if (low17) CK(cudaMemcpyAsync(h->h_frame_u32, h->d_low_key, sizeof(u32) * kNSect, cudaMemcpyDeviceToHost, h->stream));
