@@ -43,10 +43,9 @@ struct FrameArgs {
   u32* ncomp_f;              // [F]
   u32* kcount_f;             // [F]
   u32* ncrop_f;              // [F] survivors per frame
-  ClusterRec* clusters;      // packed, canonical order per frame
-  u32 clusters_cap;
+  ClusterRec* slots;         // [F][VMAX] per-frame result slots, canonical order inside a frame
+  u32* nvox_f;               // [F] voxels per frame
   u64* desc_v;               // frame descriptors for the voxel offsets
-  u64* desc_k;               // frame descriptors for the cluster offsets
   Ctl* ctl;
   u32* ticket;               // frame ticket (zeroed before the launch)
   // taps (NULL when off)
@@ -185,23 +184,30 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
         u32 total;
         u32 pos = C + block_excl_scan(cnt, s.wsum, total);
         if (cnt && C + total <= (u32)CMAX) {
+          // phase 1: only the frame-local point indices, in order (k0 is free until the sort)
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             u32 bits = w[k];
             while (bits) {
               const u32 b = (u32)__ffs(bits) - 1u;
               bits &= bits - 1;
-              const float4 p = load_point<MODE>(a.in, first + (u64)(wb + k) * 32 + b, a.layout);
-              s.px[pos] = p.x; s.py[pos] = p.y; s.pz[pos] = p.z; s.pw[pos] = p.w;
-              ++pos;
-              const u32 kx = f2ord(p.x), ky = f2ord(p.y), kz = f2ord(p.z);
-              mnx = min(mnx, kx); mxx = max(mxx, kx);
-              mny = min(mny, ky); mxy = max(mxy, ky);
-              mnz = min(mnz, kz); mxz = max(mxz, kz);
+              s.k0[pos++] = (wb + k) * 32 + b;
             }
           }
         }
         C += total;
+      }
+      __syncthreads();
+      // phase 2: all threads fetch points in parallel (independent loads, no serial chains)
+      if (C <= (u32)CMAX) {
+        for (u32 i = tid; i < C; i += kFrameThreads) {
+          const float4 p = load_point<MODE>(a.in, first + s.k0[i], a.layout);
+          s.px[i] = p.x; s.py[i] = p.y; s.pz[i] = p.z; s.pw[i] = p.w;
+          const u32 kx = f2ord(p.x), ky = f2ord(p.y), kz = f2ord(p.z);
+          mnx = min(mnx, kx); mxx = max(mxx, kx);
+          mny = min(mny, ky); mxy = max(mxy, ky);
+          mnz = min(mnz, kz); mxz = max(mxz, kz);
+        }
       }
       (void)npts;
       mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny);
@@ -360,18 +366,26 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
     const bool slow = s.slow != 0;
     if (slow) V = 0;
 
-    // ---- voxel offsets across frames (look-back in frame order)
-    if (warp == 0) {
-      const u32 e = lookback_exclusive(a.desc_v, f, V);
-      if (lane == 0) {
-        s.v_excl = e;
-        a.v_off[f] = e;
-        if (f + 1 == a.n_frames) {
-          a.v_off[f + 1] = e + V;
-          a.ctl->n_vox = e + V;
+    // ---- voxel offsets across frames: only the parity taps need them (look-back in frame
+    // order); the production path keeps frames independent
+    if (a.tap_vox) {
+      if (warp == 0) {
+        const u32 e = lookback_exclusive(a.desc_v, f, V);
+        if (lane == 0) {
+          s.v_excl = e;
+          a.v_off[f] = e;
+          if (f + 1 == a.n_frames) {
+            a.v_off[f + 1] = e + V;
+            a.ctl->n_vox = e + V;
+          }
         }
-        if (slow) atomicAdd(&a.ctl->fast_overflow, 1u);
       }
+    } else if (tid == 0) {
+      s.v_excl = 0;
+    }
+    if (tid == 0) {
+      a.nvox_f[f] = V;
+      if (slow) atomicAdd(&a.ctl->fast_overflow, 1u);
     }
     __syncthreads();
     const u32 v_excl = s.v_excl;
@@ -518,27 +532,16 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
       s.n_comp = 0;
     }
 
-    // ---- cluster offsets across frames
-    if (warp == 0) {
-      const u32 e = lookback_exclusive(a.desc_k, f, K);
-      if (lane == 0) {
-        s.k_excl = e;
-        a.k_off[f] = e;
-        a.kcount_f[f] = K;
-        a.ncomp_f[f] = s.n_comp;
-        if (f + 1 == a.n_frames) {
-          a.k_off[f + 1] = e + K;
-          a.ctl->n_clusters = e + K;
-        }
-        if ((u64)e + K > a.clusters_cap) atomicOr(&a.ctl->error, kErrVoxels);
-      }
+    // ---- per-frame results go to the frame's own slot; pack_clusters_kernel compacts them
+    if (tid == 0) {
+      a.kcount_f[f] = K;
+      a.ncomp_f[f] = s.n_comp;
     }
-    __syncthreads();
     // ---- S8/S9: centroid (src/cone_detection.cpp:261-273) and canonical rank, warp per cluster.
     // Lanes find the members 32 voxels at a time; the fp32 sums stay sequential in ascending
     // voxel index (every lane carries the same running sum).
     if (K > 0) {
-      const u32 k_excl = s.k_excl;
+      ClusterRec* slot = a.slots + (u64)f * VMAX;
       for (u32 k = warp; k < K; k += kFrameThreads / 32) {
         const u32 root = s.vstart[k];
         const u32 size = s.u.vox.csize[root];
@@ -568,11 +571,44 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
           o.y = __fdiv_rn(y, cnt);
           o.size = size;
           o.min_index = root;
-          if (k_excl + rank < a.clusters_cap) a.clusters[k_excl + rank] = o;
+          slot[rank] = o;
         }
       }
     }
   }
+}
+
+// compaction of the per-frame result slots into the packed cluster list + offsets.
+// One CTA per frame; every CTA sums the counts of the frames before it (F is small).
+__global__ void __launch_bounds__(256) pack_clusters_kernel(u32 n_frames, u32 slot_stride,
+                                                            const u32* __restrict__ kcount_f,
+                                                            const ClusterRec* __restrict__ slots,
+                                                            u32* __restrict__ k_off, ClusterRec* __restrict__ out,
+                                                            u32 out_cap, Ctl* ctl) {
+  __shared__ u32 wsum[8];
+  __shared__ u32 s_off;
+  const u32 f = blockIdx.x;
+  u32 part = 0;
+  for (u32 i = threadIdx.x; i < f; i += blockDim.x) part += kcount_f[i];
+  part = __reduce_add_sync(kFull, part);
+  if (lane_id() == 0) wsum[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 t = 0;
+    for (int w = 0; w < 8; ++w) t += wsum[w];
+    s_off = t;
+    k_off[f] = t;
+    if (f + 1 == n_frames) {
+      const u32 total = t + kcount_f[f];
+      k_off[n_frames] = total;
+      ctl->n_clusters = total;
+      if (total > out_cap) atomicOr(&ctl->error, kErrVoxels);
+    }
+  }
+  __syncthreads();
+  const u32 off = s_off, k = kcount_f[f];
+  for (u32 i = threadIdx.x; i < k; i += blockDim.x)
+    if (off + i < out_cap) out[off + i] = slots[(u64)f * slot_stride + i];
 }
 
 }  // namespace cp

@@ -62,6 +62,8 @@ struct cp_handle {
   u64 *d_desc_fv = nullptr, *d_desc_fk = nullptr;
   u32* d_frame_ticket = nullptr;
   u32* d_ncrop_f = nullptr;
+  u32* d_nvox_f = nullptr;
+  ClusterRec* d_slots = nullptr;  // [max_frames][2048] per-frame result slots of the fast back half
   bool gathered = false;  // the global scan + gather of the current run has been enqueued
 
   u64 cap_c = 0, cap_v = 0;
@@ -674,10 +676,9 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   fa.ncomp_f = h->d_ncomp_f;
   fa.kcount_f = h->d_kcount_f;
   fa.ncrop_f = h->d_ncrop_f;
-  fa.clusters = h->d_clusters;
-  fa.clusters_cap = (u32)h->cap_v;
+  fa.slots = h->d_slots;
+  fa.nvox_f = h->d_nvox_f;
   fa.desc_v = h->d_desc_fv;
-  fa.desc_k = h->d_desc_fk;
   fa.ctl = h->d_ctl;
   fa.ticket = h->d_frame_ticket;
   cudaMemsetAsync(h->d_frame_ticket, 0, sizeof(u32), h->stream);
@@ -693,6 +694,9 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
     case 1: launch_frame_kernel<CMAX, VMAX, 1>(h, fa); break;
     default: launch_frame_kernel<CMAX, VMAX, 2>(h, fa); break;
   }
+  pack_clusters_kernel<<<fa.n_frames, 256, 0, h->stream>>>(fa.n_frames, VMAX, h->d_kcount_f, h->d_slots, h->d_k_off,
+                                                           h->d_clusters, (u32)h->cap_v, h->d_ctl);
+  h->launches++;
 }
 
 cp_status enqueue_back(cp_handle* h, bool retry) {
@@ -970,6 +974,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   A(dalloc(h, &h->d_desc_a, h->tiles_cap));
   A(dalloc(h, &h->d_frame_ticket, 1));
   A(dalloc(h, &h->d_ncrop_f, F));
+  A(dalloc(h, &h->d_nvox_f, F));
+  A(dalloc(h, &h->d_slots, (size_t)F * 2048));
   A(dalloc(h, &h->d_desc_fv, F));
   A(dalloc(h, &h->d_desc_fk, F));
   A(dalloc(h, &h->d_mask, (size_t)h->tiles_cap * kTileWords));
@@ -1152,12 +1158,13 @@ cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* 
     memcpy(cluster_offsets, s, sizeof(u32) * (F + 1));
   }
   if (counters) {
-    std::vector<u32> c_off(F + 1), v_off(F + 1), ncomp(F), kc(F), gc(F), nc(F);
+    std::vector<u32> c_off(F + 1), v_off(F + 1), ncomp(F), kc(F), gc(F), nc(F), nv(F);
     std::vector<VoxelFrame> vf(F);
     CK(cudaMemcpyAsync(c_off.data(), h->d_c_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(v_off.data(), h->d_v_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(ncomp.data(), h->d_ncomp_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(kc.data(), h->d_kcount_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(nv.data(), h->d_nvox_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(nc.data(), h->d_ncrop_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(gc.data(), h->d_gcount, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(vf.data(), h->d_vf, sizeof(VoxelFrame) * F, cudaMemcpyDeviceToHost, h->stream));
@@ -1167,7 +1174,7 @@ cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* 
       c.n_points = h->hg.frame_n[f];
       c.n_ground_kept = h->counted_ground ? gc[f] : 0xFFFFFFFFu;  // only counted when the filler point matters
       c.n_cropped = h->gathered ? c_off[f + 1] - c_off[f] : nc[f];
-      c.n_voxels = v_off[f + 1] - v_off[f];
+      c.n_voxels = h->back_mode < 2 ? nv[f] : v_off[f + 1] - v_off[f];
       c.n_components = ncomp[f];
       c.n_clusters = kc[f];
       c.key_bits = vf[f].bits;
