@@ -61,6 +61,9 @@ struct cp_handle {
   RunParams rp{};
   u64 *d_desc_fv = nullptr, *d_desc_fk = nullptr;
   u32* d_frame_ticket = nullptr;
+  u32* d_done = nullptr;  // pass-1 tiles finished per frame (fused front kernel)
+  u32 fused_grid = 0;
+  bool use_fused = false, ran_fused = false;  // measured slower than two kernels: opt-in
   u32* d_ncrop_f = nullptr;
   u32* d_nvox_f = nullptr;
   ClusterRec* d_slots = nullptr;  // [max_frames][2048] per-frame result slots of the fast back half
@@ -466,6 +469,38 @@ void launch_scan_gather(cp_handle* h, const Geom& g, const GroundK& gk, u32 cap,
   h->launches += 2;
   h->gathered = true;
 }
+// both streaming passes in one persistent kernel (uniform batches with ground removal)
+void launch_front_fused(cp_handle* h, const Geom& g, const CropK& c, const GroundK& gk) {
+  MaskOut mo;
+  mo.mask = h->d_mask;
+  mo.tile_count = h->d_tile_count;
+  mo.gcount = h->d_gcount;
+  if (h->fused_grid == 0) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, front_fused_kernel<0>, kStreamThreads, 0);
+    if (occ < 1) occ = 1;
+    h->fused_grid = (u32)(h->sms * occ);
+  }
+  FusedArgs fa;
+  const u32 gf = (h->fused_grid + g.tpf - 1) / g.tpf;  // frames per group: one resident wave of tiles
+  fa.group_tiles = gf * g.tpf;
+  fa.n_groups = (g.n_frames + gf - 1) / gf;
+  fa.done = h->d_done;
+  fa.ticket = h->d_frame_ticket + 1;
+  cudaMemsetAsync(h->d_done, 0, sizeof(u32) * g.n_frames, h->stream);
+  cudaMemsetAsync(h->d_frame_ticket + 1, 0, sizeof(u32), h->stream);
+  const u32 items = fa.n_groups * fa.group_tiles * 2u;
+  const u32 grid = items < h->fused_grid ? items : h->fused_grid;
+  if (h->stage_timing) cudaEventRecord(h->ev_k[0], h->stream);
+  switch (h->layout.mode) {
+    case 0: front_fused_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo, fa); break;
+    case 1: front_fused_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo, fa); break;
+    default: front_fused_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo, fa); break;
+  }
+  if (h->stage_timing) cudaEventRecord(h->ev_k[1], h->stream);
+  h->launches++;
+}
+
 void launch_sector_min(cp_handle* h, const Geom& g, u32 grid) {
   switch (h->layout.mode) {
     case 0: ground_sector_min_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key); break;
@@ -757,13 +792,18 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   cudaEventRecord(h->ev0, h->stream);
   launch_init(h, ground ? ground->default_lowest_point : 0.0f);
   const u32 sgrid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, 8);
-  if (ground) {
-    if (h->stage_timing) cudaEventRecord(h->ev_k[0], h->stream);
-    launch_sector_min(h, g, sgrid);
-    if (h->stage_timing) cudaEventRecord(h->ev_k[1], h->stream);
-    h->launches++;
+  h->ran_fused = ground && g.uniform_n && h->use_fused;
+  if (h->ran_fused) {
+    launch_front_fused(h, g, crop, gk);
+  } else {
+    if (ground) {
+      if (h->stage_timing) cudaEventRecord(h->ev_k[0], h->stream);
+      launch_sector_min(h, g, sgrid);
+      if (h->stage_timing) cudaEventRecord(h->ev_k[1], h->stream);
+      h->launches++;
+    }
+    launch_keep_mask(h, g, crop, gk, sgrid);
   }
-  launch_keep_mask(h, g, crop, gk, sgrid);
   h->gathered = false;
   h->ran_ground = ground != nullptr;
   h->rp.d = *d;
@@ -910,6 +950,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   h->taps = tap_env && tap_env[0] == '1';
   const char* mode_env = getenv("CONESGPU_BACK_MODE");  // tests: force the back-half variant
   if (mode_env && mode_env[0] >= '0' && mode_env[0] <= '2') h->back_mode = mode_env[0] - '0';
+  const char* fused_env = getenv("CONESGPU_FUSED_FRONT");  // "1": both streaming passes in one persistent kernel
+  if (fused_env) h->use_fused = fused_env[0] == '1';
   const u64 P = cfg->max_points;
   const u32 F = cfg->max_frames;
   h->cap_c = cfg->max_survivors ? std::min<u64>(cfg->max_survivors, P + F) : P + F;
@@ -972,7 +1014,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
     h->d_clusters = reinterpret_cast<ClusterRec*>(block + off_words);
   }
   A(dalloc(h, &h->d_desc_a, h->tiles_cap));
-  A(dalloc(h, &h->d_frame_ticket, 1));
+  A(dalloc(h, &h->d_frame_ticket, 2));
+  A(dalloc(h, &h->d_done, F));
   A(dalloc(h, &h->d_ncrop_f, F));
   A(dalloc(h, &h->d_nvox_f, F));
   A(dalloc(h, &h->d_slots, (size_t)F * 2048));
@@ -1284,14 +1327,25 @@ cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms) {
     h->err = "cp_stage_ms needs cp_set_stage_timing(1) before the run";
     return CP_E_STATE;
   }
-  if (stage == CP_STAGE_SECTOR_MIN) {
-    if (!h->ran_ground) {
+  if (stage == CP_STAGE_FRONT_FUSED) {
+    if (!h->ran_fused) {
+      h->err = "the last run did not use the fused front kernel";
+      return CP_E_STATE;
+    }
+    CK(cudaEventSynchronize(h->ev_k[1]));
+    CK(cudaEventElapsedTime(ms, h->ev_k[0], h->ev_k[1]));
+  } else if (stage == CP_STAGE_SECTOR_MIN) {
+    if (!h->ran_ground || h->ran_fused) {
       h->err = "the last run had no ground removal";
       return CP_E_STATE;
     }
     CK(cudaEventSynchronize(h->ev_k[1]));
     CK(cudaEventElapsedTime(ms, h->ev_k[0], h->ev_k[1]));
   } else if (stage == CP_STAGE_MASK_CROP_COMPACT) {
+    if (h->ran_fused) {
+      h->err = "the last run used the fused front kernel";
+      return CP_E_STATE;
+    }
     CK(cudaEventSynchronize(h->ev_k[3]));
     CK(cudaEventElapsedTime(ms, h->ev_k[2], h->ev_k[3]));
   } else {

@@ -165,14 +165,62 @@ __device__ __forceinline__ bool finite3(float x, float y, float z) {
 }
 
 // ---- pass 1: per-sector minima ----------------------------------------------------------
+// prefilter bounds: max of smin over the sectors a quadrant can reach (slot 0: all sectors);
+// a point at or above its bound cannot lower any minimum.  Called by the whole CTA.
+__device__ __forceinline__ void sector_bounds(const u32* smin, u32* s_bound) {
+  const int lane = lane_id();
+  if ((threadIdx.x >> 5) == 0) {
+    // quadrant q = 1 + (x<0) + 2*(y<0) reaches sectors {0..4}, {4..8}, {12..16}, {8..12}
+    const u32 v = lane < kNSect ? smin[lane] : 0u;
+    const u32 ball = __reduce_max_sync(kFull, v);
+    const u32 b0 = __reduce_max_sync(kFull, lane <= 4 ? v : 0u);
+    const u32 b1 = __reduce_max_sync(kFull, (lane >= 4 && lane <= 8) ? v : 0u);
+    const u32 b2 = __reduce_max_sync(kFull, (lane >= 12 && lane <= 16) ? v : 0u);
+    const u32 b3 = __reduce_max_sync(kFull, (lane >= 8 && lane <= 12) ? v : 0u);
+    if (lane == 0) {
+      s_bound[0] = ball; s_bound[1] = b0; s_bound[2] = b1; s_bound[3] = b2; s_bound[4] = b3;
+    }
+  }
+  __syncthreads();
+}
+
+// one tile of pass 1 against the CTA's shared sector table (src/ground_removal.cpp:58-68)
+// the tile's points, warp-contiguous rows; out-of-range lanes get z = pad_z
 template <int MODE>
-__global__ void __launch_bounds__(kStreamThreads)
+__device__ __forceinline__ void load_tile(const uint8_t* __restrict__ in, const Layout& L, u64 base, u32 count,
+                                          float pad_z, float4 (&p)[kStreamRows]) {
+  const u32 wbase = (threadIdx.x >> 5) * (32 * kStreamRows) + lane_id();
+#pragma unroll
+  for (int r = 0; r < kStreamRows; ++r) {
+    const u32 i = wbase + r * 32;
+    p[r] = (i < count) ? load_point<MODE>(in, base + i, L) : make_float4(0.f, 0.f, pad_z, 0.f);
+  }
+}
+
+// out-of-range lanes must carry z = +inf (key above every bound, skipped by the prefilter)
+__device__ __forceinline__ void sector_min_tile(const float4 (&p)[kStreamRows], u32* smin, const u32* s_bound) {
+#pragma unroll
+  for (int r = 0; r < kStreamRows; ++r) {
+    const u32 zk = f2ord(p[r].z);
+    const float x = p[r].x, y = p[r].y;
+    // points on an axis (or with a vanishing product) use the all-sector bound
+    const u32 q = (x * y == 0.0f) ? 0u : 1u + (x < 0.0f ? 1u : 0u) + (y < 0.0f ? 2u : 0u);
+    if (zk < s_bound[q]) {
+      if (finite3(x, y, p[r].z)) {
+        bool ok;
+        const float a = atan2_approx(y, x, ok);
+        const int s = sector_of(x, y, a, ok);
+        if (zk < smin[s]) atomicMin(&smin[s], zk);   // src/ground_removal.cpp:65-67
+      }
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kStreamThreads, 4)
 ground_sector_min_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, u32* __restrict__ low_key) {
   __shared__ u32 smin[kSectStride];
-  // prefilter bounds: max of smin over the sectors a quadrant can reach (0: all sectors);
-  // a point at or above its bound cannot lower any minimum
   __shared__ u32 s_bound[5];
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
   // contiguous chunk of tiles per CTA so the shared table is flushed once per frame change
   const u32 per = (g.n_tiles + gridDim.x - 1) / gridDim.x;
   const u32 t0 = blockIdx.x * per;
@@ -188,48 +236,14 @@ ground_sector_min_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, u32* 
         atomicMin(&low_key[cur_frame * kSectStride + threadIdx.x], smin[threadIdx.x]);
       // seed from the frame's global table: the default and whatever other CTAs found so far
       if (threadIdx.x < kSectStride)
-        smin[threadIdx.x] = threadIdx.x < kNSect
-                                ? ((volatile u32*)low_key)[frame * kSectStride + threadIdx.x] : 0u;
+        smin[threadIdx.x] = threadIdx.x < kNSect ? __ldcg(&low_key[frame * kSectStride + threadIdx.x]) : 0u;
       cur_frame = frame;
     }
     __syncthreads();
-    if (warp == 0) {
-      // quadrant q = (x<0) | (y<0)<<1 reaches sectors {0..4}, {4..8}, {12..16}, {8..12}
-      const u32 v = lane < kNSect ? smin[lane] : 0u;
-      const u32 ball = __reduce_max_sync(kFull, v);
-      const u32 b0 = __reduce_max_sync(kFull, lane <= 4 ? v : 0u);
-      const u32 b1 = __reduce_max_sync(kFull, (lane >= 4 && lane <= 8) ? v : 0u);
-      const u32 b2 = __reduce_max_sync(kFull, (lane >= 12 && lane <= 16) ? v : 0u);
-      const u32 b3 = __reduce_max_sync(kFull, (lane >= 8 && lane <= 12) ? v : 0u);
-      if (lane == 0) {
-        s_bound[0] = ball; s_bound[1] = b0; s_bound[2] = b1; s_bound[3] = b2; s_bound[4] = b3;
-      }
-    }
-    __syncthreads();
-    const u32 wbase = warp * (32 * kStreamRows);
+    sector_bounds(smin, s_bound);
     float4 p[kStreamRows];
-#pragma unroll
-    for (int r = 0; r < kStreamRows; ++r) {
-      const u32 i = wbase + r * 32 + lane;
-      // out-of-range lanes get z = +inf: key above every bound, skipped by the prefilter
-      p[r] = (i < count) ? load_point<MODE>(in, first + local0 + i, L)
-                         : make_float4(0.f, 0.f, __int_as_float(0x7f800000), 0.f);
-    }
-#pragma unroll
-    for (int r = 0; r < kStreamRows; ++r) {
-      const u32 zk = f2ord(p[r].z);
-      const float x = p[r].x, y = p[r].y;
-      // points on an axis (or with a vanishing product) use the all-sector bound
-      const u32 q = (x * y == 0.0f) ? 0u : 1u + (x < 0.0f ? 1u : 0u) + (y < 0.0f ? 2u : 0u);
-      if (zk < s_bound[q]) {
-        if (finite3(x, y, p[r].z)) {
-          bool ok;
-          const float a = atan2_approx(y, x, ok);
-          const int s = sector_of(x, y, a, ok);
-          if (zk < smin[s]) atomicMin(&smin[s], zk);   // src/ground_removal.cpp:65-67
-        }
-      }
-    }
+    load_tile<MODE>(in, L, first + local0, count, __int_as_float(0x7f800000), p);
+    sector_min_tile(p, smin, s_bound);
   }
   __syncthreads();
   if (cur_frame != 0xFFFFFFFFu && threadIdx.x < kNSect)
@@ -259,14 +273,93 @@ struct MaskOut {
   u32* gcount;      // [F] ground survivors (when want_count)
 };
 
+// per-frame thresholds: :75  p.z < low + 0.1 in double  <=>  z < roundup_to_float((double)low + 0.1).
+// Called by the whole CTA; thr[17] and *thr_min live in shared memory.
+__device__ __forceinline__ void ground_thresholds(const u32* __restrict__ low_key, u32 frame, float* thr,
+                                                  float* thr_min) {
+  const int lane = lane_id();
+  if ((threadIdx.x >> 5) == 0) {
+    float t = __int_as_float(0x7f800000);
+    if (lane < kNSect) {
+      t = __double2float_ru((double)ord2f(__ldcg(&low_key[frame * kSectStride + lane])) + 0.1);
+      thr[lane] = t;
+    }
+#pragma unroll
+    for (int o2 = 16; o2; o2 >>= 1) t = fminf(t, __shfl_xor_sync(kFull, t, o2));
+    if (lane == 0) *thr_min = t;
+  }
+  __syncthreads();
+}
+
+// one tile of pass 2: keep bits (src/ground_removal.cpp:70-77 + src/cone_detection.cpp:189-204)
+// out-of-range lanes carry z = -inf (load_tile pad): dropped by `i < count` anyway
+__device__ __forceinline__ void keep_mask_tile(const float4 (&p)[kStreamRows], u32 count, const CropK& c,
+                                               const GroundK& gk, const float* thr, float thr_min,
+                                               u32* __restrict__ mask_words, u32* wtot, u32& gkept_out) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const u32 wbase = warp * (32 * kStreamRows);
+  u32 wcount = 0, gkept = 0, myword = 0;
+#pragma unroll
+  for (int r = 0; r < kStreamRows; ++r) {
+    const u32 i = wbase + r * 32 + lane;
+    const float x = p[r].x, y = p[r].y, z = p[r].z;
+    bool keep = false;
+    // ground prefilter: below the lowest threshold of any sector => ground everywhere
+    // (without the per-frame count, points failing the crop need no ground verdict either)
+    if ((i < count) && !(z < thr_min) && finite3(x, y, z)) {
+      keep = !c.do_crop || crop_keep(c, x, y, z);
+      if (keep || gk.want_count) {
+        bool ok;
+        const float a = atan2_approx(y, x, ok);
+        if (keep && c.do_crop) {
+          const float aa = fabsf(a);
+          if (!ok | (aa > c.f_lo_guard)) {
+            if (ok & (aa >= c.f_hi_guard)) keep = false;
+            else keep = fabsf(atan2_exact(y, x)) < c.f_hi;  // src/cone_detection.cpp:200-201
+          }
+        }
+        if (gk.do_ground && (keep || gk.want_count)) {
+          const int s = sector_of(x, y, a, ok);
+          const bool gkeep = !(z < thr[s]);
+          if (gkeep) gkept++;
+          keep = keep && gkeep;
+        }
+      }
+    }
+    const u32 bal = __ballot_sync(kFull, keep);
+    wcount += __popc(bal);
+    if (lane == r) myword = bal;
+  }
+  if (lane < kStreamRows) mask_words[warp * kStreamRows + lane] = myword;
+  if (lane == 0) wtot[warp] = wcount;
+  gkept_out = gkept;
+}
+
+// tile epilogue: survivors of the tile (+ the pad record on a frame's last tile); whole CTA
+__device__ __forceinline__ void keep_mask_finish(const Geom& g, const GroundK& gk, u32 tile, u32 frame, u32 local0,
+                                                 u32 count, const u32* wtot, u32 gkept, const MaskOut& o) {
+  if (gk.want_count) {
+    const u32 gsum = __reduce_add_sync(kFull, gkept);
+    if (lane_id() == 0 && gsum) atomicAdd(&o.gcount[frame], gsum);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 total = 0;
+#pragma unroll
+    for (int w = 0; w < kStreamWarps; ++w) total += wtot[w];
+    const bool last_of_frame = (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]);
+    o.tile_count[tile] = total + ((gk.pad_survives && last_of_frame) ? 1u : 0u);
+  }
+  __syncthreads();
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kStreamThreads)
+__global__ void __launch_bounds__(kStreamThreads, 4)
 keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, GroundK gk,
                  const u32* __restrict__ low_key, MaskOut o) {
   __shared__ float thr[kSectStride];
   __shared__ float s_thr_min;
   __shared__ u32 wtot[kStreamWarps];
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
   const u32 per = (g.n_tiles + gridDim.x - 1) / gridDim.x;
   const u32 t0 = blockIdx.x * per;
   const u32 t1 = t0 + per < g.n_tiles ? t0 + per : g.n_tiles;
@@ -277,76 +370,90 @@ keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, Grou
     tile_lookup(g, tile, frame, local0, count, first);
     if (gk.do_ground && frame != cur_frame) {
       __syncthreads();
-      if (warp == 0) {
-        // :75  p.z < low + 0.1 in double  <=>  z < roundup_to_float((double)low + 0.1)
-        float t = __int_as_float(0x7f800000);
-        if (lane < kNSect) {
-          t = __double2float_ru((double)ord2f(low_key[frame * kSectStride + lane]) + 0.1);
-          thr[lane] = t;
-        }
-#pragma unroll
-        for (int o2 = 16; o2; o2 >>= 1) t = fminf(t, __shfl_xor_sync(kFull, t, o2));
-        if (lane == 0) s_thr_min = t;
-      }
-      __syncthreads();
+      ground_thresholds(low_key, frame, thr, &s_thr_min);
     }
     cur_frame = frame;
-    const float thr_min = gk.do_ground ? s_thr_min : -__int_as_float(0x7f800000);
-    const u32 wbase = warp * (32 * kStreamRows);
     float4 p[kStreamRows];
-#pragma unroll
-    for (int r = 0; r < kStreamRows; ++r) {
-      const u32 i = wbase + r * 32 + lane;
-      p[r] = (i < count) ? load_point<MODE>(in, first + local0 + i, L)
-                         : make_float4(0.f, 0.f, -__int_as_float(0x7f800000), 0.f);  // z = -inf: dropped
-    }
-    u32 wcount = 0, gkept = 0, myword = 0;
-#pragma unroll
-    for (int r = 0; r < kStreamRows; ++r) {
-      const u32 i = wbase + r * 32 + lane;
-      const float x = p[r].x, y = p[r].y, z = p[r].z;
-      bool keep = false;
-      // ground prefilter: below the lowest threshold of any sector => ground everywhere
-      // (without the per-frame count, points failing the crop need no ground verdict either)
-      if ((i < count) && !(z < thr_min) && finite3(x, y, z)) {
-        keep = !c.do_crop || crop_keep(c, x, y, z);
-        if (keep || gk.want_count) {
-          bool ok;
-          const float a = atan2_approx(y, x, ok);
-          if (keep && c.do_crop) {
-            const float aa = fabsf(a);
-            if (!ok | (aa > c.f_lo_guard)) {
-              if (ok & (aa >= c.f_hi_guard)) keep = false;
-              else keep = fabsf(atan2_exact(y, x)) < c.f_hi;  // src/cone_detection.cpp:200-201
-            }
-          }
-          if (gk.do_ground && (keep || gk.want_count)) {
-            const int s = sector_of(x, y, a, ok);
-            const bool gkeep = !(z < thr[s]);
-            if (gkeep) gkept++;
-            keep = keep && gkeep;
-          }
-        }
+    load_tile<MODE>(in, L, first + local0, count, -__int_as_float(0x7f800000), p);
+    const float thr_min = gk.do_ground ? s_thr_min : -__int_as_float(0x7f800000);
+    u32 gkept;
+    keep_mask_tile(p, count, c, gk, thr, thr_min, o.mask + (u64)tile * kTileWords, wtot, gkept);
+    keep_mask_finish(g, gk, tile, frame, local0, count, wtot, gkept, o);
+  }
+}
+
+// ---- both passes in ONE persistent kernel (uniform batches with ground removal) ---------
+// Work items are handed out by ticket in the order
+//     [pass 1 of frame group 0] [pass 2 of group 0] [pass 1 of group 1] [pass 2 of group 1] ...
+// A pass-2 item waits until all pass-1 tiles of its frame have published their minima
+// (done[frame] == tiles per frame).  It can only wait on items with smaller tickets, which
+// running CTAs hold and which never wait themselves, so the kernel cannot deadlock.  A group
+// is a few frames (tens of MB), so pass 2 re-reads its points from the 126 MB L2 instead
+// of HBM: the scan crosses the HBM interface once.
+struct FusedArgs {
+  u32 group_tiles;     // tiles per frame group (multiple of tiles per frame)
+  u32 n_groups;
+  u32* done;           // [F] pass-1 tiles finished per frame (zeroed before the launch)
+  u32* ticket;         // zeroed before the launch
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kStreamThreads)
+front_fused_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, GroundK gk, u32* __restrict__ low_key,
+                   MaskOut o, FusedArgs fa) {
+  __shared__ u32 smin[kSectStride];
+  __shared__ u32 sseed[kSectStride];
+  __shared__ u32 s_bound[5];
+  __shared__ float thr[kSectStride];
+  __shared__ float s_thr_min;
+  __shared__ u32 wtot[kStreamWarps];
+  __shared__ u32 s_ticket;
+  const u32 total_items = fa.n_groups * fa.group_tiles * 2u;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(fa.ticket, 1u);
+    __syncthreads();
+    const u32 t = s_ticket;
+    if (t >= total_items) break;
+    const u32 blk = t / fa.group_tiles;
+    const u32 tile = (blk >> 1) * fa.group_tiles + (t - blk * fa.group_tiles);
+    if (tile >= g.n_tiles) continue;   // the last group may be partial
+    u32 frame, local0, count;
+    u64 first;
+    tile_lookup(g, tile, frame, local0, count, first);
+    float4 p[kStreamRows];
+    if ((blk & 1u) == 0) {
+      // ---- pass 1 item: the point loads are in flight while the sector table is seeded
+      load_tile<MODE>(in, L, first + local0, count, __int_as_float(0x7f800000), p);
+      if (threadIdx.x < kSectStride) {
+        const u32 v = threadIdx.x < kNSect ? __ldcg(&low_key[frame * kSectStride + threadIdx.x]) : 0u;
+        smin[threadIdx.x] = v;
+        sseed[threadIdx.x] = v;
       }
-      const u32 bal = __ballot_sync(kFull, keep);
-      wcount += __popc(bal);
-      if (lane == r) myword = bal;
+      __syncthreads();
+      sector_bounds(smin, s_bound);
+      sector_min_tile(p, smin, s_bound);
+      __syncthreads();
+      if (threadIdx.x < kNSect && smin[threadIdx.x] < sseed[threadIdx.x])
+        atomicMin(&low_key[frame * kSectStride + threadIdx.x], smin[threadIdx.x]);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();  // the CTA's minima (ordered before by the barrier) are visible before the count
+        atomicAdd(&fa.done[frame], 1u);
+      }
+    } else {
+      // ---- pass 2 item: all pass-1 tiles of this frame must be in; loads first (L2 hits)
+      load_tile<MODE>(in, L, first + local0, count, -__int_as_float(0x7f800000), p);
+      if (threadIdx.x == 0) {
+        while (((volatile u32*)fa.done)[frame] < g.tpf) __nanosleep(64);
+        __threadfence();
+      }
+      __syncthreads();
+      ground_thresholds(low_key, frame, thr, &s_thr_min);
+      u32 gkept;
+      keep_mask_tile(p, count, c, gk, thr, s_thr_min, o.mask + (u64)tile * kTileWords, wtot, gkept);
+      keep_mask_finish(g, gk, tile, frame, local0, count, wtot, gkept, o);
     }
-    if (lane < kStreamRows) o.mask[(u64)tile * kTileWords + warp * kStreamRows + lane] = myword;
-    if (lane == 0) wtot[warp] = wcount;
-    if (gk.want_count) {
-      const u32 gsum = __reduce_add_sync(kFull, gkept);
-      if (lane == 0 && gsum) atomicAdd(&o.gcount[frame], gsum);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      u32 total = 0;
-#pragma unroll
-      for (int w = 0; w < kStreamWarps; ++w) total += wtot[w];
-      const bool last_of_frame = (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]);
-      o.tile_count[tile] = total + ((gk.pad_survives && last_of_frame) ? 1u : 0u);
-    }
-    __syncthreads();
   }
 }
 

@@ -159,7 +159,11 @@ cp_status cp_detect_batch(cp_handle* h, const cp_cloud_view* frames, uint32_t n_
 cp_status cp_last_run_ms(cp_handle* h, float* ms);
 /* Per-kernel device times of the two streaming passes (CUDA events on the handle's stream
  * around each launch).  Off by default; bench.py switches it on for the roofline pass. */
-typedef enum cp_stage { CP_STAGE_SECTOR_MIN = 0, CP_STAGE_MASK_CROP_COMPACT = 1 } cp_stage;
+typedef enum cp_stage {
+  CP_STAGE_SECTOR_MIN = 0,        /* ground_sector_min_kernel (two-kernel front end)   */
+  CP_STAGE_MASK_CROP_COMPACT = 1, /* keep_mask_kernel (two-kernel front end)           */
+  CP_STAGE_FRONT_FUSED = 2        /* front_fused_kernel: both passes, one HBM crossing */
+} cp_stage;
 cp_status cp_set_stage_timing(cp_handle* h, int on);
 cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms);
 /* Device pointers of the last run's results (valid until the next run on this handle):
