@@ -136,3 +136,122 @@ def test_golden_fixtures_on_gpu(gpu):
         assert np.array_equal(cl.view(np.uint32), z["clusters"].view(np.uint32)), f"cfg{idx} seed {seed}"
         assert [int(ctr["n_cropped"]), int(ctr["n_voxels"]), int(ctr["n_components"]), int(ctr["n_clusters"]),
                 int(ctr["key_bits"])] == z["counters"].tolist()[2:]
+
+
+def _msg_with_layout(xyzi, point_step, offs, intensity=True, height=1, row_pad=0):
+    """PointCloud2 with arbitrary point_step / field offsets / row padding around the same points."""
+    from cones_perception_b200.pointcloud2 import PointField
+    n = len(xyzi)
+    width = n // height
+    assert width * height == n
+    row_step = width * point_step + row_pad
+    raw = np.random.default_rng(5).integers(0, 255, height * row_step, dtype=np.uint8)  # junk between fields
+    src = np.ascontiguousarray(xyzi, np.float32).view(np.uint8).reshape(n, 16)
+    for r in range(height):
+        for k, o in enumerate(offs):
+            if k == 3 and not intensity:
+                continue
+            cols = (np.arange(width)[:, None] * point_step + o + np.arange(4)[None, :]) + r * row_step
+            raw[cols.reshape(-1)] = src[r * width:(r + 1) * width, 4 * k:4 * k + 4].reshape(-1)
+    names = ["x", "y", "z", "intensity"]
+    fields = [PointField(names[k], offs[k]) for k in range(4 if intensity else 3)]
+    return PointCloud2(data=raw, width=width, height=height, point_step=point_step, row_step=row_step, fields=fields)
+
+
+@pytest.mark.parametrize("point_step,offs,intensity,height,row_pad", [
+    (32, (0, 4, 8, 16), True, 1, 0),      # PCL PointXYZI layout: what the ground_removal node publishes
+    (48, (4, 12, 20, 32), True, 1, 0),    # 4-byte aligned, reordered, padded (Ouster-like)
+    (22, (0, 4, 8, 12), True, 1, 0),      # Velodyne-like unaligned point_step
+    (19, (1, 6, 11, 15), True, 1, 0),     # everything unaligned
+    (16, (0, 4, 8, 12), False, 1, 0),     # no intensity field: faked at offset 0 (aliases x)
+    (32, (0, 4, 8, 16), True, 16, 64),    # organised cloud with row padding
+])
+def test_pointcloud2_layouts(gpu, point_step, offs, intensity, height, row_pad):
+    cfg = scans.config(1)
+    frame = scans.generate(cfg, 1, base_seed=77)[0][:29_984]   # divisible by 16 rows
+    msg = _msg_with_layout(frame, point_step, offs, intensity, height, row_pad)
+    for g in (None, GroundParams()):
+        cl, ctr = gpu.detect(msg, cfg.detect, g)
+        exp, octr, _ = O.detect(O.view_of_msg(msg, fake_missing_intensity=True), cfg.detect, g, O.CANONICAL)
+        assert len(cl) == len(exp) and len(cl) > 0
+        assert np.array_equal(cl.view(np.uint32), exp.view(np.uint32))
+        assert int(ctr["n_voxels"]) == octr.n_voxels
+    out, kept, low = gpu.ground_remove(msg, GroundParams())
+    eout, ekept, elow, _ = O.ground_node(O.view_of_msg(msg, fake_missing_intensity=False), GroundParams())
+    e = np.stack([eout[n] for n in ("x", "y", "z", "pad", "intensity", "c1", "c2", "c3")], 1)
+    assert kept == ekept and np.array_equal(out.view(np.uint32), e.view(np.uint32))
+
+
+def test_chained_nodes_equal_fused(gpu):
+    """ground_removal node -> groundless_cloud topic -> cone_detection node (the reference's launch
+    wiring) gives the same cones as the fused call, and both equal the oracle."""
+    from cones_perception_b200.pointcloud2 import PointField
+    cfg = scans.config(2)
+    frame = scans.generate(cfg, 1, base_seed=78)[0]
+    msg = PointCloud2.from_xyzi(frame)
+    out32, kept, _ = gpu.ground_remove(msg, GroundParams())
+    groundless = PointCloud2(data=out32.view(np.uint8).reshape(-1), width=len(frame), point_step=32,
+                             fields=[PointField("x", 0), PointField("y", 4), PointField("z", 8),
+                                     PointField("intensity", 16)])
+    chained, _ = gpu.detect(groundless, cfg.detect, None)
+    fused, _ = gpu.detect(msg, cfg.detect, GroundParams())
+    exp, _, _ = O.detect(O.view_of_xyzi(frame), cfg.detect, GroundParams(), O.CANONICAL)
+    assert np.array_equal(chained.view(np.uint32), exp.view(np.uint32))
+    assert np.array_equal(fused.view(np.uint32), exp.view(np.uint32))
+
+
+def test_capacity_and_parameter_errors(gpu):
+    cfg = scans.config(1)
+    frame = scans.generate(cfg, 1, base_seed=3)[0]
+    msg = PointCloud2.from_xyzi(frame)
+    with api.ConesGpu(max_points=1000, max_frames=1) as small:
+        with pytest.raises(api.ConesGpuError) as e:
+            small.detect(msg, cfg.detect, None)
+        assert e.value.status == api.CP_E_CAPACITY
+    with pytest.raises(api.ConesGpuError) as e:
+        gpu.detect(msg, cfg.detect, None, cap=2)          # output buffer too small: never truncated
+    assert e.value.status == api.CP_E_CAPACITY
+    bad = PointCloud2.from_xyzi(frame)
+    bad.fields = bad.fields[1:]                           # no x field
+    with pytest.raises(api.ConesGpuError) as e:
+        gpu.detect(bad, cfg.detect, None)
+    assert e.value.status == api.CP_E_BADFIELD
+    import dataclasses
+    d = dataclasses.replace(cfg.detect, voxel_filter_leaf_size_x=0.0)
+    with pytest.raises(api.ConesGpuError) as e:
+        gpu.detect(msg, d, None)
+    assert e.value.status == api.CP_E_PARAM
+    # survivors overflow is reported, not truncated
+    with api.ConesGpu(max_points=len(frame), max_frames=1, max_survivors=16, back_mode=2) as tiny:
+        with pytest.raises(api.ConesGpuError) as e:
+            tiny.detect(msg, cfg.detect, None)
+        assert e.value.status == api.CP_E_CAPACITY
+
+
+def test_empty_and_all_ground_frames(gpu):
+    cfg = scans.config(2)
+    empty = np.zeros((0, 4), np.float32)
+    rng = np.random.default_rng(0)
+    ground = np.zeros((5000, 4), np.float32)
+    ground[:, 0] = rng.uniform(2, 6, 5000)
+    ground[:, 1] = rng.uniform(-3, 3, 5000)
+    ground[:, 2] = -0.6 + rng.normal(0, 0.002, 5000)
+    real = scans.generate(cfg, 1, base_seed=9)[0]
+    ctr, k_off, clusters, offs, taps = run_batch_with_taps(gpu, [empty, ground, real, empty], cfg.detect, cfg.ground)
+    assert ctr["n_clusters"].tolist()[:2] == [0, 0] and ctr["n_clusters"][3] == 0 and ctr["n_clusters"][2] > 0
+    assert ctr["n_cropped"][1] == 0
+    for f, a in enumerate([empty, ground, real, empty]):
+        assert_frame_parity(gpu, f, oracle_stages(a, cfg.detect, cfg.ground), offs, taps, ctr, k_off, clusters)
+
+
+def test_zero_padding_survives_when_dmin_is_zero(gpu):
+    """distance_treshold_min <= 0: the ground node's zero filler points survive the crop
+    (src/ground_removal.cpp:79 + src/cone_detection.cpp:197) and join the voxel at the origin."""
+    import dataclasses
+    cfg = scans.config(2)
+    frame = scans.generate(cfg, 1, base_seed=12)[0]
+    d = dataclasses.replace(cfg.detect, distance_treshold_min=0.0, level_threshold=-5.0)
+    ora = oracle_stages(frame, d, GroundParams())
+    assert (ora["crop_index"] < 0).sum() > 1000                     # the filler points are really there
+    ctr, k_off, clusters, offs, taps = run_batch_with_taps(gpu, [frame], d, GroundParams())
+    assert_frame_parity(gpu, 0, ora, offs, taps, ctr, k_off, clusters)
