@@ -241,23 +241,28 @@ def run_ours(args):
     gathered = [None]
     step_no = [0]
 
+    src_view = [None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
+    freed = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
+
     def step_device():
         gpu.run(d, g)
         if world > 1:
             i = step_no[0] & 1
             step_no[0] += 1
-            _, d_off, _ = gpu.device_results()
+            if src_view[0] is None:                    # the library's result block has a fixed address
+                _, d_off, _ = gpu.device_results()
+                src_view[0] = torch.as_tensor(_DevArray(d_off, (words,)), device="cuda")
             if stage_free[i] is not None:
-                ext.wait_event(stage_free[i])       # the gather that last used this buffer is done
+                ext.wait_event(freed[i])               # the gather that last used this buffer is done
             with torch.cuda.stream(ext):
-                stage[i].copy_(torch.as_tensor(_DevArray(d_off, (words,)), device="cuda"))
-            ready = torch.cuda.Event()
-            ready.record(ext)
-            comm.wait_event(ready)
+                stage[i].copy_(src_view[0])
+            ready[i].record(ext)
+            comm.wait_event(ready[i])
             with torch.cuda.stream(comm):
                 gathered[0] = gather_cone_lists(stage[i])
-                stage_free[i] = torch.cuda.Event()
-                stage_free[i].record(comm)
+                freed[i].record(comm)
+                stage_free[i] = True
 
     def drain():
         if world > 1:
@@ -288,7 +293,6 @@ def run_ours(args):
     drain()
     e1.record(ext)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     gpu.sync()
     if world > 1 and rank == 0:
         # the gathered list must hold every rank's frames; rank 0's block must equal its own results
@@ -385,6 +389,7 @@ def run_ours(args):
         step_e2e()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    clocks = sampler.stop() if rank == 0 else None   # sampled across both timed regions (resident + e2e)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = world * F * N * e2e_steps / float(e2e_s.item())

@@ -45,6 +45,8 @@ struct FrameArgs {
   u32* ncrop_f;              // [F] survivors per frame
   ClusterRec* slots;         // [F][VMAX] per-frame result slots, canonical order inside a frame
   u32* nvox_f;               // [F] voxels per frame
+  u32* fc;                   // [F][8] cp_frame_counters records
+  int counted_ground;
   u64* desc_v;               // frame descriptors for the voxel offsets
   Ctl* ctl;
   u32* ticket;               // frame ticket (zeroed before the launch)
@@ -536,6 +538,15 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
     if (tid == 0) {
       a.kcount_f[f] = K;
       a.ncomp_f[f] = s.n_comp;
+      u32* fc = a.fc + (u64)f * 8;   // cp_frame_counters
+      fc[0] = npts;
+      fc[1] = a.counted_ground ? a.gcount[f] : 0xFFFFFFFFu;
+      fc[2] = C;
+      fc[3] = V;
+      fc[4] = s.n_comp;
+      fc[5] = K;
+      fc[6] = s.vfr.bits;
+      fc[7] = s.vfr.passthrough;
     }
     // ---- S8/S9: centroid (src/cone_detection.cpp:261-273) and canonical rank, warp per cluster.
     // Lanes find the members 32 voxels at a time; the fp32 sums stay sequential in ascending

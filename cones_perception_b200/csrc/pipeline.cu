@@ -64,6 +64,11 @@ struct cp_handle {
   u32* d_done = nullptr;  // pass-1 tiles finished per frame (fused front kernel)
   u32 fused_grid = 0;
   bool use_fused = false, ran_fused = false;  // measured slower than two kernels: opt-in
+  u32* d_fc = nullptr;      // [F][8] cp_frame_counters, written on the device
+  u32* h_fc = nullptr;      // pinned mirror
+  u32* h_result = nullptr;  // pinned mirror of the head of the result block
+  u64 prefetch_cap = 0, prefetched = 0;
+  size_t off_words = 0;
   u32* d_ncrop_f = nullptr;
   u32* d_nvox_f = nullptr;
   ClusterRec* d_slots = nullptr;  // [max_frames][2048] per-frame result slots of the fast back half
@@ -547,6 +552,23 @@ __global__ void back_reset_kernel(Ctl* ctl, u32 n_frames, u32* ncomp_f, u32* kco
   }
 }
 
+// per-frame counters of the general path in the cp_frame_counters layout
+__global__ void counters_kernel(u32 n_frames, const u32* frame_n, u32 uniform_n, const u32* c_off, const u32* v_off,
+                                const u32* ncomp_f, const u32* kcount_f, const VoxelFrame* vf, const u32* gcount,
+                                int counted_ground, u32* fc) {
+  const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  u32* o = fc + (u64)f * 8;
+  o[0] = uniform_n ? uniform_n : frame_n[f];
+  o[1] = counted_ground ? gcount[f] : 0xFFFFFFFFu;
+  o[2] = c_off[f + 1] - c_off[f];
+  o[3] = v_off[f + 1] - v_off[f];
+  o[4] = ncomp_f[f];
+  o[5] = kcount_f[f];
+  o[6] = vf[f].bits;
+  o[7] = vf[f].passthrough;
+}
+
 // general back half: global-memory kernels, any frame size
 void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   const cp_detect_params* d = &rp.d;
@@ -674,6 +696,10 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
                                                       h->d_tap_labels);
     h->launches++;
   }
+  counters_kernel<<<(F + 255) / 256, 256, 0, h->stream>>>(F, h->d_frame_n, h->hg.uniform_n, h->d_c_off, h->d_v_off,
+                                                          h->d_ncomp_f, h->d_kcount_f, h->d_vf, h->d_gcount,
+                                                          h->counted_ground ? 1 : 0, h->d_fc);
+  h->launches++;
 }
 
 // fast back half: one CTA per frame in shared memory (frame_kernels.cuh)
@@ -712,6 +738,8 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   fa.kcount_f = h->d_kcount_f;
   fa.ncrop_f = h->d_ncrop_f;
   fa.slots = h->d_slots;
+  fa.fc = h->d_fc;
+  fa.counted_ground = h->counted_ground ? 1 : 0;
   fa.nvox_f = h->d_nvox_f;
   fa.desc_v = h->d_desc_fv;
   fa.ctl = h->d_ctl;
@@ -749,7 +777,14 @@ cp_status enqueue_back(cp_handle* h, bool retry) {
     enqueue_back_general(h, rp);
   }
   cudaEventRecord(h->ev1, h->stream);
+  // results ride home behind the kernels: control block, per-frame counters and the head of the
+  // result block (offsets + the first records) go to pinned mirrors, so reading the results
+  // after cp_sync needs no further device round trip
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_fc, h->d_fc, sizeof(u32) * 8 * h->hg.n_frames, cudaMemcpyDeviceToHost, h->stream));
+  h->prefetched = std::min<u64>(h->prefetch_cap, std::max<u64>(4096, 64ull * h->hg.n_frames));
+  CK(cudaMemcpyAsync(h->h_result, h->d_k_off, sizeof(u32) * (h->off_words + 4 * h->prefetched),
+                     cudaMemcpyDeviceToHost, h->stream));
   CK(cudaGetLastError());
   return CP_OK;
 }
@@ -1012,6 +1047,11 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
     A(dalloc(h, &block, off_words + (size_t)h->cap_v * 4));
     h->d_k_off = block;
     h->d_clusters = reinterpret_cast<ClusterRec*>(block + off_words);
+    h->off_words = off_words;
+    h->prefetch_cap = std::min<u64>(h->cap_v, 1ull << 20);
+    A(palloc(h, &h->h_result, off_words + 4 * (size_t)h->prefetch_cap));
+    A(dalloc(h, &h->d_fc, (size_t)F * 8));
+    A(palloc(h, &h->h_fc, (size_t)F * 8));
   }
   A(dalloc(h, &h->d_desc_a, h->tiles_cap));
   A(dalloc(h, &h->d_frame_ticket, 2));
@@ -1194,42 +1234,17 @@ cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* 
   const u32 F = h->hg.n_frames;
   const u64 K = h->h_ctl->n_clusters;
   if (n_total) *n_total = K;
-  u32* s = h->h_frame_u32;
-  if (cluster_offsets) {
-    CK(cudaMemcpyAsync(s, h->d_k_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    memcpy(cluster_offsets, s, sizeof(u32) * (F + 1));
-  }
-  if (counters) {
-    std::vector<u32> c_off(F + 1), v_off(F + 1), ncomp(F), kc(F), gc(F), nc(F), nv(F);
-    std::vector<VoxelFrame> vf(F);
-    CK(cudaMemcpyAsync(c_off.data(), h->d_c_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(v_off.data(), h->d_v_off, sizeof(u32) * (F + 1), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(ncomp.data(), h->d_ncomp_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(kc.data(), h->d_kcount_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(nv.data(), h->d_nvox_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(nc.data(), h->d_ncrop_f, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(gc.data(), h->d_gcount, sizeof(u32) * F, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(vf.data(), h->d_vf, sizeof(VoxelFrame) * F, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    for (u32 f = 0; f < F; ++f) {
-      cp_frame_counters& c = counters[f];
-      c.n_points = h->hg.frame_n[f];
-      c.n_ground_kept = h->counted_ground ? gc[f] : 0xFFFFFFFFu;  // only counted when the filler point matters
-      c.n_cropped = h->gathered ? c_off[f + 1] - c_off[f] : nc[f];
-      c.n_voxels = h->back_mode < 2 ? nv[f] : v_off[f + 1] - v_off[f];
-      c.n_components = ncomp[f];
-      c.n_clusters = kc[f];
-      c.key_bits = vf[f].bits;
-      c.passthrough = vf[f].passthrough;
-    }
-  }
+  static_assert(sizeof(cp_frame_counters) == 32, "cp_frame_counters is 8 x u32");
+  if (cluster_offsets) memcpy(cluster_offsets, h->h_result, sizeof(u32) * (F + 1));
+  if (counters) memcpy(counters, h->h_fc, sizeof(cp_frame_counters) * F);
   if (out) {
     if (K > cap) {
       h->err = "cluster output buffer too small";
       return CP_E_CAPACITY;
     }
-    if (K) {
+    if (K <= h->prefetched) {
+      memcpy(out, h->h_result + h->off_words, sizeof(cp_cluster) * K);
+    } else {
       CK(cudaMemcpyAsync(out, h->d_clusters, sizeof(cp_cluster) * K, cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
     }
