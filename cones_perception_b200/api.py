@@ -27,6 +27,7 @@ ABI_SYMBOLS = [
     "cp_ground_remove", "cp_detect", "cp_batch_set_device_input", "cp_batch_set_host_input", "cp_batch_run",
     "cp_sync", "cp_batch_results", "cp_detect_batch", "cp_last_run_ms", "cp_last_launch_count", "cp_stream",
     "cp_debug_tap", "cp_debug_sort", "cp_set_stage_timing", "cp_stage_ms", "cp_device_results",
+    "cp_gather_create", "cp_gather_open", "cp_gather_seq", "cp_gather_wait", "cp_gather_read",
 ]
 
 CLUSTER_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.uint32), ("min_index", np.uint32)])
@@ -90,6 +91,12 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cp_set_stage_timing.argtypes = [vp, C.c_int]
     lib.cp_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     lib.cp_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.cp_gather_create.argtypes = [vp, u32, u32, vp]
+    lib.cp_gather_open.argtypes = [vp, vp, u32, u32, u32]
+    lib.cp_gather_seq.argtypes = [vp]
+    lib.cp_gather_seq.restype = u32
+    lib.cp_gather_wait.argtypes = [vp, u32, u32]
+    lib.cp_gather_read.argtypes = [vp, u32, vp, u64]
     if path is None:
         _lib = lib
     return lib
@@ -221,6 +228,28 @@ class ConesGpu:
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ck(self.lib.cp_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    # ---- multi-GPU result path over peer memory ------------------------------------------
+    def gather_create(self, world: int, slot_words: int) -> bytes:
+        """Rank 0: allocate the gather buffer; returns the 64-byte CUDA-IPC handle to broadcast."""
+        buf = (C.c_uint8 * 64)()
+        self._ck(self.lib.cp_gather_create(self._h, world, slot_words, buf))
+        return bytes(buf)
+
+    def gather_open(self, handle: bytes, rank: int, world: int, slot_words: int):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._ck(self.lib.cp_gather_open(self._h, buf, rank, world, slot_words))
+
+    def gather_seq(self) -> int:
+        return int(self.lib.cp_gather_seq(self._h))
+
+    def gather_wait(self, seq: int, timeout_ms: int = 5000):
+        self._ck(self.lib.cp_gather_wait(self._h, seq, timeout_ms))
+
+    def gather_read(self, seq: int, world: int, slot_words: int) -> np.ndarray:
+        out = np.empty((world, slot_words), dtype=np.int32)
+        self._ck(self.lib.cp_gather_read(self._h, seq, out.ctypes.data, out.nbytes))
+        return out
 
     def last_launch_count(self) -> int:
         return int(self.lib.cp_last_launch_count(self._h))

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <new>
@@ -68,6 +69,15 @@ struct cp_handle {
   u32* h_fc = nullptr;      // pinned mirror
   u32* h_result = nullptr;  // pinned mirror of the head of the result block
   u64 prefetch_cap = 0, prefetched = 0;
+  bool fetched = false;  // the pinned mirrors hold the results of the run in flight
+  // peer-memory gather of the result block (multi-GPU result path)
+  struct {
+    bool open = false, owner = false;
+    u32* base = nullptr;       // owner: own allocation; others: cudaIpcOpenMemHandle mapping
+    u32 world = 0, rank = 0, slot_words = 0, seq = 0;
+    u32* d_done = nullptr;     // local CTA-completion counter of the publish kernel
+    u32* h_flags = nullptr;    // pinned (owner)
+  } gather;
   size_t off_words = 0;
   u32* d_ncrop_f = nullptr;
   u32* d_nvox_f = nullptr;
@@ -762,6 +772,43 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   h->launches++;
 }
 
+// ---- result path over peer memory (NVLink): every rank's publish kernel stores its packed cone
+// list (offsets + records) straight into the gathering rank's buffer and then raises a sequence
+// flag there.  No collective kernel has to be co-scheduled with the grid-filling compute kernels.
+// buffer layout (u32 words): [flags: 2 x world, padded to 64] [parity 0: world slots] [parity 1: world slots]
+constexpr u32 kGatherFlagWords = 64;
+
+__global__ void __launch_bounds__(256) gather_publish_kernel(const u32* __restrict__ src, u32 words, u32* dst,
+                                                             volatile u32* flag, u32 seq, u32* done,
+                                                             const Ctl* __restrict__ ctl) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  const u32 n4 = words / 4;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const u32 t = atomicAdd(done, 1u);
+    if (t == gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      // a run whose shared-memory back half overflowed is re-run (and re-published) by cp_sync
+      if (ctl->fast_overflow == 0) *flag = seq;
+    }
+  }
+}
+
+void enqueue_gather_publish(cp_handle* h) {
+  auto& g = h->gather;
+  const u32 parity = g.seq & 1u;
+  u32* slot = g.base + kGatherFlagWords + ((size_t)parity * g.world + g.rank) * g.slot_words;
+  volatile u32* flag = g.base + parity * g.world + g.rank;
+  const u32 words = (u32)std::min<size_t>(g.slot_words, h->off_words + 4 * (size_t)h->cap_v) / 4 * 4;
+  const u32 grid = std::max<u32>(1, std::min<u32>(64, words / 4 / 256));
+  gather_publish_kernel<<<grid, 256, 0, h->stream>>>(h->d_k_off, words, slot, flag, g.seq, g.d_done, h->d_ctl);
+  h->launches++;
+}
+
 cp_status enqueue_back(cp_handle* h, bool retry) {
   const RunParams& rp = h->rp;
   if (retry) {
@@ -776,16 +823,24 @@ cp_status enqueue_back(cp_handle* h, bool retry) {
     if (!h->gathered) launch_scan_gather<false>(h, device_geom(h), rp.gk, (u32)h->cap_c, nullptr);
     enqueue_back_general(h, rp);
   }
+  if (h->gather.open) enqueue_gather_publish(h);
   cudaEventRecord(h->ev1, h->stream);
-  // results ride home behind the kernels: control block, per-frame counters and the head of the
-  // result block (offsets + the first records) go to pinned mirrors, so reading the results
-  // after cp_sync needs no further device round trip
+  h->fetched = false;
+  CK(cudaGetLastError());
+  return CP_OK;
+}
+
+// One batch of device-to-host copies behind the kernels: control block, per-frame counters and the
+// head of the result block (offsets + the first records) go to pinned mirrors, so reading results
+// costs ONE stream synchronisation.  Issued when the host asks for results (cp_sync), not per run:
+// a caller that keeps results on the device (multi-GPU gather) pays no PCIe traffic per step.
+cp_status enqueue_result_fetch(cp_handle* h) {
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_fc, h->d_fc, sizeof(u32) * 8 * h->hg.n_frames, cudaMemcpyDeviceToHost, h->stream));
   h->prefetched = std::min<u64>(h->prefetch_cap, std::max<u64>(4096, 64ull * h->hg.n_frames));
   CK(cudaMemcpyAsync(h->h_result, h->d_k_off, sizeof(u32) * (h->off_words + 4 * h->prefetched),
                      cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaGetLastError());
+  h->fetched = true;
   return CP_OK;
 }
 
@@ -847,6 +902,7 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   h->rp.gk = gk;
   h->rp.csort_bits = csort_bits;
   h->rp.osort_bits = osort_bits;
+  if (h->gather.open) h->gather.seq++;
   st = enqueue_back(h, false);
   if (st) return st;
   h->ran = true;
@@ -1087,6 +1143,7 @@ void cp_destroy(cp_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->gather.open && !h->gather.owner && h->gather.base) cudaIpcCloseMemHandle(h->gather.base);
   for (void* p : h->dev_allocs) cudaFree(p);
   for (void* p : h->pin_allocs) cudaFreeHost(p);
   if (h->d_out32) cudaFree(h->d_out32);
@@ -1206,6 +1263,10 @@ cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_
 
 cp_status cp_sync(cp_handle* h) {
   if (!h) return CP_E_PARAM;
+  if (h->ran && !h->fetched) {
+    cp_status sf = enqueue_result_fetch(h);
+    if (sf) return sf;
+  }
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   if (!h->ran) return CP_OK;
@@ -1214,6 +1275,8 @@ cp_status cp_sync(cp_handle* h) {
   while (h->back_mode < 2 && h->h_ctl->fast_overflow != 0 && !(h->h_ctl->error & kErrSurvivors)) {
     h->back_mode = (h->back_mode == 0 && h->h_ctl->fast_max_c <= 4096 && h->h_ctl->fast_max_v <= 2048) ? 1 : 2;
     cp_status st = enqueue_back(h, true);
+    if (st) return st;
+    st = enqueue_result_fetch(h);
     if (st) return st;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
@@ -1380,6 +1443,107 @@ cp_status cp_device_results(cp_handle* h, const void** d_clusters, const uint32_
   if (d_clusters) *d_clusters = h->d_clusters;
   if (d_cluster_offsets) *d_cluster_offsets = h->d_k_off;
   if (d_n_clusters) *d_n_clusters = &h->d_ctl->n_clusters;
+  return CP_OK;
+}
+
+cp_status cp_gather_create(cp_handle* h, uint32_t world, uint32_t slot_words, uint8_t handle_out[64]) {
+  if (!h || !handle_out || world == 0 || slot_words == 0 || slot_words % 4) return CP_E_PARAM;
+  CK(cudaSetDevice(h->cfg.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  auto& g = h->gather;
+  if (g.open) {
+    h->err = "gather already configured on this handle";
+    return CP_E_STATE;
+  }
+  const size_t words = kGatherFlagWords + 2ull * world * slot_words;
+  void* p = nullptr;
+  CK(cudaMalloc(&p, words * sizeof(u32)));
+  h->dev_allocs.push_back(p);
+  CK(cudaMemset(p, 0, words * sizeof(u32)));
+  cudaIpcMemHandle_t ih;
+  CK(cudaIpcGetMemHandle(&ih, p));
+  memcpy(handle_out, &ih, 64);
+  g.base = static_cast<u32*>(p);
+  g.owner = true;
+  g.world = world;
+  g.rank = 0;
+  g.slot_words = slot_words;
+  g.seq = 0;
+  cp_status st = dalloc(h, &g.d_done, 1);
+  if (st) return st;
+  CK(cudaMemset(g.d_done, 0, sizeof(u32)));
+  st = palloc(h, &g.h_flags, kGatherFlagWords);
+  if (st) return st;
+  g.open = true;
+  return CP_OK;
+}
+
+cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, uint32_t world, uint32_t slot_words) {
+  if (!h || !handle || rank == 0 || rank >= world || slot_words == 0 || slot_words % 4) return CP_E_PARAM;
+  CK(cudaSetDevice(h->cfg.device));
+  auto& g = h->gather;
+  if (g.open) {
+    h->err = "gather already configured on this handle";
+    return CP_E_STATE;
+  }
+  cudaIpcMemHandle_t ih;
+  memcpy(&ih, handle, 64);
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+  g.base = static_cast<u32*>(p);
+  g.owner = false;
+  g.world = world;
+  g.rank = rank;
+  g.slot_words = slot_words;
+  g.seq = 0;
+  cp_status st = dalloc(h, &g.d_done, 1);
+  if (st) return st;
+  CK(cudaMemset(g.d_done, 0, sizeof(u32)));
+  g.open = true;
+  return CP_OK;
+}
+
+uint32_t cp_gather_seq(const cp_handle* h) { return h ? h->gather.seq : 0; }
+
+cp_status cp_gather_wait(cp_handle* h, uint32_t seq, uint32_t timeout_ms) {
+  if (!h) return CP_E_PARAM;
+  auto& g = h->gather;
+  if (!g.open || !g.owner) {
+    h->err = "cp_gather_wait is for the handle that created the gather buffer";
+    return CP_E_STATE;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  const u32 parity = seq & 1u;
+  for (u32 waited = 0;; ++waited) {
+    CK(cudaMemcpy(g.h_flags, g.base, kGatherFlagWords * sizeof(u32), cudaMemcpyDeviceToHost));
+    bool all = true;
+    for (u32 r = 0; r < g.world; ++r) all = all && (g.h_flags[parity * g.world + r] == seq);
+    if (all) return CP_OK;
+    if (waited >= timeout_ms * 10) {
+      h->err = "timed out waiting for the ranks to publish their cone lists";
+      return CP_E_STATE;
+    }
+    struct timespec ts = {0, 100000};
+    nanosleep(&ts, nullptr);
+  }
+}
+
+cp_status cp_gather_read(cp_handle* h, uint32_t seq, void* out_host, uint64_t cap_bytes) {
+  if (!h || !out_host) return CP_E_PARAM;
+  auto& g = h->gather;
+  if (!g.open || !g.owner) {
+    h->err = "cp_gather_read is for the handle that created the gather buffer";
+    return CP_E_STATE;
+  }
+  const size_t bytes = (size_t)g.world * g.slot_words * sizeof(u32);
+  if (bytes > cap_bytes) {
+    h->err = "gather output buffer too small";
+    return CP_E_CAPACITY;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  const u32 parity = seq & 1u;
+  CK(cudaMemcpy(out_host, g.base + kGatherFlagWords + (size_t)parity * g.world * g.slot_words, bytes,
+                cudaMemcpyDeviceToHost));
   return CP_OK;
 }
 

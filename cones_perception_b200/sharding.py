@@ -2,8 +2,11 @@
 
 Frames are independent on the GPU path, so a batch is cut into contiguous blocks of frames,
 one block per rank, with NO collective on the data path.  The only exchange is the result
-path: every rank's packed cone list (16 B per cone) plus its per-frame counts are gathered
-to rank 0 — NCCL over NVLink on the GPU box, gloo in the CPU tests.
+path: every rank's packed cone list (16 B per cone) plus its per-frame offsets are gathered
+to rank 0.  Two implementations of the same packed format:
+  * peer memory (production, `setup_peer_gather`): libconesgpu's publish kernel stores the list
+    straight into rank 0's buffer over NVLink (CUDA-IPC mapping) at the end of every run;
+  * one fixed-capacity all_gather (`gather_cone_lists`): NCCL on GPUs, gloo in the CPU tests.
 """
 from __future__ import annotations
 
@@ -51,6 +54,27 @@ def gather_cone_lists(packed, group=None, dst: int = 0):
     if rank != dst:
         return None
     return out.view(world, -1)
+
+
+def setup_peer_gather(gpu, rank: int, world: int, frames_per_rank: int, cap_cones: int, group=None) -> int:
+    """Wire the peer-memory result path of libconesgpu (cp_gather_*): rank 0 allocates the gather
+    buffer and broadcasts its CUDA-IPC handle; the other ranks map it over NVLink.  After this every
+    cp_batch_run publishes the rank's packed cone list into rank 0's memory from inside the library's
+    own kernel — no collective on the step path.  Returns slot_words."""
+    import torch
+    import torch.distributed as dist
+
+    slot_words = pack_words(frames_per_rank, cap_cones)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    buf = torch.zeros(64, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        handle = gpu.gather_create(world, slot_words)
+        buf.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+    dist.broadcast(buf, src=0, group=group)
+    if rank != 0:
+        gpu.gather_open(bytes(buf.cpu().numpy().tobytes()), rank, world, slot_words)
+    dist.barrier(group=group)
+    return slot_words
 
 
 def unpack_gathered(gathered: np.ndarray, frames_per_rank: int):

@@ -173,6 +173,23 @@ cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms);
  * 32-bit words (n_frames_max = cp_config.max_frames), so one collective can move both. */
 cp_status cp_device_results(cp_handle* h, const void** d_clusters, const uint32_t** d_cluster_offsets,
                             const uint32_t** d_n_clusters);
+/* --- multi-GPU result path over peer memory (NVLink 5 / NVSwitch) --------------------------
+ * Frames are sharded across GPUs with no data-path collective; the only exchange is the result:
+ * every rank's packed cone list is gathered on one rank.  Instead of a separate collective, each
+ * cp_batch_run ends with a publish kernel that stores the rank's result block
+ * [cluster offsets | cp_cluster records] into the gathering rank's buffer through a CUDA-IPC peer
+ * mapping and then raises a per-rank sequence flag there.  Double-buffered by run parity.
+ *   rank 0:  cp_gather_create(h, world, slot_words, handle)   -> broadcast the 64-byte handle
+ *   others:  cp_gather_open(h, handle, rank, world, slot_words)
+ *   then cp_batch_run as usual on every rank; run number = cp_gather_seq(h)
+ *   rank 0:  cp_gather_wait(h, seq, timeout_ms); cp_gather_read(h, seq, out, cap)
+ * slot_words (multiple of 4) >= round_up(max_frames + 1, 4) + 4 * (cone capacity per rank). */
+cp_status cp_gather_create(cp_handle* h, uint32_t world, uint32_t slot_words, uint8_t handle_out[64]);
+cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, uint32_t world,
+                         uint32_t slot_words);
+uint32_t cp_gather_seq(const cp_handle* h);
+cp_status cp_gather_wait(cp_handle* h, uint32_t seq, uint32_t timeout_ms);
+cp_status cp_gather_read(cp_handle* h, uint32_t seq, void* out_host, uint64_t cap_bytes);
 /* Kernel launches enqueued by the last cp_batch_run / cp_detect / cp_ground_remove. */
 uint32_t cp_last_launch_count(const cp_handle* h);
 /* The handle's stream as a cudaStream_t, for callers that time with their own events. */

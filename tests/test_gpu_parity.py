@@ -255,3 +255,27 @@ def test_zero_padding_survives_when_dmin_is_zero(gpu):
     assert (ora["crop_index"] < 0).sum() > 1000                     # the filler points are really there
     ctr, k_off, clusters, offs, taps = run_batch_with_taps(gpu, [frame], d, GroundParams())
     assert_frame_parity(gpu, 0, ora, offs, taps, ctr, k_off, clusters)
+
+
+def test_peer_gather_single_rank_roundtrip():
+    """The peer-memory result path with world = 1: the publish kernel writes the packed cone list
+    into the gather buffer and raises the sequence flag; the owner reads back what cp_batch_results
+    returns.  (The 2-GPU path is exercised by `bench.py --gpus 2`, which asserts the same.)"""
+    from cones_perception_b200.sharding import pack_words, unpack_gathered
+    cfg = scans.config(3)
+    frames = list(scans.generate(cfg, 4, base_seed=60))
+    F, cap = len(frames), 4 * 64
+    with api.ConesGpu(max_points=F * cfg.points_per_frame, max_frames=F) as h:
+        words = pack_words(F, cap)
+        handle = h.gather_create(1, words)
+        assert len(handle) == 64
+        for rep in range(3):                    # both parities of the double buffer
+            h.set_host_input([PointCloud2.from_xyzi(f) for f in frames])
+            h.run(cfg.detect, cfg.ground)
+            ctr, off, cl = h.results()
+            seq = h.gather_seq()
+            assert seq == rep + 1
+            h.gather_wait(seq)
+            got = unpack_gathered(h.gather_read(seq, 1, words), F)
+            assert [len(g) for g in got] == np.diff(off).tolist()
+            assert np.array_equal(np.concatenate(got).view(np.uint32), cl.view(np.uint32))
