@@ -185,6 +185,34 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ ours
+def bind_to_gpu_numa(gpu_index: int) -> str:
+    """Best effort: run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node
+    the GPU hangs off, so 8 ranks streaming from host memory do not all cross the socket link."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu_index]) if vis else gpu_index
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        nv.nvmlShutdown()
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read())
+        if node < 0:
+            return "numa: unknown"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa node {node}, {len(allowed)} cpus"
+        return f"numa node {node}: no allowed cpus"
+    except Exception as e:  # containers often hide the topology
+        return f"numa: not bound ({type(e).__name__})"
+
+
 class _DevArray:
     """Zero-copy torch view of a raw device pointer (result buffers of the library)."""
 
@@ -212,6 +240,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libconesgpu has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -466,7 +495,7 @@ def run_ours(args):
                                    f"{F} frames per GPU, frame-sharded, cone lists gathered over NCCL when N>1",
                        "frames_per_gpu": F, "points_per_frame": N, "global_frames": world * F,
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                       "result_gather": gather_mode,
+                       "result_gather": gather_mode, "host_binding_rank0": numa,
                        "cache": f"inputs larger than L2 ({F * N * 16 / 1e6:.0f} MB per rank vs 126 MB), no flush needed",
                        "latency_workload": "cfg2 single frame, host cloud in -> cone list out"},
             "per_step_counts": {"points": F * N, "cropped": C_tot, "voxels": V_tot, "clusters": K_tot},
