@@ -55,7 +55,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("CONESGPU_LIB") or LIB_PATH   # CONESGPU_LIB: an instrumented build, for debugging
     if not os.path.exists(p):
         raise FileNotFoundError(
             f"{p} is missing: build it with `python -m cones_perception_b200.build` "
@@ -161,14 +161,17 @@ class ConesGpu:
         """ConeDetector::cloud_handler hot path (src/cone_detection.cpp:151-167 + :261-273).
         Returns (clusters structured array, counters structured scalar)."""
         view = make_view(msg, fake_missing_intensity)
-        out = np.zeros(cap, dtype=CLUSTER_DTYPE)
-        ctr = np.zeros(1, dtype=COUNTER_DTYPE)
+        if getattr(self, "_det_cap", None) != cap:       # output buffers are reused between calls
+            self._det_out = np.zeros(cap, dtype=CLUSTER_DTYPE)
+            self._det_ctr = np.zeros(1, dtype=COUNTER_DTYPE)
+            self._det_cap = cap
+        out, ctr = self._det_out, self._det_ctr
         k = C.c_uint32()
         cd = to_c_detect(d)
         cg = to_c_ground(g) if g is not None else None
         self._ck(self.lib.cp_detect(self._h, C.byref(view), C.byref(cd), C.byref(cg) if cg is not None else None,
                                     out.ctypes.data, cap, C.byref(k), ctr.ctypes.data))
-        return out[:k.value].copy(), ctr[0]
+        return out[:k.value].copy(), ctr[0].copy()
 
     # ---- batches ----------------------------------------------------------------------
     def set_device_input(self, d_ptr: int, frame_points, point_step: int = 16, off=(0, 4, 8, 12), keep=None):

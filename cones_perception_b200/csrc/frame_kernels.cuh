@@ -25,6 +25,12 @@ namespace cp {
 
 constexpr int kFrameThreads = 512;
 
+#ifdef CP_PHASE_CLOCKS
+#define CP_PHASE(name) do { __syncthreads(); if (tid == 0 && f == 0) { long long c_ = clock64(); printf("%-10s %8lld cyc\n", name, c_ - s_clk); s_clk = c_; } } while (0)
+#else
+#define CP_PHASE(name) do { } while (0)
+#endif
+
 struct FrameArgs {
   u32 n_frames;
   const uint8_t* in;         // raw input points (the kernel gathers its frame's survivors itself)
@@ -146,6 +152,9 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
     __syncthreads();
     const u32 f = s.frame;
     if (f >= a.n_frames) break;
+#ifdef CP_PHASE_CLOCKS
+    long long s_clk = clock64();
+#endif
     // frame geometry: tiles [tile0, tile0 + ntiles), points [first, first + n)
     u32 tile0, ntiles, npts;
     u64 first;
@@ -234,6 +243,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
     }
     __syncthreads();
 
+    CP_PHASE("gather");
     // ---- S0b: VoxelGrid setup from the survivors' bounding box (thread 0)
     if (tid == 0) {
       VoxelFrame v;
@@ -285,6 +295,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
         s.k0[i] = (u32)i0 + (u32)i1 * vfr.mul1 + (u32)i2 * vfr.mul2;
         s.v0[i] = (unsigned short)i;
       }
+      CP_PHASE("keys");
       // ---- S2: stable LSD radix sort in shared memory, 8-bit digits, only the live key bits.
       // Warp w owns a contiguous chunk and walks it 32 items at a time, so ranks keep the
       // input (= point) order inside a voxel.
@@ -346,6 +357,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
         }
         __syncthreads();
       }
+      CP_PHASE("sort");
       const u32* ks = (passes & 1) ? s.k1 : s.k0;
       // ---- S3: segment heads -> voxel ids
       const u32 per = (C + kFrameThreads - 1) / kFrameThreads;
@@ -368,6 +380,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
     const bool slow = s.slow != 0;
     if (slow) V = 0;
 
+    CP_PHASE("heads");
     // ---- voxel offsets across frames: only the parity taps need them (look-back in frame
     // order); the production path keeps frames independent
     if (a.tap_vox) {
@@ -426,6 +439,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
           a.tap_order[c0 + r] = c0 + vs[r];
         }
       }
+      CP_PHASE("means");
       // ---- S5: connected components of "L2_Simple(i,j) < r2".
       // Sweep: voxels are binned along the longer horizontal axis of the bounding box into
       // cells of edge >= 1.01 * tolerance (counting sort), so a voxel only meets the voxels of
@@ -480,6 +494,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
         s.u.vox.perm[s.vstart[c] + atomicAdd(&s.u.vox.label[c], 1u)] = (unsigned short)v;
       }
       __syncthreads();
+      CP_PHASE("binning");
       for (u32 r = warp; r < V; r += kFrameThreads / 32) {
         const u32 i = s.u.vox.perm[r];
         const u32 ci = s.u.vox.vcell[i];
@@ -499,6 +514,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
         }
       }
       __syncthreads();
+      CP_PHASE("union");
       // ---- S6: labels (root = min voxel index of the component) and component sizes
       for (u32 v = tid; v < V; v += kFrameThreads) s.u.vox.label[v] = smem_find(s.u.vox.parent, v);
       __syncthreads();
@@ -534,6 +550,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
       s.n_comp = 0;
     }
 
+    CP_PHASE("labels+kept");
     // ---- per-frame results go to the frame's own slot; pack_clusters_kernel compacts them
     if (tid == 0) {
       a.kcount_f[f] = K;
