@@ -106,13 +106,17 @@ class ConesGpu:
     """Owner of one cp_handle (one CUDA device, one stream, used by one thread at a time)."""
 
     def __init__(self, max_points: int, max_frames: int = 1, device: int = 0, max_point_step: int = 16,
-                 max_survivors: int = 0, max_voxels: int = 0, taps: bool = False, back_mode: int | None = None):
+                 max_survivors: int = 0, max_voxels: int = 0, taps: bool = False, back_mode: int | None = None,
+                 cluster_front: bool | None = None):
         self.lib = load_library()
         self._h = C.c_void_p()
         if taps:
             os.environ["CONESGPU_TAPS"] = "1"
         if back_mode is not None:   # tests: 0/1 shared-memory back half, 2 general global-memory path
             os.environ["CONESGPU_BACK_MODE"] = str(back_mode)
+        prev_cluster = os.environ.get("CONESGPU_CLUSTER_FRONT")
+        if cluster_front is not None:   # single-pass 16-CTA-cluster front end on / off
+            os.environ["CONESGPU_CLUSTER_FRONT"] = "1" if cluster_front else "0"
         try:
             cfg = CConfig(device, max_points, max_frames, max_point_step, max_survivors, max_voxels)
             st = self.lib.cp_create(C.byref(self._h), C.byref(cfg))
@@ -120,6 +124,11 @@ class ConesGpu:
             if taps:
                 os.environ.pop("CONESGPU_TAPS", None)
             os.environ.pop("CONESGPU_BACK_MODE", None)
+            if cluster_front is not None:
+                if prev_cluster is None:
+                    os.environ.pop("CONESGPU_CLUSTER_FRONT", None)
+                else:
+                    os.environ["CONESGPU_CLUSTER_FRONT"] = prev_cluster
         if st != CP_OK:
             raise ConesGpuError(st, self.lib.cp_create_error().decode())
         self.max_points, self.max_frames = max_points, max_frames

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "cluster_front.cuh"
 #include "cluster_kernels.cuh"
 #include "common.cuh"
 #include "frame_kernels.cuh"
@@ -64,6 +65,9 @@ struct cp_handle {
   u32* d_frame_ticket = nullptr;
   u32* d_done = nullptr;  // pass-1 tiles finished per frame (fused front kernel)
   u32 fused_grid = 0;
+  bool use_cluster = false, ran_cluster = false;  // single-pass cluster front end (cluster_front.cuh)
+  size_t cluster_smem = 0;
+  u32 cluster_max = 0;
   bool use_fused = false, ran_fused = false;  // measured slower than two kernels: opt-in
   u32* d_fc = nullptr;      // [F][8] cp_frame_counters, written on the device
   u32* h_fc = nullptr;      // pinned mirror
@@ -494,6 +498,70 @@ void launch_scan_gather(cp_handle* h, const Geom& g, const GroundK& gk, u32 cap,
   h->launches += 2;
   h->gathered = true;
 }
+// single HBM pass: one 16-CTA cluster per frame, points stashed in shared memory (cluster_front.cuh)
+bool cluster_front_eligible(const cp_handle* h, const Geom& g, bool ground) {
+  return h->use_cluster && ground && g.uniform_n && h->layout.mode == 0 &&
+         g.uniform_n <= (u32)kClusterSize * kClMaxPtsPerCta;
+}
+
+bool launch_front_cluster(cp_handle* h, const Geom& g, const CropK& c, const GroundK& gk, float default_low) {
+  ClusterArgs a;
+  a.in = reinterpret_cast<const float4*>(h->in_ptr);
+  a.n_frames = g.n_frames;
+  a.n = g.uniform_n;
+  const u32 per = (g.uniform_n + kClusterSize - 1) / kClusterSize;
+  a.pts_per_cta = (per + kStreamTile - 1) / kStreamTile * kStreamTile;
+  a.tpf = g.tpf;
+  a.default_low = default_low;
+  a.c = c;
+  a.gk = gk;
+  a.low_key = h->d_low_key;
+  a.o.mask = h->d_mask;
+  a.o.tile_count = h->d_tile_count;
+  a.o.gcount = h->d_gcount;
+  const size_t smem = (size_t)a.pts_per_cta * 3 * sizeof(float);  // x, y, z stash
+  if (h->cluster_smem != smem) {
+    if (cudaFuncSetAttribute(front_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(front_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    h->cluster_smem = smem;
+    h->cluster_max = 0;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kClusterSize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kClThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (h->cluster_max == 0) {
+    cfg.gridDim = dim3(kClusterSize, 1, 1);
+    int nmax = 0;
+    if (cudaOccupancyMaxActiveClusters(&nmax, front_cluster_kernel, &cfg) != cudaSuccess || nmax < 1) {
+      cudaGetLastError();
+      return false;
+    }
+    h->cluster_max = (u32)nmax;
+  }
+  const u32 ncl = std::min<u32>(h->cluster_max, g.n_frames);
+  cfg.gridDim = dim3(ncl * kClusterSize, 1, 1);
+  if (h->stage_timing && !h->capturing) cudaEventRecord(h->ev_k[0], h->stream);
+  if (cudaLaunchKernelEx(&cfg, front_cluster_kernel, a) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (h->stage_timing && !h->capturing) cudaEventRecord(h->ev_k[1], h->stream);
+  h->launches++;
+  return true;
+}
+
 // both streaming passes in one persistent kernel (uniform batches with ground removal)
 void launch_front_fused(cp_handle* h, const Geom& g, const CropK& c, const GroundK& gk) {
   MaskOut mo;
@@ -892,8 +960,12 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   if (!h->capturing) cudaEventRecord(h->ev0, h->stream);
   launch_init(h, ground ? ground->default_lowest_point : 0.0f);
   const u32 sgrid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, 8);
-  h->ran_fused = ground && g.uniform_n && h->use_fused;
-  if (h->ran_fused) {
+  h->ran_cluster = cluster_front_eligible(h, g, ground != nullptr) &&
+                   launch_front_cluster(h, g, crop, gk, ground->default_lowest_point);
+  h->ran_fused = !h->ran_cluster && ground && g.uniform_n && h->use_fused;
+  if (h->ran_cluster) {
+    // front end done in one launch
+  } else if (h->ran_fused) {
     launch_front_fused(h, g, crop, gk);
   } else {
     if (ground) {
@@ -1051,6 +1123,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   h->taps = tap_env && tap_env[0] == '1';
   const char* mode_env = getenv("CONESGPU_BACK_MODE");  // tests: force the back-half variant
   if (mode_env && mode_env[0] >= '0' && mode_env[0] <= '2') h->back_mode = mode_env[0] - '0';
+  const char* cl_env = getenv("CONESGPU_CLUSTER_FRONT");  // "1": single-pass 16-CTA-cluster front end
+  if (cl_env) h->use_cluster = cl_env[0] == '1';
   const char* graph_env = getenv("CONESGPU_GRAPH");  // "0": never replay runs from a CUDA graph
   if (graph_env && graph_env[0] == '0') h->use_graph = false;
   const char* fused_env = getenv("CONESGPU_FUSED_FRONT");  // "1": both streaming passes in one persistent kernel
@@ -1502,7 +1576,14 @@ cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms) {
     h->err = "cp_stage_ms needs cp_set_stage_timing(1) before the run";
     return CP_E_STATE;
   }
-  if (stage == CP_STAGE_FRONT_FUSED) {
+  if (stage == CP_STAGE_FRONT_CLUSTER) {
+    if (!h->ran_cluster) {
+      h->err = "the last run did not use the cluster front kernel";
+      return CP_E_STATE;
+    }
+    CK(cudaEventSynchronize(h->ev_k[1]));
+    CK(cudaEventElapsedTime(ms, h->ev_k[0], h->ev_k[1]));
+  } else if (stage == CP_STAGE_FRONT_FUSED) {
     if (!h->ran_fused) {
       h->err = "the last run did not use the fused front kernel";
       return CP_E_STATE;
@@ -1510,15 +1591,15 @@ cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms) {
     CK(cudaEventSynchronize(h->ev_k[1]));
     CK(cudaEventElapsedTime(ms, h->ev_k[0], h->ev_k[1]));
   } else if (stage == CP_STAGE_SECTOR_MIN) {
-    if (!h->ran_ground || h->ran_fused) {
+    if (!h->ran_ground || h->ran_fused || h->ran_cluster) {
       h->err = "the last run had no ground removal";
       return CP_E_STATE;
     }
     CK(cudaEventSynchronize(h->ev_k[1]));
     CK(cudaEventElapsedTime(ms, h->ev_k[0], h->ev_k[1]));
   } else if (stage == CP_STAGE_MASK_CROP_COMPACT) {
-    if (h->ran_fused) {
-      h->err = "the last run used the fused front kernel";
+    if (h->ran_fused || h->ran_cluster) {
+      h->err = "the last run used a single-kernel front end";
       return CP_E_STATE;
     }
     CK(cudaEventSynchronize(h->ev_k[3]));

@@ -162,7 +162,8 @@ cp_status cp_last_run_ms(cp_handle* h, float* ms);
 typedef enum cp_stage {
   CP_STAGE_SECTOR_MIN = 0,        /* ground_sector_min_kernel (two-kernel front end)   */
   CP_STAGE_MASK_CROP_COMPACT = 1, /* keep_mask_kernel (two-kernel front end)           */
-  CP_STAGE_FRONT_FUSED = 2        /* front_fused_kernel: both passes, one HBM crossing */
+  CP_STAGE_FRONT_FUSED = 2,       /* front_fused_kernel: both passes, pass 2 from L2   */
+  CP_STAGE_FRONT_CLUSTER = 3      /* front_cluster_kernel: one HBM pass, 16-CTA clusters */
 } cp_stage;
 cp_status cp_set_stage_timing(cp_handle* h, int on);
 cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms);

@@ -11,11 +11,13 @@ from tests.util import assert_frame_parity, boundary_cloud, oracle_stages, run_b
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["fast", "general"])
+@pytest.fixture(scope="module", params=["fast", "general", "cluster"])
 def gpu(request):
-    """Both back-half variants: the per-frame shared-memory kernel (which falls back to the
-    general path on frames it cannot hold) and the general global-memory path forced on."""
-    g = api.ConesGpu(max_points=1 << 22, max_frames=64, taps=True, back_mode=0 if request.param == "fast" else 2)
+    """Pipeline variants: the per-frame shared-memory back half (falls back to the general path on
+    frames it cannot hold), the general global-memory back half forced on, and the single-pass
+    16-CTA-cluster front end in front of the fast back half."""
+    g = api.ConesGpu(max_points=1 << 22, max_frames=64, taps=True, back_mode=2 if request.param == "general" else 0,
+                     cluster_front=(request.param == "cluster"))
     yield g
     g.close()
 
