@@ -293,3 +293,58 @@ def test_generator_is_thread_count_independent():
     b = scans.generate(cfg, 3, 5, nthreads=3)
     assert np.array_equal(a, b)
     assert not np.array_equal(a[0], a[1])
+
+
+# ------------------------------------------------------------------ independent numpy restatements
+def _np_sector(x, y):
+    a = np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(np.float32)
+    ang = np.where(a < 0, (a.astype(np.float64) + 2 * np.pi).astype(np.float32), a)
+    sa = np.float32((360 // 16) * np.pi / 180)
+    return np.floor(ang / sa).astype(np.int64)
+
+
+def test_ground_and_crop_match_vectorised_numpy():
+    """The C++ oracle's masks against a vectorised numpy restatement of the same reference lines
+    (src/ground_removal.cpp:58-77, src/cone_detection.cpp:189-204) on a full 130k-point scan."""
+    cfg = scans.config(2)
+    f = scans.generate(cfg, 1, 33)[0]
+    x, y, z = f[:, 0], f[:, 1], f[:, 2]
+    pts = O.points32(f)
+    s = _np_sector(x, y)
+    low = np.full(17, np.float32(-0.1))
+    np.minimum.at(low, s, z)
+    assert np.array_equal(O.ground_minima(pts, -0.1), low)
+    keep_g = ~(z.astype(np.float64) < low[s].astype(np.float64) + 0.1)
+    assert np.array_equal(O.ground_mask(pts, low).astype(bool), keep_g)
+    for d in PRESETS.values():
+        dist = np.sqrt(x.astype(np.float64) ** 2 + y.astype(np.float64) ** 2 + z.astype(np.float64) ** 2).astype(np.float32)
+        a = np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(np.float32).astype(np.float64)
+        th = d.angle_threshold * np.pi / 180
+        drop = (z.astype(np.float64) < d.level_threshold) | (dist.astype(np.float64) > d.distance_treshold_max) | \
+               (dist.astype(np.float64) < d.distance_treshold_min) | (-th >= a) | (a >= th)
+        assert np.array_equal(O.crop_mask(pts, d).astype(bool), ~drop)
+
+
+def test_voxel_grid_matches_numpy_restatement():
+    """pcl::VoxelGrid keys, voxel order and counts against numpy (np.unique on the PCL idx); centroids
+    within float rounding of the float64 mean (the oracle sums sequentially in fp32)."""
+    cfg = scans.config(2)
+    f = scans.generate(cfg, 1, 34)[0]
+    st = oracle_stages(f, cfg.detect, cfg.ground)
+    c = st["cropped"]
+    xyz = np.stack([c["x"], c["y"], c["z"]], 1)
+    inv = np.float32(1.0) / np.float32(0.04)
+    cell = np.floor(xyz * inv).astype(np.int64)
+    min_b = np.floor(xyz.min(0) * inv).astype(np.int64)
+    max_b = np.floor(xyz.max(0) * inv).astype(np.int64)
+    div = max_b - min_b + 1
+    idx = (cell[:, 0] - min_b[0]) + (cell[:, 1] - min_b[1]) * div[0] + (cell[:, 2] - min_b[2]) * div[0] * div[1]
+    order = np.argsort(idx, kind="stable")
+    assert np.array_equal(st["keys"], idx[order].astype(np.uint32))
+    assert np.array_equal(st["order"], order.astype(np.uint32))
+    uniq, inverse, counts = np.unique(idx, return_inverse=True, return_counts=True)
+    assert len(st["vox"]) == len(uniq)
+    mean = np.zeros((len(uniq), 3))
+    np.add.at(mean, inverse, xyz.astype(np.float64))
+    mean /= counts[:, None]
+    assert np.abs(vox_xyzi(st["vox"])[:, :3] - mean).max() < 2e-6
