@@ -26,7 +26,8 @@ using namespace cp;
 namespace {
 
 constexpr u32 kAbiVersion = 1;
-constexpr size_t kStageChunk = 64ull << 20;  // pinned staging chunk for pageable host clouds
+constexpr size_t kStageChunk = 32ull << 20;  // pinned staging buffers for pageable host clouds (two of them)
+constexpr size_t kStageMinChunk = 256ull << 10;
 
 struct HostGeom {
   std::vector<u32> frame_n;
@@ -1011,7 +1012,9 @@ cp_status stage_view(cp_handle* h, const cp_cloud_view* v, size_t dst_off, int* 
   const size_t total = row_bytes * v->height;
   size_t done = 0;
   while (done < total) {
-    const size_t chunk = std::min(kStageChunk, total - done);
+    // a cloud is cut into at least 4 pieces so the host memcpy of piece k+1 overlaps the DMA of piece k
+    const size_t piece = std::min(kStageChunk, std::max(kStageMinChunk, (total / 4 + 255) / 256 * 256));
+    const size_t chunk = std::min(piece, total - done);
     const int r = *ring;
     CK(cudaEventSynchronize(h->ev_stage[r]));
     if (contiguous) {
