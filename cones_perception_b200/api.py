@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "cp_sync", "cp_batch_results", "cp_detect_batch", "cp_last_run_ms", "cp_last_launch_count", "cp_stream",
     "cp_debug_tap", "cp_debug_sort", "cp_set_stage_timing", "cp_stage_ms", "cp_device_results",
     "cp_gather_create", "cp_gather_open", "cp_gather_seq", "cp_gather_wait", "cp_gather_read",
+    "cp_last_rows_loaded",
 ]
 
 CLUSTER_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.uint32), ("min_index", np.uint32)])
@@ -97,6 +98,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cp_gather_seq.restype = u32
     lib.cp_gather_wait.argtypes = [vp, u32, u32]
     lib.cp_gather_read.argtypes = [vp, u32, vp, u64]
+    lib.cp_last_rows_loaded.argtypes = [vp]
+    lib.cp_last_rows_loaded.restype = u64
     if path is None:
         _lib = lib
     return lib
@@ -262,6 +265,9 @@ class ConesGpu:
         out = np.empty((world, slot_words), dtype=np.int32)
         self._ck(self.lib.cp_gather_read(self._h, seq, out.ctypes.data, out.nbytes))
         return out
+
+    def last_rows_loaded(self) -> int:
+        return int(self.lib.cp_last_rows_loaded(self._h))
 
     def last_launch_count(self) -> int:
         return int(self.lib.cp_last_launch_count(self._h))

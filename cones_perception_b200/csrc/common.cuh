@@ -32,7 +32,7 @@ struct Ctl {
   u32 fast_overflow;   // frames the shared-memory back half could not hold
   u32 fast_max_c;      // largest per-frame survivor count seen by it
   u32 fast_max_v;      // largest per-frame voxel count seen by it
-  u32 pad0;
+  u32 rows_loaded;     // 32-point rows the keep-mask pass actually read (the rest were skipped as all-ground)
 };
 
 enum : u32 { kErrSurvivors = 1u, kErrVoxels = 2u, kErrHash = 4u, kErrInternal = 8u };

@@ -122,6 +122,10 @@ struct cp_handle {
   u32* d_hvals = nullptr;
   ClusterRec* d_clusters = nullptr;
   u32 *d_mask = nullptr, *d_tile_count = nullptr, *d_tile_excl = nullptr;
+  float* d_thr_f = nullptr;    // [F][32] ground thresholds per sector, slot 31 = their minimum
+  u32* d_rowmax = nullptr;     // highest z (ordered key) of every 32-point row, written by pass 1
+  bool rowmax_valid = false;   // pass 1 of the current run filled d_rowmax
+  bool use_rowskip = true;     // CONESGPU_ROWSKIP=0 disables the skip (A/B measurements)
   u64 *d_desc_a = nullptr, *d_desc_b = nullptr, *d_desc_c = nullptr, *d_desc_d = nullptr;
   u32 *d_tap_keys = nullptr, *d_tap_order = nullptr;
   i32* d_tap_labels = nullptr;
@@ -466,11 +470,19 @@ void launch_keep_mask(cp_handle* h, const Geom& g, const CropK& c, const GroundK
   mo.mask = h->d_mask;
   mo.tile_count = h->d_tile_count;
   mo.gcount = h->d_gcount;
+  mo.rows_loaded = &h->d_ctl->rows_loaded;
+  if (gk.do_ground) {
+    ground_thresholds_kernel<<<(g.n_frames + 127) / 128, 128, 0, h->stream>>>(g.n_frames, h->d_low_key, h->d_thr_f);
+    h->launches++;
+  }
+  // skipped units write nothing: the keep mask and the tile counts start from zero
+  cudaMemsetAsync(h->d_mask, 0, sizeof(u32) * (size_t)g.n_tiles * kTileWords, h->stream);
+  cudaMemsetAsync(h->d_tile_count, 0, sizeof(u32) * g.n_tiles, h->stream);
   if (h->stage_timing) cudaEventRecord(h->ev_k[2], h->stream);
   switch (h->layout.mode) {
-    case 0: keep_mask_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo); break;
-    case 1: keep_mask_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo); break;
-    default: keep_mask_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_low_key, mo); break;
+    case 0: keep_mask_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_thr_f, h->rowmax_valid ? h->d_rowmax : nullptr, mo); break;
+    case 1: keep_mask_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_thr_f, h->rowmax_valid ? h->d_rowmax : nullptr, mo); break;
+    default: keep_mask_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_thr_f, h->rowmax_valid ? h->d_rowmax : nullptr, mo); break;
   }
   if (h->stage_timing) cudaEventRecord(h->ev_k[3], h->stream);
   h->launches++;
@@ -520,6 +532,7 @@ bool launch_front_cluster(cp_handle* h, const Geom& g, const CropK& c, const Gro
   a.o.mask = h->d_mask;
   a.o.tile_count = h->d_tile_count;
   a.o.gcount = h->d_gcount;
+  a.o.rows_loaded = &h->d_ctl->rows_loaded;
   const size_t smem = (size_t)a.pts_per_cta * 3 * sizeof(float);  // x, y, z stash
   if (h->cluster_smem != smem) {
     if (cudaFuncSetAttribute(front_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
@@ -569,6 +582,7 @@ void launch_front_fused(cp_handle* h, const Geom& g, const CropK& c, const Groun
   mo.mask = h->d_mask;
   mo.tile_count = h->d_tile_count;
   mo.gcount = h->d_gcount;
+  mo.rows_loaded = &h->d_ctl->rows_loaded;
   if (h->fused_grid == 0) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, front_fused_kernel<0>, kStreamThreads, 0);
@@ -597,9 +611,9 @@ void launch_front_fused(cp_handle* h, const Geom& g, const CropK& c, const Groun
 
 void launch_sector_min(cp_handle* h, const Geom& g, u32 grid) {
   switch (h->layout.mode) {
-    case 0: ground_sector_min_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key); break;
-    case 1: ground_sector_min_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key); break;
-    default: ground_sector_min_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key); break;
+    case 0: ground_sector_min_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key, h->d_rowmax); break;
+    case 1: ground_sector_min_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key, h->d_rowmax); break;
+    default: ground_sector_min_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key, h->d_rowmax); break;
   }
 }
 
@@ -969,11 +983,13 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   } else if (h->ran_fused) {
     launch_front_fused(h, g, crop, gk);
   } else {
+    h->rowmax_valid = false;
     if (ground) {
       if (h->stage_timing) cudaEventRecord(h->ev_k[0], h->stream);
       launch_sector_min(h, g, sgrid);
       if (h->stage_timing) cudaEventRecord(h->ev_k[1], h->stream);
       h->launches++;
+      h->rowmax_valid = h->use_rowskip;
     }
     launch_keep_mask(h, g, crop, gk, sgrid);
   }
@@ -1126,6 +1142,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   h->taps = tap_env && tap_env[0] == '1';
   const char* mode_env = getenv("CONESGPU_BACK_MODE");  // tests: force the back-half variant
   if (mode_env && mode_env[0] >= '0' && mode_env[0] <= '2') h->back_mode = mode_env[0] - '0';
+  const char* rs_env = getenv("CONESGPU_ROWSKIP");
+  if (rs_env) h->use_rowskip = rs_env[0] != '0';
   const char* cl_env = getenv("CONESGPU_CLUSTER_FRONT");  // "1": single-pass 16-CTA-cluster front end
   if (cl_env) h->use_cluster = cl_env[0] == '1';
   const char* graph_env = getenv("CONESGPU_GRAPH");  // "0": never replay runs from a CUDA graph
@@ -1207,6 +1225,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   A(dalloc(h, &h->d_desc_fv, F));
   A(dalloc(h, &h->d_desc_fk, F));
   A(dalloc(h, &h->d_mask, (size_t)h->tiles_cap * kTileWords));
+  A(dalloc(h, &h->d_rowmax, (size_t)h->tiles_cap * kTileWords));
+  A(dalloc(h, &h->d_thr_f, (size_t)F * kSectStride));
   A(dalloc(h, &h->d_tile_count, h->tiles_cap));
   A(dalloc(h, &h->d_tile_excl, h->tiles_cap));
   const size_t nb = h->cap_c / kHeadTile + 2;
@@ -1534,6 +1554,7 @@ cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_groun
   launch_init(h, g->default_lowest_point);
   const u32 sgrid = grid_for((u64)geo.n_tiles * kStreamThreads, kStreamThreads, h->sms, 8);
   launch_sector_min(h, geo, sgrid);
+  h->rowmax_valid = h->use_rowskip;
   CropK crop;
   memset(&crop, 0, sizeof(crop));
   GroundK gk;
@@ -1685,6 +1706,9 @@ cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, 
 }
 
 uint32_t cp_gather_seq(const cp_handle* h) { return h ? h->gather.seq : 0; }
+
+// rows of 32 points the keep-mask pass read in the last synchronised run (others were skipped)
+uint64_t cp_last_rows_loaded(const cp_handle* h) { return h ? h->h_ctl->rows_loaded : 0; }
 
 cp_status cp_gather_wait(cp_handle* h, uint32_t seq, uint32_t timeout_ms) {
   if (!h) return CP_E_PARAM;

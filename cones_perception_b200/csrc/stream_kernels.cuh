@@ -186,14 +186,16 @@ __device__ __forceinline__ void sector_bounds(const u32* smin, u32* s_bound) {
 
 // one tile of pass 1 against the CTA's shared sector table (src/ground_removal.cpp:58-68)
 // the tile's points, warp-contiguous rows; out-of-range lanes get z = pad_z
+// `rows`: bit r set = this warp needs its row r (32 consecutive points, 512 B in the compact layout)
 template <int MODE>
 __device__ __forceinline__ void load_tile(const uint8_t* __restrict__ in, const Layout& L, u64 base, u32 count,
-                                          float pad_z, float4 (&p)[kStreamRows]) {
+                                          float pad_z, float4 (&p)[kStreamRows], u32 rows = 0xFFu) {
   const u32 wbase = (threadIdx.x >> 5) * (32 * kStreamRows) + lane_id();
 #pragma unroll
   for (int r = 0; r < kStreamRows; ++r) {
     const u32 i = wbase + r * 32;
-    p[r] = (i < count) ? load_point<MODE>(in, base + i, L) : make_float4(0.f, 0.f, pad_z, 0.f);
+    p[r] = ((i < count) && ((rows >> r) & 1u)) ? load_point<MODE>(in, base + i, L)
+                                                : make_float4(0.f, 0.f, pad_z, 0.f);
   }
 }
 
@@ -218,7 +220,8 @@ __device__ __forceinline__ void sector_min_tile(const float4 (&p)[kStreamRows], 
 
 template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads, 4)
-ground_sector_min_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, u32* __restrict__ low_key) {
+ground_sector_min_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, u32* __restrict__ low_key,
+                         u32* __restrict__ rowmax) {
   __shared__ u32 smin[kSectStride];
   __shared__ u32 s_bound[5];
   // contiguous chunk of tiles per CTA so the shared table is flushed once per frame change
@@ -244,6 +247,18 @@ ground_sector_min_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, u32* 
     float4 p[kStreamRows];
     load_tile<MODE>(in, L, first + local0, count, __int_as_float(0x7f800000), p);
     sector_min_tile(p, smin, s_bound);
+    // highest z of every 32-point row (as an ordered key): pass 2 skips rows that lie entirely
+    // below the lowest ground threshold without reading them
+    if (rowmax) {
+      u32 mine = 0;
+#pragma unroll
+      for (int r = 0; r < kStreamRows; ++r) {
+        const u32 m = __reduce_max_sync(kFull, f2ord(p[r].z));
+        if (lane_id() == r) mine = m;
+      }
+      if (lane_id() < kStreamRows)
+        rowmax[(u64)tile * kTileWords + (threadIdx.x >> 5) * kStreamRows + lane_id()] = mine;
+    }
   }
   __syncthreads();
   if (cur_frame != 0xFFFFFFFFu && threadIdx.x < kNSect)
@@ -271,6 +286,7 @@ struct MaskOut {
   u32* mask;        // [n_tiles * 64] keep bits, word (tile, w*8 + r) covers points w*256 + r*32 .. +31
   u32* tile_count;  // [n_tiles] survivors per tile (+1 on a frame's last tile when pad_survives)
   u32* gcount;      // [F] ground survivors (when want_count)
+  u32* rows_loaded; // total 32-point rows pass 2 actually read (statistics for the roofline)
 };
 
 // per-frame thresholds: :75  p.z < low + 0.1 in double  <=>  z < roundup_to_float((double)low + 0.1).
@@ -292,12 +308,13 @@ __device__ __forceinline__ void ground_thresholds(const u32* __restrict__ low_ke
 }
 
 // one tile of pass 2: keep bits (src/ground_removal.cpp:70-77 + src/cone_detection.cpp:189-204)
-// out-of-range lanes carry z = -inf (load_tile pad): dropped by `i < count` anyway
-__device__ __forceinline__ void keep_mask_tile(const float4 (&p)[kStreamRows], u32 count, const CropK& c,
-                                               const GroundK& gk, const float* thr, float thr_min,
-                                               u32* __restrict__ mask_words, u32* wtot, u32& gkept_out) {
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const u32 wbase = warp * (32 * kStreamRows);
+// keep verdicts of one warp's 8 rows (256 consecutive points starting at tile-local index wbase):
+// src/ground_removal.cpp:70-77 + src/cone_detection.cpp:189-204.  Returns this lane's mask word
+// (lane r < 8 holds the word of row r) and the warp's survivor count.
+__device__ __forceinline__ u32 keep_rows(const float4 (&p)[kStreamRows], u32 wbase, u32 count, const CropK& c,
+                                         const GroundK& gk, const float* thr, float thr_min, u32& wcount_out,
+                                         u32& gkept_out) {
+  const int lane = lane_id();
   u32 wcount = 0, gkept = 0, myword = 0;
 #pragma unroll
   for (int r = 0; r < kStreamRows; ++r) {
@@ -330,9 +347,20 @@ __device__ __forceinline__ void keep_mask_tile(const float4 (&p)[kStreamRows], u
     wcount += __popc(bal);
     if (lane == r) myword = bal;
   }
+  wcount_out = wcount;
+  gkept_out = gkept;
+  return myword;
+}
+
+// out-of-range lanes carry z = -inf (load_tile pad): dropped by `i < count` anyway
+__device__ __forceinline__ void keep_mask_tile(const float4 (&p)[kStreamRows], u32 count, const CropK& c,
+                                               const GroundK& gk, const float* thr, float thr_min,
+                                               u32* __restrict__ mask_words, u32* wtot, u32& gkept_out) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  u32 wcount;
+  const u32 myword = keep_rows(p, warp * (32 * kStreamRows), count, c, gk, thr, thr_min, wcount, gkept_out);
   if (lane < kStreamRows) mask_words[warp * kStreamRows + lane] = myword;
   if (lane == 0) wtot[warp] = wcount;
-  gkept_out = gkept;
 }
 
 // tile epilogue: survivors of the tile (+ the pad record on a frame's last tile); whole CTA
@@ -353,33 +381,124 @@ __device__ __forceinline__ void keep_mask_finish(const Geom& g, const GroundK& g
   __syncthreads();
 }
 
+// one row (32 consecutive points, one per lane): keep verdict of this lane's point
+__device__ __forceinline__ bool keep_point(const float4& q, bool in_range, const CropK& c, const GroundK& gk,
+                                           const float* thr, float thr_min, u32& gkept) {
+  const float x = q.x, y = q.y, z = q.z;
+  bool keep = false;
+  // ground prefilter: below the lowest threshold of any sector => ground everywhere
+  // (without the per-frame count, points failing the crop need no ground verdict either)
+  if (in_range && !(z < thr_min) && finite3(x, y, z)) {
+    keep = !c.do_crop || crop_keep(c, x, y, z);
+    if (keep || gk.want_count) {
+      bool ok;
+      const float a = atan2_approx(y, x, ok);
+      if (keep && c.do_crop) {
+        const float aa = fabsf(a);
+        if (!ok | (aa > c.f_lo_guard)) {
+          if (ok & (aa >= c.f_hi_guard)) keep = false;
+          else keep = fabsf(atan2_exact(y, x)) < c.f_hi;  // src/cone_detection.cpp:200-201
+        }
+      }
+      if (gk.do_ground && (keep || gk.want_count)) {
+        const int s = sector_of(x, y, a, ok);
+        const bool gkeep = !(z < thr[s]);
+        if (gkeep) gkept++;
+        keep = keep && gkeep;
+      }
+    }
+  }
+  return keep;
+}
+
+// per-frame ground thresholds, once per frame instead of once per tile:
+// :75  p.z < low + 0.1 in double  <=>  z < roundup_to_float((double)low + 0.1).
+// thr_f[f*32 + s] for the 17 sectors, thr_f[f*32 + 31] = their minimum.
+__global__ void ground_thresholds_kernel(u32 n_frames, const u32* __restrict__ low_key, float* __restrict__ thr_f) {
+  const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  float mn = __int_as_float(0x7f800000);
+  for (int s = 0; s < kNSect; ++s) {
+    const float t = __double2float_ru((double)ord2f(low_key[f * kSectStride + s]) + 0.1);
+    thr_f[f * kSectStride + s] = t;
+    mn = fminf(mn, t);
+  }
+  thr_f[f * kSectStride + 31] = mn;
+}
+
+// Pass 2 as a warp-independent streaming map.  A group is 32 rows = 1024 consecutive points
+// (half a tile, one 128 B load of row maxima from pass 1); groups are dealt round-robin over all
+// warps, which never meet at a block barrier.  Rows whose highest z lies below the lowest ground
+// threshold of any sector are ground in every sector — exact, since z < thr_min <= thr[s] — and
+// are neither loaded nor evaluated: on a 64-beam scan ~88 % of the rows.  The rows that remain
+// are fetched four at a time (independent loads in flight together).  `mask` and `tile_count`
+// must be zero before the launch (skipped rows write nothing).
 template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads, 4)
 keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, GroundK gk,
-                 const u32* __restrict__ low_key, MaskOut o) {
-  __shared__ float thr[kSectStride];
-  __shared__ float s_thr_min;
-  __shared__ u32 wtot[kStreamWarps];
-  const u32 per = (g.n_tiles + gridDim.x - 1) / gridDim.x;
-  const u32 t0 = blockIdx.x * per;
-  const u32 t1 = t0 + per < g.n_tiles ? t0 + per : g.n_tiles;
-  u32 cur_frame = 0xFFFFFFFFu;
-  for (u32 tile = t0; tile < t1; ++tile) {
+                 const float* __restrict__ thr_f, const u32* __restrict__ rowmax, MaskOut o) {
+  constexpr int kBatch = 4;
+  const int lane = lane_id();
+  const u32 nwarps = gridDim.x * kStreamWarps;
+  const u32 gw = blockIdx.x * kStreamWarps + (threadIdx.x >> 5);
+  const u32 ngroups = g.n_tiles * 2u;                          // group G = rows [G*32, G*32+32) of the mask
+  const bool skipping = gk.do_ground && rowmax != nullptr && !gk.want_count;
+  u32 nrows = 0;
+  // scan order clusters the rows that cannot be skipped (e.g. the beams above the horizon); a
+  // contiguous split would leave most warps idle while a few do all the work
+  // (the warp slot is rotated by an odd step every round: with a plain stride the same warps would
+  // meet the same ring of every frame whenever the warp count is a multiple of the frame's groups)
+  for (u32 round = 0, g0 = 0; g0 < ngroups; ++round, g0 += nwarps) {
+    const u32 grp = g0 + (gw + round * 37u) % nwarps;
+    if (grp >= ngroups) continue;
+    const u32 rk = skipping ? rowmax[(u64)grp * 32 + lane] : 0xFFFFFFFFu;   // lane = row within the group
+    const u32 tile = grp >> 1;
     u32 frame, local0, count;
     u64 first;
     tile_lookup(g, tile, frame, local0, count, first);
-    if (gk.do_ground && frame != cur_frame) {
-      __syncthreads();
-      ground_thresholds(low_key, frame, thr, &s_thr_min);
+    const float* thr = thr_f + (size_t)frame * kSectStride;
+    const float thr_min = gk.do_ground ? __ldg(thr + 31) : -__int_as_float(0x7f800000);
+    const u32 half0 = (grp & 1u) * (kStreamTile / 2);          // tile-local index of the group's first point
+    if (gk.pad_survives && (grp & 1u) && lane == 0 &&
+        (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]))
+      atomicAdd(&o.tile_count[tile], 1u);                      // the record standing for the zero padding
+    u32 todo = __ballot_sync(kFull, rk >= f2ord(thr_min));     // bit r: row r of the group must be evaluated
+    if (todo == 0) continue;
+    nrows += __popc(todo);
+    const u32 live = todo;
+    u32 myword = 0, gcount = 0, gkept = 0;
+    while (todo) {
+      // up to four rows per round: all their loads are issued before the first verdict
+      float4 p[kBatch];
+      u32 rowid[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        rowid[j] = todo ? (u32)__ffs(todo) - 1u : 0xFFFFFFFFu;
+        todo &= todo - 1;
+        const u32 i = half0 + rowid[j] * 32 + lane;
+        p[j] = (rowid[j] != 0xFFFFFFFFu && i < count) ? load_point<MODE>(in, first + local0 + i, L)
+                                                       : make_float4(0.f, 0.f, -__int_as_float(0x7f800000), 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        if (rowid[j] == 0xFFFFFFFFu) break;
+        const u32 i = half0 + rowid[j] * 32 + lane;
+        const bool keep = keep_point(p[j], i < count, c, gk, thr, thr_min, gkept);
+        const u32 bal = __ballot_sync(kFull, keep);
+        gcount += __popc(bal);
+        if ((u32)lane == rowid[j]) myword = bal;
+      }
     }
-    cur_frame = frame;
-    float4 p[kStreamRows];
-    load_tile<MODE>(in, L, first + local0, count, -__int_as_float(0x7f800000), p);
-    const float thr_min = gk.do_ground ? s_thr_min : -__int_as_float(0x7f800000);
-    u32 gkept;
-    keep_mask_tile(p, count, c, gk, thr, thr_min, o.mask + (u64)tile * kTileWords, wtot, gkept);
-    keep_mask_finish(g, gk, tile, frame, local0, count, wtot, gkept, o);
+    if (gcount) {
+      if ((live >> lane) & 1u) o.mask[(u64)grp * 32 + lane] = myword;
+      if (lane == 0) atomicAdd(&o.tile_count[tile], gcount);
+    }
+    if (gk.want_count) {
+      const u32 gsum = __reduce_add_sync(kFull, gkept);
+      if (lane == 0 && gsum) atomicAdd(&o.gcount[frame], gsum);
+    }
   }
+  if (lane == 0 && nrows) atomicAdd(o.rows_loaded, nrows);
 }
 
 // ---- both passes in ONE persistent kernel (uniform batches with ground removal) ---------

@@ -191,6 +191,9 @@ cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, 
 uint32_t cp_gather_seq(const cp_handle* h);
 cp_status cp_gather_wait(cp_handle* h, uint32_t seq, uint32_t timeout_ms);
 cp_status cp_gather_read(cp_handle* h, uint32_t seq, void* out_host, uint64_t cap_bytes);
+/* 32-point rows (512 B in the compact layout) that pass 2 actually read in the last synchronised run;
+ * rows lying entirely below every sector's ground threshold are skipped without being loaded. */
+uint64_t cp_last_rows_loaded(const cp_handle* h);
 /* Kernel launches enqueued by the last cp_batch_run / cp_detect / cp_ground_remove. */
 uint32_t cp_last_launch_count(const cp_handle* h);
 /* The handle's stream as a cudaStream_t, for callers that time with their own events. */
