@@ -115,7 +115,7 @@ class ConesGpu:
         self._h = C.c_void_p()
         if taps:
             os.environ["CONESGPU_TAPS"] = "1"
-        if back_mode is not None:   # tests: 0/1 shared-memory back half, 2 general global-memory path
+        if back_mode is not None:   # tests: 0..2 shared-memory back half (growing budgets), 3 general path
             os.environ["CONESGPU_BACK_MODE"] = str(back_mode)
         prev_cluster = os.environ.get("CONESGPU_CLUSTER_FRONT")
         if cluster_front is not None:   # single-pass 16-CTA-cluster front end on / off

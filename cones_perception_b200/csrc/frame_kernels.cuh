@@ -23,7 +23,7 @@
 
 namespace cp {
 
-constexpr int kFrameThreads = 512;
+constexpr int kFrameThreadsMax = 512;
 
 #ifdef CP_PHASE_CLOCKS
 #define CP_PHASE(name) do { __syncthreads(); if (tid == 0 && f == 0) { long long c_ = clock64(); printf("%-10s %8lld cyc\n", name, c_ - s_clk); s_clk = c_; } } while (0)
@@ -64,14 +64,14 @@ struct FrameArgs {
   i32* tap_labels;
 };
 
-template <int CMAX, int VMAX>
+template <int CMAX, int VMAX, int T>
 struct FrameSmem {
   float px[CMAX], py[CMAX], pz[CMAX], pw[CMAX];
   u32 k0[CMAX], k1[CMAX];              // voxel idx, ping-pong buffers of the radix sort
   unsigned short v0[CMAX], v1[CMAX];   // survivor position, ping-pong
   union {
     struct {                           // scratch of the radix sort (dead before the voxel arrays live)
-      u32 whist[kFrameThreads / 32][256];
+      u32 whist[T / 32][256];
       u32 gbase[256];
     } sort;
     struct {
@@ -84,7 +84,7 @@ struct FrameSmem {
     } vox;
   } u;
   u32 vstart[VMAX + 1];                // voxel -> first sorted record; then sweep cell starts; then kept roots
-  u32 wsum[kFrameThreads / 32];
+  u32 wsum[T / 32];
   VoxelFrame vfr;
   u32 frame, slow, n_vox, v_excl, k_excl, n_kept, n_comp, n_surv;
   u32 bbox[8];
@@ -117,6 +117,7 @@ __device__ __forceinline__ void smem_union(u32* parent, u32 a, u32 b) {
 }
 
 // block-wide exclusive scan of one value per thread; returns the exclusive prefix and the total
+template <int T>
 __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* wsum, u32& total) {
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   u32 inc = v;
@@ -131,7 +132,7 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* wsum, u32& total) {
   u32 woff = 0;
   total = 0;
 #pragma unroll
-  for (int w = 0; w < kFrameThreads / 32; ++w) {
+  for (int w = 0; w < T / 32; ++w) {
     const u32 t = wsum[w];
     if (w < warp) woff += t;
     total += t;
@@ -139,10 +140,11 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* wsum, u32& total) {
   return woff + inc - v;
 }
 
-template <int CMAX, int VMAX, int MODE>
-__global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs a) {
+template <int CMAX, int VMAX, int MODE, int T>
+__global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
+  constexpr int kFrameThreads = T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FrameSmem<CMAX, VMAX>& s = *reinterpret_cast<FrameSmem<CMAX, VMAX>*>(smem_raw);
+  FrameSmem<CMAX, VMAX, T>& s = *reinterpret_cast<FrameSmem<CMAX, VMAX, T>*>(smem_raw);
   const u32 tid = threadIdx.x;
   const int lane = lane_id(), warp = tid >> 5;
 
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
           for (int k = 0; k < 8; ++k) cnt += __popc(w[k]);
         }
         u32 total;
-        u32 pos = C + block_excl_scan(cnt, s.wsum, total);
+        u32 pos = C + block_excl_scan<T>(cnt, s.wsum, total);
         if (cnt && C + total <= (u32)CMAX) {
           // phase 1: only the frame-local point indices, in order (k0 is free until the sort)
 #pragma unroll
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
           }
         }
         u32 tot;
-        const u32 gb = block_excl_scan(run, s.wsum, tot);
+        const u32 gb = block_excl_scan<T>(run, s.wsum, tot);
         if (tid < 256) s.u.sort.gbase[tid] = gb;
         __syncthreads();
 #pragma unroll
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
       u32 cnt = 0;
       for (u32 r = r0; r < r1; ++r) cnt += (r == 0 || ks[r] != ks[r - 1]) ? 1u : 0u;
       u32 total;
-      u32 vid = block_excl_scan(cnt, s.wsum, total);
+      u32 vid = block_excl_scan<T>(cnt, s.wsum, total);
       V = total;
       if (V <= (u32)VMAX) {
         for (u32 r = r0; r < r1; ++r)
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
         u32 sum = 0;
         for (u32 q = q0; q < q1; ++q) sum += s.vstart[q];
         u32 tot;
-        u32 run = block_excl_scan(sum, s.wsum, tot);
+        u32 run = block_excl_scan<T>(sum, s.wsum, tot);
         for (u32 q = q0; q < q1; ++q) {
           const u32 t = s.vstart[q];
           s.vstart[q] = run;
@@ -535,8 +537,8 @@ __global__ void __launch_bounds__(kFrameThreads) frame_backend_kernel(FrameArgs 
         }
       }
       u32 ktotal, ctotal;
-      u32 kpos = block_excl_scan(kc, s.wsum, ktotal);
-      block_excl_scan(cc, s.wsum, ctotal);
+      u32 kpos = block_excl_scan<T>(kc, s.wsum, ktotal);
+      block_excl_scan<T>(cc, s.wsum, ctotal);
       K = ktotal;
       for (u32 v = v0; v < v1; ++v) {
         if (s.u.vox.label[v] == v) {

@@ -60,7 +60,9 @@ struct cp_handle {
   u32 launches = 0;
   bool batch_ready = false, ran = false;
   bool taps = false, counted_ground = false, ran_ground = false;
-  int back_mode = 0;  // 0: fast (2048/1024 per frame), 1: fast (4096/2048), 2: general
+  // back half: 0..2 = shared-memory frame kernel with growing budgets (1024/512 survivors/voxels at
+  // 4 CTAs per SM, 2048/1024 at 2, 4096/2048 at 1), 3 = general global-memory path
+  int back_mode = 0;
   RunParams rp{};
   u64 *d_desc_fv = nullptr, *d_desc_fk = nullptr;
   u32* d_frame_ticket = nullptr;
@@ -806,22 +808,26 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
 }
 
 // fast back half: one CTA per frame in shared memory (frame_kernels.cuh)
-template <int CMAX, int VMAX, int MODE>
+template <int CMAX, int VMAX, int MODE, int T>
 void launch_frame_kernel(cp_handle* h, const FrameArgs& fa) {
-  const size_t smem = sizeof(FrameSmem<CMAX, VMAX>);
+  const size_t smem = sizeof(FrameSmem<CMAX, VMAX, T>);
   static bool attr_set = false;
+  static int per_sm = 1;
   if (!attr_set) {
-    cudaFuncSetAttribute(frame_backend_kernel<CMAX, VMAX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(frame_backend_kernel<CMAX, VMAX, MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_backend_kernel<CMAX, VMAX, MODE, T>, T, smem) !=
+            cudaSuccess || per_sm < 1)
+      per_sm = 1;
     attr_set = true;
   }
-  const u32 per_sm = (u32)std::max<size_t>(1, std::min<size_t>(4, (220u << 10) / (smem + 1024)));
-  const u32 grid = std::min<u32>(fa.n_frames, (u32)h->sms * per_sm);
-  frame_backend_kernel<CMAX, VMAX, MODE><<<grid, kFrameThreads, smem, h->stream>>>(fa);
+  const u32 grid = std::min<u32>(fa.n_frames, (u32)h->sms * (u32)per_sm);
+  frame_backend_kernel<CMAX, VMAX, MODE, T><<<grid, T, smem, h->stream>>>(fa);
   h->launches++;
 }
 
 // fast back half: one CTA per frame in shared memory (frame_kernels.cuh)
-template <int CMAX, int VMAX>
+template <int CMAX, int VMAX, int T>
 void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   FrameArgs fa;
   fa.n_frames = h->hg.n_frames;
@@ -856,9 +862,9 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   // the crop taps (survivor arrays, offsets) come from the global gather
   if (h->taps && !h->gathered) launch_scan_gather<false>(h, fa.geom, rp.gk, (u32)h->cap_c, nullptr);
   switch (h->layout.mode) {
-    case 0: launch_frame_kernel<CMAX, VMAX, 0>(h, fa); break;
-    case 1: launch_frame_kernel<CMAX, VMAX, 1>(h, fa); break;
-    default: launch_frame_kernel<CMAX, VMAX, 2>(h, fa); break;
+    case 0: launch_frame_kernel<CMAX, VMAX, 0, T>(h, fa); break;
+    case 1: launch_frame_kernel<CMAX, VMAX, 1, T>(h, fa); break;
+    default: launch_frame_kernel<CMAX, VMAX, 2, T>(h, fa); break;
   }
   pack_clusters_kernel<<<fa.n_frames, 256, 0, h->stream>>>(fa.n_frames, VMAX, h->d_kcount_f, h->d_slots, h->d_k_off,
                                                            h->d_clusters, (u32)h->cap_v, h->d_ctl);
@@ -910,8 +916,12 @@ cp_status enqueue_back(cp_handle* h, bool retry) {
     CK(cudaMemsetAsync(h->d_desc_fk, 0, sizeof(u64) * h->hg.n_frames, h->stream));
     h->launches++;
   }
-  if (h->back_mode == 0) enqueue_back_fast<2048, 1024>(h, rp);
-  else if (h->back_mode == 1) enqueue_back_fast<4096, 2048>(h, rp);
+  // smallest budget: 256-thread CTAs (4 per SM) keep a whole big batch resident in one wave; for a few
+  // frames latency matters instead, so they get 512 threads each
+  if (h->back_mode == 0 && h->hg.n_frames > (u32)h->sms * 2) enqueue_back_fast<1024, 512, 256>(h, rp);
+  else if (h->back_mode == 0) enqueue_back_fast<1024, 512, 512>(h, rp);
+  else if (h->back_mode == 1) enqueue_back_fast<2048, 1024, 512>(h, rp);
+  else if (h->back_mode == 2) enqueue_back_fast<4096, 2048, 512>(h, rp);
   else {
     if (!h->gathered) launch_scan_gather<false>(h, device_geom(h), rp.gk, (u32)h->cap_c, nullptr);
     enqueue_back_general(h, rp);
@@ -1141,7 +1151,7 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   const char* tap_env = getenv("CONESGPU_TAPS");
   h->taps = tap_env && tap_env[0] == '1';
   const char* mode_env = getenv("CONESGPU_BACK_MODE");  // tests: force the back-half variant
-  if (mode_env && mode_env[0] >= '0' && mode_env[0] <= '2') h->back_mode = mode_env[0] - '0';
+  if (mode_env && mode_env[0] >= '0' && mode_env[0] <= '3') h->back_mode = mode_env[0] - '0';
   const char* rs_env = getenv("CONESGPU_ROWSKIP");
   if (rs_env) h->use_rowskip = rs_env[0] != '0';
   const char* cl_env = getenv("CONESGPU_CLUSTER_FRONT");  // "1": single-pass 16-CTA-cluster front end
@@ -1397,7 +1407,7 @@ static RunKey make_key(const cp_handle* h, const cp_detect_params* d, const cp_g
 cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_params* ground) {
   if (!h) return CP_E_PARAM;
   CK(cudaSetDevice(h->cfg.device));
-  const bool eligible = h->use_graph && d && h->batch_ready && !h->taps && !h->stage_timing && h->back_mode < 2 &&
+  const bool eligible = h->use_graph && d && h->batch_ready && !h->taps && !h->stage_timing && h->back_mode < 3 &&
                         !h->gather.open && h->hg.uniform_n != 0;
   if (!eligible) {
     h->key_valid = false;
@@ -1466,8 +1476,12 @@ cp_status cp_sync(cp_handle* h) {
   if (!h->ran) return CP_OK;
   // the shared-memory back half reports frames it could not hold: pick the next variant
   // (bigger shared-memory budget, then the general global-memory path) and redo the back half
-  while (h->back_mode < 2 && h->h_ctl->fast_overflow != 0 && !(h->h_ctl->error & kErrSurvivors)) {
-    h->back_mode = (h->back_mode == 0 && h->h_ctl->fast_max_c <= 4096 && h->h_ctl->fast_max_v <= 2048) ? 1 : 2;
+  while (h->back_mode < 3 && h->h_ctl->fast_overflow != 0 && !(h->h_ctl->error & kErrSurvivors)) {
+    const u32 mc = h->h_ctl->fast_max_c, mv = h->h_ctl->fast_max_v;
+    int next = 3;
+    if (h->back_mode < 1 && mc <= 2048 && mv <= 1024) next = 1;
+    else if (h->back_mode < 2 && mc <= 4096 && mv <= 2048) next = 2;
+    h->back_mode = next;
     cp_status st = enqueue_back(h, true);
     if (st) return st;
     st = enqueue_result_fetch(h);

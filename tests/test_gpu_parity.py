@@ -16,7 +16,7 @@ def gpu(request):
     """Pipeline variants: the per-frame shared-memory back half (falls back to the general path on
     frames it cannot hold), the general global-memory back half forced on, and the single-pass
     16-CTA-cluster front end in front of the fast back half."""
-    g = api.ConesGpu(max_points=1 << 22, max_frames=64, taps=True, back_mode=2 if request.param == "general" else 0,
+    g = api.ConesGpu(max_points=1 << 22, max_frames=64, taps=True, back_mode=3 if request.param == "general" else 0,
                      cluster_front=(request.param == "cluster"))
     yield g
     g.close()
@@ -224,7 +224,7 @@ def test_capacity_and_parameter_errors(gpu):
         gpu.detect(msg, d, None)
     assert e.value.status == api.CP_E_PARAM
     # survivors overflow is reported, not truncated
-    with api.ConesGpu(max_points=len(frame), max_frames=1, max_survivors=16, back_mode=2) as tiny:
+    with api.ConesGpu(max_points=len(frame), max_frames=1, max_survivors=16, back_mode=3) as tiny:
         with pytest.raises(api.ConesGpuError) as e:
             tiny.detect(msg, cfg.detect, None)
         assert e.value.status == api.CP_E_CAPACITY

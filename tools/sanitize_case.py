@@ -16,7 +16,7 @@ from oracle import oracle as O  # noqa: E402
 cfg = scans.config(1)
 frames = list(scans.generate(cfg, 3, base_seed=1))
 frames[1] = frames[1][:5000]
-for mode in (0, 2):
+for mode in (0, 3):
     with api.ConesGpu(max_points=1 << 17, max_frames=4, back_mode=mode) as gpu:
         ctr, off, cl = gpu.detect_batch([PointCloud2.from_xyzi(f) for f in frames], cfg.detect, GroundParams())
         for i, f in enumerate(frames):
