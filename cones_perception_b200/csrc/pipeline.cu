@@ -88,6 +88,7 @@ struct cp_handle {
     u32* base = nullptr;       // owner: own allocation; others: cudaIpcOpenMemHandle mapping
     u32 world = 0, rank = 0, slot_words = 0, seq = 0;
     u32* d_done = nullptr;     // local CTA-completion counter of the publish kernel
+    u32* d_seq = nullptr;      // local run number (device-resident: graph replays need no parameter update)
     u32* h_flags = nullptr;    // pinned (owner)
   } gather;
   size_t off_words = 0;
@@ -877,9 +878,15 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
 // buffer layout (u32 words): [flags: 2 x world, padded to 64] [parity 0: world slots] [parity 1: world slots]
 constexpr u32 kGatherFlagWords = 64;
 
-__global__ void __launch_bounds__(256) gather_publish_kernel(const u32* __restrict__ src, u32 words, u32* dst,
-                                                             volatile u32* flag, u32 seq, u32* done,
-                                                             const Ctl* __restrict__ ctl) {
+// The run number lives on the device (d_seq) so that a CUDA-graph replay publishes under a fresh
+// number without any kernel parameter changing: every CTA reads it on entry, the last one to finish
+// advances it.  `advance` = 0 re-publishes under the current number (back-half retry by cp_sync).
+__global__ void __launch_bounds__(256) gather_publish_kernel(const u32* __restrict__ src, u32 words, u32* base,
+                                                             u32 world, u32 rank, u32 slot_words, u32* d_seq,
+                                                             u32 advance, u32* done, const Ctl* __restrict__ ctl) {
+  const u32 seq = *((volatile u32*)d_seq) + advance;
+  const u32 parity = seq & 1u;
+  u32* dst = base + kGatherFlagWords + ((size_t)parity * world + rank) * slot_words;
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   uint4* d4 = reinterpret_cast<uint4*>(dst);
   const u32 n4 = words / 4;
@@ -890,21 +897,20 @@ __global__ void __launch_bounds__(256) gather_publish_kernel(const u32* __restri
     const u32 t = atomicAdd(done, 1u);
     if (t == gridDim.x - 1) {
       *done = 0;
+      *d_seq = seq;
       __threadfence_system();
       // a run whose shared-memory back half overflowed is re-run (and re-published) by cp_sync
-      if (ctl->fast_overflow == 0) *flag = seq;
+      if (ctl->fast_overflow == 0) *((volatile u32*)(base + parity * world + rank)) = seq;
     }
   }
 }
 
-void enqueue_gather_publish(cp_handle* h) {
+void enqueue_gather_publish(cp_handle* h, bool retry) {
   auto& g = h->gather;
-  const u32 parity = g.seq & 1u;
-  u32* slot = g.base + kGatherFlagWords + ((size_t)parity * g.world + g.rank) * g.slot_words;
-  volatile u32* flag = g.base + parity * g.world + g.rank;
   const u32 words = (u32)std::min<size_t>(g.slot_words, h->off_words + 4 * (size_t)h->cap_v) / 4 * 4;
   const u32 grid = std::max<u32>(1, std::min<u32>(64, words / 4 / 256));
-  gather_publish_kernel<<<grid, 256, 0, h->stream>>>(h->d_k_off, words, slot, flag, g.seq, g.d_done, h->d_ctl);
+  gather_publish_kernel<<<grid, 256, 0, h->stream>>>(h->d_k_off, words, g.base, g.world, g.rank, g.slot_words,
+                                                     g.d_seq, retry ? 0u : 1u, g.d_done, h->d_ctl);
   h->launches++;
 }
 
@@ -926,7 +932,7 @@ cp_status enqueue_back(cp_handle* h, bool retry) {
     if (!h->gathered) launch_scan_gather<false>(h, device_geom(h), rp.gk, (u32)h->cap_c, nullptr);
     enqueue_back_general(h, rp);
   }
-  if (h->gather.open) enqueue_gather_publish(h);
+  if (h->gather.open) enqueue_gather_publish(h, retry);
   if (!h->capturing) cudaEventRecord(h->ev1, h->stream);
   h->fetched = false;
   CK(cudaGetLastError());
@@ -1408,7 +1414,7 @@ cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_
   if (!h) return CP_E_PARAM;
   CK(cudaSetDevice(h->cfg.device));
   const bool eligible = h->use_graph && d && h->batch_ready && !h->taps && !h->stage_timing && h->back_mode < 3 &&
-                        !h->gather.open && h->hg.uniform_n != 0;
+                        h->hg.uniform_n != 0;
   if (!eligible) {
     h->key_valid = false;
     return enqueue_pipeline(h, d, ground);
@@ -1419,6 +1425,7 @@ cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_
   memcpy(h->last_key, &key, sizeof(RunKey));
   h->key_valid = true;
   if (same && h->graph_exec && h->graph_key_valid && memcmp(&key, h->graph_key, sizeof(RunKey)) == 0) {
+    if (h->gather.open) h->gather.seq++;
     cudaEventRecord(h->ev0, h->stream);
     CK(cudaGraphLaunch(h->graph_exec, h->stream));
     cudaEventRecord(h->ev1, h->stream);
@@ -1445,6 +1452,7 @@ cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
     h->use_graph = false;  // capture is not possible here: stay on direct launches
+    if (h->gather.open && st == CP_OK) h->gather.seq--;  // the captured (never executed) run was counted
     return st != CP_OK ? st : enqueue_pipeline(h, d, ground);
   }
   ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
@@ -1453,6 +1461,7 @@ cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_
     cudaGetLastError();
     h->graph_exec = nullptr;
     h->use_graph = false;
+    if (h->gather.open) h->gather.seq--;
     return enqueue_pipeline(h, d, ground);
   }
   memcpy(h->graph_key, &key, sizeof(RunKey));
@@ -1688,6 +1697,9 @@ cp_status cp_gather_create(cp_handle* h, uint32_t world, uint32_t slot_words, ui
   cp_status st = dalloc(h, &g.d_done, 1);
   if (st) return st;
   CK(cudaMemset(g.d_done, 0, sizeof(u32)));
+  st = dalloc(h, &g.d_seq, 1);
+  if (st) return st;
+  CK(cudaMemset(g.d_seq, 0, sizeof(u32)));
   st = palloc(h, &g.h_flags, kGatherFlagWords);
   if (st) return st;
   g.open = true;
@@ -1715,6 +1727,9 @@ cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, 
   cp_status st = dalloc(h, &g.d_done, 1);
   if (st) return st;
   CK(cudaMemset(g.d_done, 0, sizeof(u32)));
+  st = dalloc(h, &g.d_seq, 1);
+  if (st) return st;
+  CK(cudaMemset(g.d_seq, 0, sizeof(u32)));
   g.open = true;
   return CP_OK;
 }
