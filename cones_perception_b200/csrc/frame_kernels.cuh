@@ -86,7 +86,7 @@ struct FrameSmem {
   u32 vstart[VMAX + 1];                // voxel -> first sorted record; then sweep cell starts; then kept roots
   u32 wsum[T / 32];
   VoxelFrame vfr;
-  u32 frame, slow, n_vox, v_excl, k_excl, n_kept, n_comp, n_surv;
+  u32 frame, slow, v_excl, n_comp;
   u32 bbox[8];
   u32 sw_axis, sw_ncell;
   float sw_min, sw_inv;

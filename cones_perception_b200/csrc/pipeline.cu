@@ -64,7 +64,7 @@ struct cp_handle {
   // 4 CTAs per SM, 2048/1024 at 2, 4096/2048 at 1), 3 = general global-memory path
   int back_mode = 0;
   RunParams rp{};
-  u64 *d_desc_fv = nullptr, *d_desc_fk = nullptr;
+  u64* d_desc_fv = nullptr;  // frame descriptors of the voxel-offset look-back (parity taps only)
   u32* d_frame_ticket = nullptr;
   u32* d_done = nullptr;  // pass-1 tiles finished per frame (fused front kernel)
   u32 fused_grid = 0;
@@ -626,7 +626,6 @@ void launch_init(cp_handle* h, float default_low) {
                                                  h->d_c_off, h->d_gcount, h->d_ncomp_f, h->d_kcount_f,
                                                  h->d_desc_a, h->hg.n_tiles, h->d_desc_b, h->d_desc_c, h->d_desc_d, nb);
   cudaMemsetAsync(h->d_desc_fv, 0, sizeof(u64) * h->hg.n_frames, h->stream);
-  cudaMemsetAsync(h->d_desc_fk, 0, sizeof(u64) * h->hg.n_frames, h->stream);
   h->launches++;
 }
 
@@ -919,7 +918,6 @@ cp_status enqueue_back(cp_handle* h, bool retry) {
   if (retry) {
     back_reset_kernel<<<h->sms, 256, 0, h->stream>>>(h->d_ctl, h->hg.n_frames, h->d_ncomp_f, h->d_kcount_f);
     CK(cudaMemsetAsync(h->d_desc_fv, 0, sizeof(u64) * h->hg.n_frames, h->stream));
-    CK(cudaMemsetAsync(h->d_desc_fk, 0, sizeof(u64) * h->hg.n_frames, h->stream));
     h->launches++;
   }
   // smallest budget: 256-thread CTAs (4 per SM) keep a whole big batch resident in one wave; for a few
@@ -986,7 +984,6 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   vk.frame_bits = ceil_log2_host(h->hg.n_frames);
 
   const Geom g = device_geom(h);
-  const u32 F = h->hg.n_frames;
   h->launches = 0;
   if (!h->capturing) cudaEventRecord(h->ev0, h->stream);
   launch_init(h, ground ? ground->default_lowest_point : 0.0f);
@@ -1239,7 +1236,6 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   A(dalloc(h, &h->d_nvox_f, F));
   A(dalloc(h, &h->d_slots, (size_t)F * 2048));
   A(dalloc(h, &h->d_desc_fv, F));
-  A(dalloc(h, &h->d_desc_fk, F));
   A(dalloc(h, &h->d_mask, (size_t)h->tiles_cap * kTileWords));
   A(dalloc(h, &h->d_rowmax, (size_t)h->tiles_cap * kTileWords));
   A(dalloc(h, &h->d_thr_f, (size_t)F * kSectStride));

@@ -281,3 +281,55 @@ def test_peer_gather_single_rank_roundtrip():
             got = unpack_gathered(h.gather_read(seq, 1, words), F)
             assert [len(g) for g in got] == np.diff(off).tolist()
             assert np.array_equal(np.concatenate(got).view(np.uint32), cl.view(np.uint32))
+
+
+def _random_scene(rng, n):
+    """Unstructured random cloud: ground sheet with holes, blobs, thin lines, outliers, duplicates."""
+    parts = []
+    m = int(n * rng.uniform(0.3, 0.7))
+    g = np.stack([rng.uniform(-12, 12, m), rng.uniform(-12, 12, m),
+                  rng.uniform(-1.0, -0.3) + rng.normal(0, rng.uniform(0.001, 0.05), m)], 1)
+    parts.append(g)
+    for _ in range(int(rng.integers(3, 40))):
+        c = rng.uniform(-9, 9, 3) * np.array([1, 1, 0.1])
+        k = int(rng.integers(1, 400))
+        parts.append(c + rng.normal(0, rng.uniform(0.01, 0.3), (k, 3)))
+    for _ in range(int(rng.integers(0, 6))):
+        a, b = rng.uniform(-8, 8, 3) * np.array([1, 1, 0.2]), rng.uniform(-8, 8, 3) * np.array([1, 1, 0.2])
+        t = rng.uniform(0, 1, int(rng.integers(10, 300)))[:, None]
+        parts.append(a + t * (b - a))
+    parts.append(rng.uniform(-60, 60, (int(rng.integers(0, 50)), 3)))
+    a = np.concatenate(parts)
+    if len(a) > 10:
+        a = np.concatenate([a, a[rng.integers(0, len(a), 10)]])      # exact duplicate points
+    rng.shuffle(a)
+    a = a[:n]
+    out = np.zeros((len(a), 4), np.float32)
+    out[:, :3] = a
+    out[:, 3] = rng.uniform(0, 255, len(a))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_scenes_and_parameters(gpu, seed):
+    """Random clouds x random (valid) parameter sets, several frames per batch, with and without
+    ground removal: every stage must equal the oracle bit for bit."""
+    import dataclasses
+    rng = np.random.default_rng(1000 + seed)
+    base = PRESETS[["our", "fsai", "simulation"][seed % 3]]
+    d = dataclasses.replace(
+        base,
+        distance_treshold_max=float(rng.uniform(3, 14)), distance_treshold_min=float(rng.uniform(0.0, 2.0)),
+        level_threshold=float(rng.uniform(-2.0, 0.2)), angle_threshold=float(rng.uniform(20, 200)),
+        voxel_filter_leaf_size_x=float(rng.choice([0.03, 0.04, 0.05, 0.1])),
+        voxel_filter_leaf_size_y=float(rng.choice([0.03, 0.04, 0.07])),
+        voxel_filter_leaf_size_z=float(rng.choice([0.04, 0.08])),
+        min_cluster_size=int(rng.integers(1, 5)), max_cluster_size=int(rng.integers(5, 600)))
+    g = GroundParams(16, float(rng.choice([-0.1, -0.4, 0.0]))) if seed % 2 == 0 else None
+    frames = [_random_scene(rng, int(rng.integers(500, 60_000))) for _ in range(4)]
+    ctr, k_off, clusters, offs, taps = run_batch_with_taps(gpu, frames, d, g)
+    for f, a in enumerate(frames):
+        ora = oracle_stages(a, d, g)
+        if g is not None:
+            assert np.array_equal(taps["low"][f].view(np.uint32), ora["low"].view(np.uint32))
+        assert_frame_parity(gpu, f, ora, offs, taps, ctr, k_off, clusters)
