@@ -427,7 +427,10 @@ def run_ours(args):
                 "kernels": kernels,
                 "pipeline_algorithmic_bytes_per_step": b_alg_step,
                 "pipeline_GBps": b_alg_step / (ms_total * 1e-3 / args.steps) / 1e9,
-                "pipeline_frac": b_alg_step / (ms_total * 1e-3 / args.steps) / 1e9 / peak}
+                "pipeline_frac": b_alg_step / (ms_total * 1e-3 / args.steps) / 1e9 / peak,
+                "pipeline_note": "SURVEY 8(d) algorithmic bytes (two full passes over the scan) / step time; it can "
+                                 "exceed 1 because pass 2 provably skips rows that are entirely ground "
+                                 "(see kernels.keep_mask_kernel.rows_read_fraction) instead of reading them"}
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + pipeline + D2H
     msgs = [PointCloud2.from_xyzi(hnp[f]) for f in range(F)]
