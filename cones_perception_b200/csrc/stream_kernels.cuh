@@ -467,6 +467,27 @@ keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, Grou
     nrows += __popc(todo);
     const u32 live = todo;
     u32 myword = 0, gcount = 0, gkept = 0;
+    if (todo == 0xFFFFFFFFu) {
+      // a fully live group (e.g. a ring above the horizon): straight-line, eight rows per round
+#pragma unroll 1
+      for (u32 b = 0; b < 4; ++b) {
+        float4 p[kStreamRows];
+#pragma unroll
+        for (int r = 0; r < kStreamRows; ++r) {
+          const u32 i = half0 + (b * kStreamRows + r) * 32 + lane;
+          p[r] = (i < count) ? load_point<MODE>(in, first + local0 + i, L)
+                             : make_float4(0.f, 0.f, -__int_as_float(0x7f800000), 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < kStreamRows; ++r) {
+          const u32 i = half0 + (b * kStreamRows + r) * 32 + lane;
+          const u32 bal = __ballot_sync(kFull, keep_point(p[r], i < count, c, gk, thr, thr_min, gkept));
+          gcount += __popc(bal);
+          if ((u32)lane == b * kStreamRows + r) myword = bal;
+        }
+      }
+      todo = 0;
+    }
     while (todo) {
       // up to four rows per round: all their loads are issued before the first verdict
       float4 p[kBatch];
