@@ -110,13 +110,15 @@ class ConesGpu:
 
     def __init__(self, max_points: int, max_frames: int = 1, device: int = 0, max_point_step: int = 16,
                  max_survivors: int = 0, max_voxels: int = 0, taps: bool = False, back_mode: int | None = None,
-                 cluster_front: bool | None = None):
+                 cluster_front: bool | None = None, env: dict | None = None):
         self.lib = load_library()
         self._h = C.c_void_p()
         if taps:
             os.environ["CONESGPU_TAPS"] = "1"
         if back_mode is not None:   # tests: 0..2 shared-memory back half (growing budgets), 3 general path
             os.environ["CONESGPU_BACK_MODE"] = str(back_mode)
+        saved_env = {k: os.environ.get(k) for k in (env or {})}   # extra CONESGPU_* switches read by cp_create
+        os.environ.update({k: str(v) for k, v in (env or {}).items()})
         prev_cluster = os.environ.get("CONESGPU_CLUSTER_FRONT")
         if cluster_front is not None:   # single-pass 16-CTA-cluster front end on / off
             os.environ["CONESGPU_CLUSTER_FRONT"] = "1" if cluster_front else "0"
@@ -127,6 +129,11 @@ class ConesGpu:
             if taps:
                 os.environ.pop("CONESGPU_TAPS", None)
             os.environ.pop("CONESGPU_BACK_MODE", None)
+            for k, v in saved_env.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
             if cluster_front is not None:
                 if prev_cluster is None:
                     os.environ.pop("CONESGPU_CLUSTER_FRONT", None)

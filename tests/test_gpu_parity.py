@@ -333,3 +333,25 @@ def test_randomised_scenes_and_parameters(gpu, seed):
         if g is not None:
             assert np.array_equal(taps["low"][f].view(np.uint32), ora["low"].view(np.uint32))
         assert_frame_parity(gpu, f, ora, offs, taps, ctr, k_off, clusters)
+
+
+def test_row_skipping_is_exact_and_effective():
+    """Pass 2 skips rows whose highest z is below every ground threshold.  The result must not depend
+    on the skip (A/B against CONESGPU_ROWSKIP=0) and on a 64-beam scan most rows must be skipped."""
+    cfg = scans.config(3)
+    frames = list(scans.generate(cfg, 8, base_seed=70))
+    msgs = [PointCloud2.from_xyzi(f) for f in frames]
+    out = {}
+    for skip in ("1", "0"):
+        with api.ConesGpu(max_points=8 * cfg.points_per_frame, max_frames=8, env={"CONESGPU_ROWSKIP": skip}) as h:
+            ctr, off, cl = h.detect_batch(msgs, cfg.detect, cfg.ground)
+            out[skip] = (ctr.copy(), off.copy(), cl.copy(), h.last_rows_loaded())
+    rows_total = 8 * cfg.points_per_frame // 32
+    assert out["0"][3] == rows_total
+    assert 0 < out["1"][3] < 0.3 * rows_total
+    for a, b in zip(out["1"][:3], out["0"][:3]):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    for f, fr in enumerate(frames):
+        exp, _, _ = O.detect(O.view_of_xyzi(fr), cfg.detect, cfg.ground, O.CANONICAL)
+        got = out["1"][2][out["1"][1][f]:out["1"][1][f + 1]]
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
