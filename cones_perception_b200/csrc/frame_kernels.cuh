@@ -26,7 +26,16 @@ namespace cp {
 constexpr int kFrameThreadsMax = 512;
 
 #ifdef CP_PHASE_CLOCKS
-#define CP_PHASE(name) do { __syncthreads(); if (tid == 0 && f == 0) { long long c_ = clock64(); printf("%-10s %8lld cyc\n", name, c_ - s_clk); s_clk = c_; } } while (0)
+// instrumented build (-DCP_PHASE_CLOCKS): thread 0 of the CTA that owns frame 0 stamps every phase
+// and prints the cycle counts when the frame is done (one printf, so the phases are not perturbed)
+#define CP_PHASE(name)                                                          \
+  do {                                                                          \
+    __syncthreads();                                                            \
+    if (tid == 0 && f == 0 && clk_n < 16) {                                     \
+      clk_name[clk_n] = name;                                                   \
+      clk_t[clk_n++] = clock64();                                               \
+    }                                                                           \
+  } while (0)
 #else
 #define CP_PHASE(name) do { } while (0)
 #endif
@@ -155,7 +164,10 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
     const u32 f = s.frame;
     if (f >= a.n_frames) break;
 #ifdef CP_PHASE_CLOCKS
-    long long s_clk = clock64();
+    const char* clk_name[16];
+    long long clk_t[16];
+    int clk_n = 0;
+    const long long clk_0 = clock64();
 #endif
     // frame geometry: tiles [tile0, tile0 + ntiles), points [first, first + n)
     u32 tile0, ntiles, npts;
@@ -213,6 +225,7 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
       __syncthreads();
       // phase 2: all threads fetch points in parallel (independent loads, no serial chains)
       if (C <= (u32)CMAX) {
+#pragma unroll 4
         for (u32 i = tid; i < C; i += kFrameThreads) {
           const float4 p = load_point<MODE>(a.in, first + s.k0[i], a.layout);
           s.px[i] = p.x; s.py[i] = p.y; s.pz[i] = p.z; s.pw[i] = p.w;
@@ -497,26 +510,53 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
       }
       __syncthreads();
       CP_PHASE("binning");
-      for (u32 r = warp; r < V; r += kFrameThreads / 32) {
+#ifdef CP_UNION_LEVEL
+      __shared__ u32 dbg_cnt[2];
+      if (tid < 2) dbg_cnt[tid] = 0;
+      __syncthreads();
+#endif
+      // eight lanes per row, candidates strided over them: a few dozen rows run side by side per
+      // warp and a crowded cell (many candidates) does not stall the warp the way one thread per row
+      // does (measured: rows average 26 candidates but the longest have > 100).  The lanes of a row
+      // need no communication: each carries the row's root in a register, a hit costs one find.
+      constexpr u32 kLanesPerRow = 8;
+      for (u32 r = tid / kLanesPerRow; r < V; r += kFrameThreads / kLanesPerRow) {
         const u32 i = s.u.vox.perm[r];
         const u32 ci = s.u.vox.vcell[i];
         const u32 lo = s.vstart[ci ? ci - 1 : 0];
         const float xi = s.u.vox.vx[i], yi = s.u.vox.vy[i], zi = s.u.vox.vz[i];
-        for (u32 base = lo; base < r; base += 32) {
-          const u32 jp = base + lane;
-          const u32 j = jp < r ? s.u.vox.perm[jp] : 0u;
-          const bool hit = jp < r &&
-                           l2_simple(xi, yi, zi, s.u.vox.vx[j], s.u.vox.vy[j], s.u.vox.vz[j]) < a.ck.r2;
-          if (!__any_sync(kFull, hit)) continue;
-          const u32 rj = hit ? smem_find(s.u.vox.parent, j) : 0xFFFFFFFFu;
-          const u32 ri = smem_find(s.u.vox.parent, i);
-          const u32 m = min(__reduce_min_sync(kFull, rj), ri);
-          if (hit && rj != m && atomicCAS(&s.u.vox.parent[rj], rj, m) != rj) smem_union(s.u.vox.parent, rj, m);
-          if (lane == 0 && ri != m && atomicCAS(&s.u.vox.parent[ri], ri, m) != ri) smem_union(s.u.vox.parent, ri, m);
+        u32 ri = smem_find(s.u.vox.parent, i);
+#ifdef CP_UNION_LEVEL
+        u32 dbg_hits = 0, dbg_cand = (tid % kLanesPerRow == 0) ? r - lo : 0;
+#endif
+        for (u32 jp = lo + tid % kLanesPerRow; jp < r; jp += kLanesPerRow) {
+          const u32 j = s.u.vox.perm[jp];
+          if (l2_simple(xi, yi, zi, s.u.vox.vx[j], s.u.vox.vy[j], s.u.vox.vz[j]) < a.ck.r2) {
+#if defined(CP_UNION_LEVEL) && CP_UNION_LEVEL == 0
+            dbg_hits++;
+#elif defined(CP_UNION_LEVEL) && CP_UNION_LEVEL == 1
+            dbg_hits += smem_find(s.u.vox.parent, j);
+#else
+            const u32 rj = smem_find(s.u.vox.parent, j);
+            if (rj != ri) {
+              smem_union(s.u.vox.parent, rj, ri);
+              ri = smem_find(s.u.vox.parent, i);
+            }
+#endif
+          }
         }
+#ifdef CP_UNION_LEVEL
+        if (f == 0) {
+          atomicAdd(&dbg_cnt[0], dbg_cand);
+          atomicAdd(&dbg_cnt[1], dbg_hits);
+        }
+#endif
       }
       __syncthreads();
       CP_PHASE("union");
+#ifdef CP_UNION_LEVEL
+      if (tid == 0 && f == 0) printf("V=%u candidates=%u hits(or sum)=%u\n", V, dbg_cnt[0], dbg_cnt[1]);
+#endif
       // ---- S6: labels (root = min voxel index of the component) and component sizes
       for (u32 v = tid; v < V; v += kFrameThreads) s.u.vox.label[v] = smem_find(s.u.vox.parent, v);
       __syncthreads();
@@ -605,6 +645,17 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
         }
       }
     }
+#ifdef CP_PHASE_CLOCKS
+    __syncthreads();
+    if (tid == 0 && f == 0) {
+      long long prev = clk_0;
+      for (int q = 0; q < clk_n; ++q) {
+        printf("%-12s %8lld cyc\n", clk_name[q], clk_t[q] - prev);
+        prev = clk_t[q];
+      }
+      printf("%-12s %8lld cyc  (total %lld)\n", "tail", clock64() - prev, clock64() - clk_0);
+    }
+#endif
   }
 }
 
