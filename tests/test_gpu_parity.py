@@ -1,4 +1,6 @@
 """-m gpu: the CUDA path (through the C ABI) against the CPU oracle, bit for bit."""
+import os
+
 import numpy as np
 import pytest
 
@@ -310,7 +312,7 @@ def _random_scene(rng, n):
     return out
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CONES_STRESS_SEEDS", "6"))))
 def test_randomised_scenes_and_parameters(gpu, seed):
     """Random clouds x random (valid) parameter sets, several frames per batch, with and without
     ground removal: every stage must equal the oracle bit for bit."""
@@ -355,3 +357,21 @@ def test_row_skipping_is_exact_and_effective():
         exp, _, _ = O.detect(O.view_of_xyzi(fr), cfg.detect, cfg.ground, O.CANONICAL)
         got = out["1"][2][out["1"][1][f]:out["1"][1][f + 1]]
         assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_every_back_half_variant_gives_the_same_cones(mode):
+    """All four back-half variants (three shared-memory budgets + the general path), forced one by one,
+    on a batch whose frames fit every budget."""
+    cfg = scans.config(3)
+    frames = list(scans.generate(cfg, 5, base_seed=80))
+    with api.ConesGpu(max_points=5 * cfg.points_per_frame, max_frames=5, back_mode=mode) as h:
+        ctr, off, cl = h.detect_batch([PointCloud2.from_xyzi(f) for f in frames], cfg.detect, cfg.ground)
+        single, _ = h.detect(PointCloud2.from_xyzi(frames[0]), cfg.detect, cfg.ground)   # few-frame (512-thread) path
+    for f, fr in enumerate(frames):
+        exp, octr, _ = O.detect(O.view_of_xyzi(fr), cfg.detect, cfg.ground, O.CANONICAL)
+        got = cl[off[f]:off[f + 1]]
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (mode, f)
+        assert int(ctr["n_cropped"][f]) == octr.n_cropped and int(ctr["n_voxels"][f]) == octr.n_voxels
+        assert int(ctr["n_components"][f]) == octr.n_components and int(ctr["key_bits"][f]) == octr.key_bits
+    assert np.array_equal(single.view(np.uint32), cl[off[0]:off[1]].view(np.uint32))
