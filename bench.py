@@ -260,6 +260,16 @@ def run_ours(args):
     frame_points = np.full(F, N, dtype=np.uint32)
     gpu.set_device_input(dev.data_ptr(), frame_points, keep=dev)
     cone_cap = F * CONE_CAP_PER_FRAME
+    # Two batches in flight: consecutive steps alternate between two handles (two streams, two sets of
+    # intermediates), so the latency-bound tail of one batch (pass 2, per-frame kernel, packing) overlaps
+    # the HBM-bound first pass of the next.  Every step still runs the whole path on the whole batch.
+    lanes = [gpu]
+    if args.lanes >= 2:
+        gpu_b = api.ConesGpu(max_points=F * N, max_frames=F, device=local, max_survivors=max(F * N // 8, 1 << 20),
+                             max_voxels=max(F * N // 16, 1 << 19))
+        gpu_b.set_device_input(dev.data_ptr(), frame_points, keep=dev)
+        lanes.append(gpu_b)
+    exts = [torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local)) for h in lanes]
 
     # result path when N > 1: the rank's packed cone list (offsets + records, one device block)
     # is copied to a staging buffer on the compute stream and gathered to rank 0 with ONE
@@ -270,7 +280,8 @@ def run_ours(args):
     gather_mode = os.environ.get("BENCH_GATHER", "peer") if world > 1 else "none"
     if gather_mode == "peer":
         try:
-            setup_peer_gather(gpu, rank, world, F, cone_cap)
+            for h in lanes:
+                setup_peer_gather(h, rank, world, F, cone_cap)
         except Exception as e:  # CUDA IPC unavailable: fall back to the collective
             print(f"[bench] peer gather unavailable ({e}); using NCCL all_gather", file=sys.stderr)
             gather_mode = "nccl"
@@ -278,6 +289,8 @@ def run_ours(args):
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if int(flags.item()) == 0:
             gather_mode = "nccl"
+    if gather_mode == "nccl":
+        lanes, exts = lanes[:1], exts[:1]      # the collective fallback keeps one batch in flight
     # high priority: the collective's few CTAs get SM slots ahead of the next step's grid-filling kernels
     comm = torch.cuda.Stream(priority=-1) if world > 1 else None
     stage = [torch.empty(words, dtype=torch.int32, device="cuda") for _ in range(2)] if world > 1 else None
@@ -289,8 +302,11 @@ def run_ours(args):
     ready = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
     freed = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
 
+    lane_no = [0]
+
     def step_device():
-        gpu.run(d, g)
+        lanes[lane_no[0] % len(lanes)].run(d, g)
+        lane_no[0] += 1
         if gather_mode == "nccl":
             i = step_no[0] & 1
             step_no[0] += 1
@@ -309,19 +325,23 @@ def run_ours(args):
                 stage_free[i] = True
 
     def drain():
-        if world > 1:
+        if world > 1 and comm is not None:
             ext.wait_stream(comm)
+        for e in exts[1:]:
+            ext.wait_stream(e)                      # lane 0's stream waits for the other lane
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) * len(lanes)):
         step_device()
     drain()
-    gpu.sync()
+    for h in lanes:
+        h.sync()
     torch.cuda.synchronize()
+    lane_no[0] = 0
     ctr, k_off, clusters = gpu.results()
     launches_per_step = gpu.last_launch_count()
 
@@ -332,16 +352,21 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
+    for e in exts[1:]:
+        e.wait_event(e0)                            # no lane starts before the start event
     for _ in range(args.steps):
         step_device()
     drain()
     e1.record(ext)
     barrier()
     gpu.sync()
+    for h in lanes:
+        h.sync()
     if gather_mode == "peer" and rank == 0:
-        seq = gpu.gather_seq()
-        gpu.gather_wait(seq)
-        gathered[0] = torch.from_numpy(gpu.gather_read(seq, world, words))
+        last = lanes[(args.steps - 1) % len(lanes)]
+        seq = last.gather_seq()
+        last.gather_wait(seq)
+        gathered[0] = torch.from_numpy(last.gather_read(seq, world, words))
     if world > 1 and rank == 0 and gathered[0] is not None:
         # the gathered list must hold every rank's frames; rank 0's block must equal its own results
         from cones_perception_b200.sharding import unpack_gathered
@@ -522,6 +547,7 @@ def run_ours(args):
                        "frames_per_gpu": F, "points_per_frame": N, "global_frames": world * F,
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                        "result_gather": gather_mode, "host_binding_rank0": numa,
+                       "batches_in_flight": len(lanes),
                        "cache": f"inputs larger than L2 ({F * N * 16 / 1e6:.0f} MB per rank vs 126 MB), no flush needed",
                        "latency_workload": "cfg2 single frame, host cloud in -> cone list out"},
             "per_step_counts": {"points": F * N, "cropped": C_tot, "voxels": V_tot, "clusters": K_tot},
@@ -529,7 +555,8 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
         }
-    gpu.close()
+    for h in lanes:
+        h.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -547,6 +574,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--frames-per-gpu", type=int, default=512)
     ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--lanes", type=int, default=2, help="batches in flight (handles/streams alternating per step)")
     ap.add_argument("--cpu-sample-frames", type=int, default=512, help="frames timed on one core for cpu_baseline")
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0, help="minimum CPU time spent on cpu_baseline")
     ap.add_argument("--cpu-step-frames", type=int, default=128, help="frames per step of --impl reference")

@@ -129,6 +129,7 @@ struct cp_handle {
   u32* d_rowmax = nullptr;     // highest z (ordered key) of every 32-point row, written by pass 1
   bool rowmax_valid = false;   // pass 1 of the current run filled d_rowmax
   bool use_rowskip = true;     // CONESGPU_ROWSKIP=0 disables the skip (A/B measurements)
+  int stream_ctas_per_sm = 8;  // grid cap of the streaming kernels (CONESGPU_STREAM_CTAS: leave room for a second handle)
   u64 *d_desc_a = nullptr, *d_desc_b = nullptr, *d_desc_c = nullptr, *d_desc_d = nullptr;
   u32 *d_tap_keys = nullptr, *d_tap_order = nullptr;
   i32* d_tap_labels = nullptr;
@@ -987,7 +988,7 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   h->launches = 0;
   if (!h->capturing) cudaEventRecord(h->ev0, h->stream);
   launch_init(h, ground ? ground->default_lowest_point : 0.0f);
-  const u32 sgrid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, 8);
+  const u32 sgrid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, h->stream_ctas_per_sm);
   h->ran_cluster = cluster_front_eligible(h, g, ground != nullptr) &&
                    launch_front_cluster(h, g, crop, gk, ground->default_lowest_point);
   h->ran_fused = !h->ran_cluster && ground && g.uniform_n && h->use_fused;
@@ -1155,6 +1156,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   h->taps = tap_env && tap_env[0] == '1';
   const char* mode_env = getenv("CONESGPU_BACK_MODE");  // tests: force the back-half variant
   if (mode_env && mode_env[0] >= '0' && mode_env[0] <= '3') h->back_mode = mode_env[0] - '0';
+  const char* sc_env = getenv("CONESGPU_STREAM_CTAS");
+  if (sc_env && atoi(sc_env) >= 1 && atoi(sc_env) <= 8) h->stream_ctas_per_sm = atoi(sc_env);
   const char* rs_env = getenv("CONESGPU_ROWSKIP");
   if (rs_env) h->use_rowskip = rs_env[0] != '0';
   const char* cl_env = getenv("CONESGPU_CLUSTER_FRONT");  // "1": single-pass 16-CTA-cluster front end
