@@ -264,11 +264,11 @@ def run_ours(args):
     # intermediates), so the latency-bound tail of one batch (pass 2, per-frame kernel, packing) overlaps
     # the HBM-bound first pass of the next.  Every step still runs the whole path on the whole batch.
     lanes = [gpu]
-    if args.lanes >= 2:
-        gpu_b = api.ConesGpu(max_points=F * N, max_frames=F, device=local, max_survivors=max(F * N // 8, 1 << 20),
-                             max_voxels=max(F * N // 16, 1 << 19))
-        gpu_b.set_device_input(dev.data_ptr(), frame_points, keep=dev)
-        lanes.append(gpu_b)
+    for _ in range(1, max(1, args.lanes)):
+        h2 = api.ConesGpu(max_points=F * N, max_frames=F, device=local, max_survivors=max(F * N // 8, 1 << 20),
+                          max_voxels=max(F * N // 16, 1 << 19))
+        h2.set_device_input(dev.data_ptr(), frame_points, keep=dev)
+        lanes.append(h2)
     exts = [torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local)) for h in lanes]
 
     # result path when N > 1: the rank's packed cone list (offsets + records, one device block)
