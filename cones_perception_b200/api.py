@@ -28,8 +28,11 @@ ABI_SYMBOLS = [
     "cp_sync", "cp_batch_results", "cp_detect_batch", "cp_last_run_ms", "cp_last_launch_count", "cp_stream",
     "cp_debug_tap", "cp_debug_sort", "cp_set_stage_timing", "cp_stage_ms", "cp_device_results",
     "cp_gather_create", "cp_gather_open", "cp_gather_seq", "cp_gather_wait", "cp_gather_read",
-    "cp_last_rows_loaded",
+    "cp_last_rows_loaded", "cp_cone_crops", "cp_cone_images", "cp_rasterize_crops",
 ]
+
+CONE_IMG_ROWS, CONE_IMG_COLS = 15, 12
+CONE_EMPTY, CONE_BAD_INDEX, CONE_BAD_INTENSITY, CONE_AMBIGUOUS = 1, 2, 4, 8
 
 CLUSTER_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.uint32), ("min_index", np.uint32)])
 COUNTER_DTYPE = np.dtype([(n, np.uint32) for n in (
@@ -100,6 +103,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cp_gather_read.argtypes = [vp, u32, vp, u64]
     lib.cp_last_rows_loaded.argtypes = [vp]
     lib.cp_last_rows_loaded.restype = u64
+    lib.cp_cone_crops.argtypes = [vp, C.POINTER(CCloudView), u32, vp, u32, C.c_float, vp, vp, u32]
+    lib.cp_cone_images.argtypes = [vp, C.POINTER(CCloudView), u32, vp, u32, C.c_float, vp, vp, vp]
+    lib.cp_rasterize_crops.argtypes = [vp, vp, vp, u32, vp, vp]
     if path is None:
         _lib = lib
     return lib
@@ -147,7 +153,7 @@ class ConesGpu:
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self.lib.cp_destroy(self._h)
-            self._h = C.c_void_p()
+            self._h = None
 
     __del__ = close
 
@@ -191,6 +197,46 @@ class ConesGpu:
         self._ck(self.lib.cp_detect(self._h, C.byref(view), C.byref(cd), C.byref(cg) if cg is not None else None,
                                     out.ctypes.data, cap, C.byref(k), ctr.ctypes.data))
         return out[:k.value].copy(), ctr[0].copy()
+
+    # ---- colour path inputs ----------------------------------------------
+    @staticmethod
+    def _centers(centers) -> np.ndarray:
+        return np.ascontiguousarray(np.asarray(centers, dtype=np.float32).reshape(-1, 2))
+
+    def cone_crops(self, centers, cone_width: float = 0.228, msg: PointCloud2 | None = None, frame: int = 0,
+                   cap_points: int = 1 << 16, fake_missing_intensity: bool = True):
+        """get_reconstructed_cone (src/cone_detection.cpp:222-238) for all centres at once.  msg=None
+        reuses frame `frame` of the input already staged on the device.  Returns (offsets, xyzi)."""
+        c = self._centers(centers)
+        view = make_view(msg, fake_missing_intensity) if msg is not None else None
+        off = np.zeros(len(c) + 1, np.uint32)
+        pts = np.empty((cap_points, 4), np.float32)
+        self._ck(self.lib.cp_cone_crops(self._h, C.byref(view) if view is not None else None, frame, c.ctypes.data,
+                                        len(c), cone_width, off.ctypes.data, pts.ctypes.data, cap_points))
+        return off, pts[:off[-1]].copy()
+
+    def cone_images(self, centers, cone_width: float = 0.228, msg: PointCloud2 | None = None, frame: int = 0,
+                    fake_missing_intensity: bool = True):
+        """Crops + ColorClassifier.to_image (scripts/color_classifier_server.py:130-156) on the device.
+        Returns (images [n,15,12] uint8, counts, flags)."""
+        c = self._centers(centers)
+        view = make_view(msg, fake_missing_intensity) if msg is not None else None
+        img = np.zeros((len(c), CONE_IMG_ROWS, CONE_IMG_COLS), np.uint8)
+        counts, flags = np.zeros(len(c), np.uint32), np.zeros(len(c), np.uint32)
+        self._ck(self.lib.cp_cone_images(self._h, C.byref(view) if view is not None else None, frame, c.ctypes.data,
+                                         len(c), cone_width, img.ctypes.data, counts.ctypes.data, flags.ctypes.data))
+        return img, counts, flags
+
+    def rasterize_crops(self, xyzi: np.ndarray, offsets):
+        """to_image on host crops (packed x,y,z,intensity rows + offsets).  Returns (images, flags)."""
+        a = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        off = np.ascontiguousarray(offsets, np.uint32)
+        n = len(off) - 1
+        img = np.zeros((n, CONE_IMG_ROWS, CONE_IMG_COLS), np.uint8)
+        flags = np.zeros(n, np.uint32)
+        self._ck(self.lib.cp_rasterize_crops(self._h, a.ctypes.data, off.ctypes.data, n, img.ctypes.data,
+                                             flags.ctypes.data))
+        return img, flags
 
     # ---- batches ----------------------------------------------------------------------
     def set_device_input(self, d_ptr: int, frame_points, point_step: int = 16, off=(0, 4, 8, 12), keep=None):

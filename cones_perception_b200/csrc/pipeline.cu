@@ -15,6 +15,7 @@
 
 #include "cluster_front.cuh"
 #include "cluster_kernels.cuh"
+#include "color_kernels.cuh"
 #include "common.cuh"
 #include "frame_kernels.cuh"
 #include "radix_sort.cuh"
@@ -105,6 +106,13 @@ struct cp_handle {
   uint8_t* d_in = nullptr;  // staged input (host batches)
   size_t d_in_bytes = 0;
   uint8_t* d_out32 = nullptr;
+  // colour path (color_kernels.cuh): allocated on first use, grown on demand
+  struct ColorBufs {
+    u32 *mask = nullptr, *tcount = nullptr, *texcl = nullptr, *off = nullptr, *flags = nullptr;
+    float4* pts = nullptr;
+    uint8_t* img = nullptr;
+    size_t mask_n = 0, tile_n = 0, texcl_n = 0, off_n = 0, flags_n = 0, pts_n = 0, img_n = 0;
+  } color;
   const uint8_t* in_ptr = nullptr;  // current batch input (d_in or caller memory)
   Layout layout{};
   HostGeom hg;
@@ -129,6 +137,9 @@ struct cp_handle {
   u32* d_rowmax = nullptr;     // highest z (ordered key) of every 32-point row, written by pass 1
   bool rowmax_valid = false;   // pass 1 of the current run filled d_rowmax
   bool use_rowskip = true;     // CONESGPU_ROWSKIP=0 disables the skip (A/B measurements)
+  bool tail_priority = false;  // CONESGPU_PRIO=1: greatest-priority stream, pass 1 demoted
+  int prio_low = 0;
+  int k1_ctas_per_sm = 0;  // CONESGPU_K1_CTAS: separate grid cap for pass 1 (0 = stream_ctas_per_sm)
   int stream_ctas_per_sm = 8;  // grid cap of the streaming kernels (CONESGPU_STREAM_CTAS: leave room for a second handle)
   u64 *d_desc_a = nullptr, *d_desc_b = nullptr, *d_desc_c = nullptr, *d_desc_d = nullptr;
   u32 *d_tap_keys = nullptr, *d_tap_order = nullptr;
@@ -613,11 +624,32 @@ void launch_front_fused(cp_handle* h, const Geom& g, const CropK& c, const Groun
   h->launches++;
 }
 
+template <int MODE>
+void launch_sector_min_mode(cp_handle* h, const Geom& g, u32 grid) {
+  if (!h->tail_priority) {
+    ground_sector_min_kernel<MODE><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key, h->d_rowmax);
+    return;
+  }
+  // the stream runs at the greatest priority; pass 1 alone is demoted, so that the short kernels behind
+  // it (another handle's pass 2 / per-frame kernel) take the SM slots pass 1 frees, not the other way round
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kStreamThreads);
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributePriority;
+  at[0].val.priority = h->prio_low;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, ground_sector_min_kernel<MODE>, h->in_ptr, h->layout, g, h->d_low_key, h->d_rowmax);
+}
 void launch_sector_min(cp_handle* h, const Geom& g, u32 grid) {
+  if (h->k1_ctas_per_sm)
+    grid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, h->k1_ctas_per_sm);
   switch (h->layout.mode) {
-    case 0: ground_sector_min_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key, h->d_rowmax); break;
-    case 1: ground_sector_min_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key, h->d_rowmax); break;
-    default: ground_sector_min_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, h->d_low_key, h->d_rowmax); break;
+    case 0: launch_sector_min_mode<0>(h, g, grid); break;
+    case 1: launch_sector_min_mode<1>(h, g, grid); break;
+    default: launch_sector_min_mode<2>(h, g, grid); break;
   }
 }
 
@@ -1080,6 +1112,116 @@ cp_status device_errors(cp_handle* h) {
 }  // namespace
 
 // ======================================================================== C ABI
+// ---- colour path inputs (color_kernels.cuh) ----------------------------------------------
+template <typename T>
+cp_status grow(cp_handle* h, T** p, size_t* have, size_t need) {
+  if (need <= *have && *p) return CP_OK;
+  if (*p) {
+    cudaStreamSynchronize(h->stream);
+    cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+  }
+  void* q = nullptr;
+  const size_t n = std::max<size_t>(need, 1);
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    h->err = std::string("cudaMalloc failed (colour path): ") + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? CP_E_NOMEM : CP_E_CUDA;
+  }
+  *p = static_cast<T*>(q);
+  *have = n;
+  return CP_OK;
+}
+
+// src/cone_detection.cpp:226-227 as fp32 bounds: `c + hw >= (double)p` <=> p <= largest float <= c + hw, and
+// `c - hw <= (double)p` <=> p >= smallest float >= c - hw (every float is exactly representable as a double)
+static void box_bounds(float c, double hw, float* lo, float* hi) {
+  const double dhi = (double)c + hw, dlo = (double)c - hw;
+  float fhi = (float)dhi, flo = (float)dlo;
+  if ((double)fhi > dhi) fhi = std::nextafterf(fhi, -INFINITY);
+  if ((double)flo < dlo) flo = std::nextafterf(flo, INFINITY);
+  *lo = flo;  // NaN centres give NaN bounds: nothing matches, like the reference
+  *hi = fhi;
+}
+
+// Resolves the cloud a colour-path call works on and enqueues the box gather of all centres.
+// On return crop offsets are in h->color.off (device) and the packed crops in h->color.pts.
+cp_status enqueue_cone_crops(cp_handle* h, const cp_cloud_view* cloud, u32 frame, const cp_cone_center* centers,
+                             u32 n_centers, float cone_width, size_t want_cap) {
+  if (n_centers && !centers) {
+    h->err = "NULL centers";
+    return CP_E_PARAM;
+  }
+  if (cloud) {
+    cp_status st = cp_batch_set_host_input(h, cloud, 1);
+    if (st) return st;
+    frame = 0;
+  } else if (!h->batch_ready) {
+    h->err = "cloud is NULL and no input has been staged on this handle";
+    return CP_E_STATE;
+  }
+  if (frame >= h->hg.n_frames) {
+    h->err = "frame index outside the staged batch";
+    return CP_E_PARAM;
+  }
+  const u32 n_points = h->hg.frame_n[frame];
+  const u64 first_point = h->hg.frame_off[frame];
+  const u32 n_rows = (n_points + 31) / 32;
+  const u32 n_tiles = std::max<u32>(1, (n_rows + kTileWords - 1) / kTileWords);
+  cp_handle::ColorBufs& cb = h->color;
+  cp_status st;
+  if ((st = grow(h, &cb.mask, &cb.mask_n, (size_t)kConeChunk * std::max<u32>(n_rows, 1)))) return st;
+  if ((st = grow(h, &cb.tcount, &cb.tile_n, (size_t)kConeChunk * n_tiles))) return st;
+  if ((st = grow(h, &cb.texcl, &cb.texcl_n, (size_t)kConeChunk * n_tiles))) return st;
+  if ((st = grow(h, &cb.off, &cb.off_n, (size_t)n_centers + 1))) return st;
+  if ((st = grow(h, &cb.flags, &cb.flags_n, (size_t)n_centers + 1))) return st;
+  if ((st = grow(h, &cb.pts, &cb.pts_n, std::max<size_t>(want_cap, 1u << 16)))) return st;
+  const u32 cap = (u32)std::min<size_t>(cb.pts_n, 0xFFFFFFFFu);
+  CK(cudaMemsetAsync(cb.off, 0, sizeof(u32), h->stream));
+  const double hw = (double)cone_width / 1.5;  // CONE_WIDTH / 1.5: float / double literal
+  for (u32 k0 = 0; k0 < n_centers; k0 += kConeChunk) {
+    ConeBoxes B;
+    memset(&B, 0, sizeof(B));
+    B.n = std::min<u32>(kConeChunk, n_centers - k0);
+    for (u32 k = 0; k < B.n; ++k) {
+      box_bounds(centers[k0 + k].x, hw, &B.xlo[k], &B.xhi[k]);
+      box_bounds(centers[k0 + k].y, hw, &B.ylo[k], &B.yhi[k]);
+    }
+    CK(cudaMemsetAsync(cb.mask, 0, sizeof(u32) * (size_t)B.n * std::max<u32>(n_rows, 1), h->stream));
+    CK(cudaMemsetAsync(cb.tcount, 0, sizeof(u32) * (size_t)B.n * n_tiles, h->stream));
+    if (n_points) {
+      switch (h->layout.mode) {
+        case 0: cone_box_mask_kernel<0><<<n_tiles, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, n_points, B, n_rows, n_tiles, cb.mask, cb.tcount); break;
+        case 1: cone_box_mask_kernel<1><<<n_tiles, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, n_points, B, n_rows, n_tiles, cb.mask, cb.tcount); break;
+        default: cone_box_mask_kernel<2><<<n_tiles, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, n_points, B, n_rows, n_tiles, cb.mask, cb.tcount); break;
+      }
+    }
+    cone_box_scan_kernel<<<1, 1024, 0, h->stream>>>(B.n, k0, n_tiles, cb.tcount, cb.texcl, cb.off);
+    if (n_points) {
+      switch (h->layout.mode) {
+        case 0: cone_box_gather_kernel<0><<<n_tiles, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, B.n, k0, n_rows, n_tiles, cb.mask, cb.tcount, cb.texcl, cb.off, cap, cb.pts); break;
+        case 1: cone_box_gather_kernel<1><<<n_tiles, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, B.n, k0, n_rows, n_tiles, cb.mask, cb.tcount, cb.texcl, cb.off, cap, cb.pts); break;
+        default: cone_box_gather_kernel<2><<<n_tiles, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, B.n, k0, n_rows, n_tiles, cb.mask, cb.tcount, cb.texcl, cb.off, cap, cb.pts); break;
+      }
+    }
+  }
+  CK(cudaGetLastError());
+  return CP_OK;
+}
+
+cp_status enqueue_raster(cp_handle* h, u32 n_cones) {
+  cp_handle::ColorBufs& cb = h->color;
+  cp_status st = grow(h, &cb.img, &cb.img_n, (size_t)std::max<u32>(n_cones, 1) * kImgPix);
+  if (st) return st;
+  if (n_cones)
+    cone_raster_kernel<<<n_cones, kRasterThreads, 0, h->stream>>>(cb.pts, cb.off, (u32)std::min<size_t>(cb.pts_n, 0xFFFFFFFFu),
+                                                                 cb.img, cb.flags);
+  CK(cudaGetLastError());
+  return CP_OK;
+}
+
 extern "C" {
 
 const char* cp_strerror(cp_status s) {
@@ -1143,7 +1285,13 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
     return fail(CP_E_CUDA);
   }
   h->sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  const char* prio_env = getenv("CONESGPU_PRIO");
+  h->tail_priority = prio_env && prio_env[0] == '1';
+  int prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&h->prio_low, &prio_hi);
+  const char* k1_env = getenv("CONESGPU_K1_CTAS");
+  if (k1_env && atoi(k1_env) >= 1 && atoi(k1_env) <= 256) h->k1_ctas_per_sm = atoi(k1_env);
+  if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, h->tail_priority ? prio_hi : h->prio_low) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming) != cudaSuccess ||
@@ -1271,6 +1419,9 @@ void cp_destroy(cp_handle* h) {
   for (void* p : h->dev_allocs) cudaFree(p);
   for (void* p : h->pin_allocs) cudaFreeHost(p);
   if (h->d_out32) cudaFree(h->d_out32);
+  for (void* q : {(void*)h->color.mask, (void*)h->color.tcount, (void*)h->color.texcl, (void*)h->color.off,
+                  (void*)h->color.flags, (void*)h->color.pts, (void*)h->color.img})
+    if (q) cudaFree(q);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1856,6 +2007,103 @@ cp_status cp_debug_sort(cp_handle* h, uint64_t* keys, uint32_t* vals, uint32_t n
   CK(cudaMemcpyAsync(vals, inb ? h->d_ovals_b : h->d_ovals_a, sizeof(u32) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
+  return CP_OK;
+}
+
+cp_status cp_cone_crops(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame, const cp_cone_center* centers,
+                        uint32_t n_centers, float cone_width, uint32_t* crop_offsets, float* crop_xyzi,
+                        uint32_t cap_points) {
+  if (!h) return CP_E_PARAM;
+  if (!crop_offsets) {
+    h->err = "NULL crop_offsets";
+    return CP_E_PARAM;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  cp_status st = enqueue_cone_crops(h, cloud, frame, centers, n_centers, cone_width, crop_xyzi ? cap_points : 0);
+  if (st) return st;
+  CK(cudaMemcpyAsync(crop_offsets, h->color.off, sizeof(u32) * ((size_t)n_centers + 1), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const u32 total = crop_offsets[n_centers];
+  if (crop_xyzi) {
+    if (total > cap_points) {
+      h->err = "cone crops hold " + std::to_string(total) + " points, more than cap_points";
+      return CP_E_CAPACITY;
+    }
+    if (total) {
+      CK(cudaMemcpyAsync(crop_xyzi, h->color.pts, sizeof(float4) * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+  }
+  return CP_OK;
+}
+
+cp_status cp_cone_images(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame, const cp_cone_center* centers,
+                         uint32_t n_centers, float cone_width, uint8_t* images, uint32_t* counts, uint32_t* flags) {
+  if (!h) return CP_E_PARAM;
+  if (n_centers && !images) {
+    h->err = "NULL images";
+    return CP_E_PARAM;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<u32> off((size_t)n_centers + 1);
+  size_t want = h->color.pts_n;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // the cloud is staged by the first attempt only; a retry (crop buffer too small) reuses it
+    cp_status st = enqueue_cone_crops(h, attempt == 0 ? cloud : nullptr, attempt == 0 ? frame : (cloud ? 0 : frame),
+                                      centers, n_centers, cone_width, want);
+    if (st) return st;
+    CK(cudaMemcpyAsync(off.data(), h->color.off, sizeof(u32) * off.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (off[n_centers] <= h->color.pts_n) break;
+    if (off[n_centers] == 0xFFFFFFFFu || attempt == 1) {
+      h->err = "cone crops exceed the addressable crop buffer";
+      return CP_E_CAPACITY;
+    }
+    want = off[n_centers];
+  }
+  cp_status st = enqueue_raster(h, n_centers);
+  if (st) return st;
+  if (n_centers) {
+    CK(cudaMemcpyAsync(images, h->color.img, (size_t)n_centers * kImgPix, cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, h->color.flags, sizeof(u32) * n_centers, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  if (counts)
+    for (u32 c = 0; c < n_centers; ++c) counts[c] = off[c + 1] - off[c];
+  return CP_OK;
+}
+
+cp_status cp_rasterize_crops(cp_handle* h, const float* crop_xyzi, const uint32_t* crop_offsets, uint32_t n_crops,
+                             uint8_t* images, uint32_t* flags) {
+  if (!h) return CP_E_PARAM;
+  if (!crop_offsets || (n_crops && !images)) {
+    h->err = "NULL crop_offsets or images";
+    return CP_E_PARAM;
+  }
+  for (u32 c = 0; c < n_crops; ++c)
+    if (crop_offsets[c + 1] < crop_offsets[c]) {
+      h->err = "crop_offsets must be non-decreasing";
+      return CP_E_PARAM;
+    }
+  const u32 total = crop_offsets[n_crops];
+  if (total && !crop_xyzi) {
+    h->err = "NULL crop_xyzi";
+    return CP_E_PARAM;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  cp_handle::ColorBufs& cb = h->color;
+  cp_status st;
+  if ((st = grow(h, &cb.off, &cb.off_n, (size_t)n_crops + 1))) return st;
+  if ((st = grow(h, &cb.flags, &cb.flags_n, (size_t)n_crops + 1))) return st;
+  if ((st = grow(h, &cb.pts, &cb.pts_n, std::max<size_t>(total, 1u << 16)))) return st;
+  CK(cudaMemcpyAsync(cb.off, crop_offsets, sizeof(u32) * ((size_t)n_crops + 1), cudaMemcpyHostToDevice, h->stream));
+  if (total) CK(cudaMemcpyAsync(cb.pts, crop_xyzi, sizeof(float4) * (size_t)total, cudaMemcpyHostToDevice, h->stream));
+  if ((st = enqueue_raster(h, n_crops))) return st;
+  if (n_crops) {
+    CK(cudaMemcpyAsync(images, cb.img, (size_t)n_crops * kImgPix, cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, cb.flags, sizeof(u32) * n_crops, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
   return CP_OK;
 }
 

@@ -199,6 +199,41 @@ uint32_t cp_last_launch_count(const cp_handle* h);
 /* The handle's stream as a cudaStream_t, for callers that time with their own events. */
 void* cp_stream(cp_handle* h);
 
+/* --- colour path inputs: what sits between a detected cone and the classifier ---
+ * Only needed with classify_colors:=true.  The network itself (models/dam_net) stays with the
+ * reference's Python service: there is no TFLite oracle to hold an implementation to. */
+typedef struct cp_cone_center {
+  float x, y; /* the centroid AFTER the radial extension (src/cone_detection.cpp:276-278), as passed at :309 */
+} cp_cone_center;
+#define CP_CONE_IMG_ROWS 15 /* scripts/color_classifier_server.py:27-30 */
+#define CP_CONE_IMG_COLS 12
+enum {
+  CP_CONE_EMPTY = 1,         /* no point in the box: the service skips the cone (color_classifier_server.py:83-84) */
+  CP_CONE_BAD_INDEX = 2,     /* numpy would raise IndexError (elevation above +15 deg, non-finite coordinates) */
+  CP_CONE_BAD_INTENSITY = 4, /* interp1d would raise ValueError (intensity outside [0, 255] or NaN) */
+  CP_CONE_AMBIGUOUS = 8      /* a pixel coordinate lies within 1e-9 of a rounding boundary: image not guaranteed */
+};
+/* Replaces ConeDetector::get_reconstructed_cone (src/cone_detection.cpp:222-238) for n_centers cones in one
+ * pass: the points of the raw cloud with |x-cx| <= CONE_WIDTH/1.5 and |y-cy| <= CONE_WIDTH/1.5 (the reference's
+ * double-precision comparisons, both ends inclusive), in cloud order.
+ *   cloud: the raw cloud, or NULL to use frame `frame` of the input already on the device (the cloud the last
+ *          cp_detect / cp_batch_set_*_input call of this handle staged) — no second host-to-device copy.
+ *   crop_offsets[n_centers+1]: cone c owns crop_xyzi[4*crop_offsets[c] .. 4*crop_offsets[c+1]).
+ *   crop_xyzi: x, y, z, intensity per point (cap_points points); NULL to get the offsets only.
+ * CP_E_CAPACITY if the crops hold more than cap_points points (crop_offsets is still complete). */
+cp_status cp_cone_crops(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame, const cp_cone_center* centers,
+                        uint32_t n_centers, float cone_width, uint32_t* crop_offsets, float* crop_xyzi,
+                        uint32_t cap_points);
+/* cp_cone_crops followed on the device by ColorClassifier.to_image (scripts/color_classifier_server.py:
+ * 130-156): images[n_centers][15][12] uint8 (the classifier's input before the float cast at :108),
+ * counts[n_centers] = points per crop, flags[n_centers] = CP_CONE_* bits (image all zero unless flags is 0 or
+ * CP_CONE_AMBIGUOUS).  counts / flags may be NULL.  180 bytes per cone travel back instead of the crops. */
+cp_status cp_cone_images(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame, const cp_cone_center* centers,
+                         uint32_t n_centers, float cone_width, uint8_t* images, uint32_t* counts, uint32_t* flags);
+/* to_image alone, on host crops in the cp_cone_crops format (what handle_classify_color receives, :78-90). */
+cp_status cp_rasterize_crops(cp_handle* h, const float* crop_xyzi, const uint32_t* crop_offsets, uint32_t n_crops,
+                             uint8_t* images, uint32_t* flags);
+
 /* --- stage taps for parity tests (valid after cp_sync, whole batch, frame-major) ----
  * Every tap copies device state of the last run to host memory.  count = entries written. */
 typedef enum cp_tap {

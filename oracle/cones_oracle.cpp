@@ -580,6 +580,72 @@ void orc_extend(float* x, float* y, double extension_length) {
   *y = ny;
 }
 
+// ---- colour path inputs ---------------------------------------------------------------
+
+uint32_t orc_reconstruct_cone(const orc_point* cloud, uint32_t n, float cx, float cy, float cone_width,
+                              orc_point* out, uint32_t cap) {
+  // src/cone_detection.cpp:226-227: CONE_WIDTH is a float member, 1.5 a double literal, so the
+  // half width and both sums are evaluated in double; the point coordinates are widened.
+  const double hw = static_cast<double>(cone_width) / 1.5;
+  const double dcx = static_cast<double>(cx), dcy = static_cast<double>(cy);
+  uint32_t m = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const orc_point& q = cloud[i];
+    const double qx = q.x, qy = q.y;
+    if ((dcx + hw >= qx && dcx - hw <= qx) && (dcy + hw >= qy && dcy - hw <= qy)) {
+      if (m < cap) {
+        orc_point p;  // `Point p;` (:224): PCL's default constructor, then four fields assigned
+        p.x = q.x; p.y = q.y; p.z = q.z; p.pad = 1.0f;
+        p.intensity = q.intensity; p.c1 = p.c2 = p.c3 = 0.0f;
+        out[m] = p;
+      }
+      ++m;
+    }
+  }
+  return m;
+}
+
+uint32_t orc_to_image(const float* xyzi, uint32_t n, uint8_t* img) {
+  std::memset(img, 0, ORC_IMG_ROWS * ORC_IMG_COLS);
+  if (n == 0) return ORC_CONE_EMPTY;  // color_classifier_server.py:83-84
+  // module constants (:18-33): slope_vert = IMG_ROWS / (MIN_V_ANGLE - MAX_V_ANGLE) = 15 / -30
+  const double kMinV = -15.0, kSlopeVert = 15.0 / (-15.0 - 15.0);
+  const double kRad2Deg = 180.0 / M_PI;  // np.degrees
+  std::vector<double> va(n), ha(n);
+  uint32_t flags = 0;
+  double hmin = std::numeric_limits<double>::infinity(), hmax = -hmin;
+  for (uint32_t i = 0; i < n; ++i) {
+    const double X = xyzi[4 * i], Y = xyzi[4 * i + 1], Z = xyzi[4 * i + 2], I = xyzi[4 * i + 3];
+    const double xx = X * X, yy = Y * Y;           // pow(X, 2.0): numpy squares
+    const double s = xx + yy;
+    va[i] = std::atan2(Z, std::sqrt(s)) * kRad2Deg;  // :137
+    ha[i] = std::atan2(Y, X) * kRad2Deg;             // :142
+    if (!std::isfinite(va[i]) || !std::isfinite(ha[i])) flags |= ORC_CONE_BAD_INDEX;
+    if (!(I >= 0.0 && I <= 255.0)) flags |= ORC_CONE_BAD_INTENSITY;  // interp1d([0,255],...) bounds (:35)
+    hmin = std::min(hmin, ha[i]);
+    hmax = std::max(hmax, ha[i]);
+  }
+  if (flags) return flags;
+  const double slope_h = (ORC_IMG_COLS - 1) / (hmax - hmin + 1e-16);  // :148
+  std::vector<int> row(n), col(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    const double v = std::nearbyint(kSlopeVert * (va[i] - kMinV));  // np.round: half to even (:139)
+    const double h = std::nearbyint(slope_h * (ha[i] - hmin));      // :149
+    if (!(v >= -ORC_IMG_ROWS && v <= ORC_IMG_ROWS - 1) || !(h >= -ORC_IMG_COLS && h <= ORC_IMG_COLS - 1)) {
+      flags |= ORC_CONE_BAD_INDEX;  // numpy: IndexError
+      continue;
+    }
+    row[i] = v < 0 ? static_cast<int>(v) + ORC_IMG_ROWS : static_cast<int>(v);  // negative indices wrap
+    col[i] = h < 0 ? static_cast<int>(h) + ORC_IMG_COLS : static_cast<int>(h);
+  }
+  if (flags) return flags;
+  // image[rows, cols, 0] = intensity (:153): repeated pixels keep the last point's value; the
+  // identity interp1d returns the value itself and the uint8 store truncates toward zero
+  for (uint32_t i = 0; i < n; ++i)
+    img[row[i] * ORC_IMG_COLS + col[i]] = static_cast<uint8_t>(static_cast<int>(xyzi[4 * i + 3]));
+  return 0;
+}
+
 int orc_detect(const orc_view* v, const orc_detect_params* d, const orc_ground_params* g, int mode,
                orc_cluster* clusters, uint32_t cap, uint32_t* n_clusters, orc_counters* ctr,
                orc_timing* tm) {

@@ -119,6 +119,28 @@ int orc_detect(const orc_view* v, const orc_detect_params* d, const orc_ground_p
 /* A.7  host post-processing: radial extension (src/cone_detection.cpp:276-278) */
 void orc_extend(float* x, float* y, double extension_length);
 
+/* ---- colour path inputs (first two stages) -------------------------------
+ * PINNED: scripts/color_classifier_server.py is plain numpy/scipy, so the reference's own
+ * to_image runs in the build container; tests/golden/cone_images.npz holds its output on
+ * the 577 real cone crops (tests/golden/make_golden.py) and orc_to_image is checked
+ * against it byte for byte. */
+
+/* src/cone_detection.cpp:222-238  get_reconstructed_cone: points of the raw cloud inside the
+ * axis-aligned box |x-cx|,|y-cy| <= CONE_WIDTH/1.5 (double arithmetic, both ends inclusive),
+ * in cloud order.  out: n matches written as orc_point (pad 1.0f), capacity cap; returns the
+ * number of matches (may exceed cap; only cap are written). */
+uint32_t orc_reconstruct_cone(const orc_point* cloud, uint32_t n, float cx, float cy, float cone_width,
+                              orc_point* out, uint32_t cap);
+
+enum { ORC_IMG_ROWS = 15, ORC_IMG_COLS = 12 };
+enum { ORC_CONE_EMPTY = 1, ORC_CONE_BAD_INDEX = 2, ORC_CONE_BAD_INTENSITY = 4 };
+/* scripts/color_classifier_server.py:130-156  ColorClassifier.to_image on one cone cloud
+ * (x,y,z,intensity float32 widened to double, as pc2.read_points hands them over).
+ * img: 15x12 bytes, row-major.  Returns a flag word: EMPTY = the handler skips the cone
+ * (:83-84); BAD_INDEX = numpy would raise IndexError (row outside [-15,14]); BAD_INTENSITY =
+ * interp1d would raise (value outside [0,255] or NaN).  img is all zero when a flag is set. */
+uint32_t orc_to_image(const float* xyzi /* n x 4 */, uint32_t n, uint8_t* img);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,10 @@ def lib() -> C.CDLL:
                                  C.POINTER(u32), C.POINTER(Counters), C.POINTER(Timing)]
         L.orc_extend.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_double]
         L.orc_extend.restype = None
+        L.orc_reconstruct_cone.argtypes = [vp, u32, C.c_float, C.c_float, C.c_float, vp, u32]
+        L.orc_reconstruct_cone.restype = u32
+        L.orc_to_image.argtypes = [vp, u32, vp]
+        L.orc_to_image.restype = u32
         _lib = L
     return _lib
 
@@ -229,3 +233,22 @@ def extend(x: float, y: float, length: float):
     cx, cy = C.c_float(x), C.c_float(y)
     lib().orc_extend(C.byref(cx), C.byref(cy), length)
     return cx.value, cy.value
+
+
+IMG_ROWS, IMG_COLS = 15, 12
+CONE_EMPTY, CONE_BAD_INDEX, CONE_BAD_INTENSITY = 1, 2, 4
+
+
+def reconstruct_cone(pts: np.ndarray, cx: float, cy: float, cone_width: float = 0.228) -> np.ndarray:
+    """get_reconstructed_cone (src/cone_detection.cpp:222-238) on PointXYZI records; returns the crop."""
+    out = np.zeros(max(len(pts), 1), dtype=POINT_DTYPE)
+    m = lib().orc_reconstruct_cone(pts.ctypes.data, len(pts), cx, cy, cone_width, out.ctypes.data, len(out))
+    return out[:m].copy()
+
+
+def to_image(xyzi: np.ndarray):
+    """ColorClassifier.to_image (scripts/color_classifier_server.py:130-156); returns (image[15,12] u8, flags)."""
+    a = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+    img = np.zeros((IMG_ROWS, IMG_COLS), np.uint8)
+    flags = lib().orc_to_image(a.ctypes.data, len(a), img.ctypes.data)
+    return img, int(flags)

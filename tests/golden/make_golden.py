@@ -6,6 +6,10 @@
   (/root/reference/cones_clouds/cones.pkl, written by the data-collection branch of
   scripts/color_classifier_server.py:95-104).  Imported here because /root/reference does
   not exist on the GPU box.  Only x, y, z, intensity and the per-cone lengths are kept.
+* cone_images.npz — PINNED golden: the reference's own ColorClassifier.to_image
+  (/root/reference/scripts/color_classifier_server.py:130-156, plain numpy/scipy, executed
+  here from its source) on the 577 real crops and on seeded synthetic crops, including the
+  inputs on which it raises (IndexError / interp1d ValueError -> flag, zero image).
 * cfg*_golden.npz — outputs of the CPU oracle (canonical mode) on seeded synthetic scans.
   The reference has no golden vectors of its own ("parity unpinned"); these pin OUR oracle
   against regressions and give the GPU tests a second, committed target.
@@ -43,6 +47,83 @@ def cone_crops():
     print("cone_crops:", len(lens), "cones,", len(pts), "points")
 
 
+def reference_to_image():
+    """The reference's to_image, compiled from its own source (the module itself imports rospy and
+    tensorflow, which are not installed, so only the constants and the function body are taken)."""
+    import ast
+    from scipy.interpolate import interp1d
+    tree = ast.parse(open("/root/reference/scripts/color_classifier_server.py").read())
+    keep = []
+    for node in tree.body:
+        if isinstance(node, ast.Assign):
+            keep.append(node)
+        if isinstance(node, ast.ClassDef):
+            for m in node.body:
+                if isinstance(m, ast.FunctionDef) and m.name == "to_image":
+                    m.decorator_list = []
+                    keep.append(m)
+    ns = {"np": np, "interp1d": interp1d}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "color_classifier_server.py", "exec"), ns)
+    return ns["to_image"]
+
+
+def synthetic_crops(seed=0, n_crops=256):
+    """Seeded cone-sized crops: box +-0.152 m around a centre 1.2..20 m away, any azimuth; a few
+    degenerate ones (single point, repeated point, intensity / elevation outside the image)."""
+    rng = np.random.default_rng(seed)
+    crops = []
+    for i in range(n_crops):
+        r, az = rng.uniform(1.2, 20.0), rng.uniform(-np.pi, np.pi)
+        cx, cy = r * np.cos(az), r * np.sin(az)
+        n = int(rng.integers(1, 120))
+        x = cx + rng.uniform(-0.152, 0.152, n)
+        y = cy + rng.uniform(-0.152, 0.152, n)
+        z = rng.uniform(-0.3, 0.3, n) if r > 2 else rng.uniform(-0.25, 0.25, n)
+        it = rng.uniform(0, 255, n)
+        kind = i % 16
+        if kind == 11:
+            n = 1
+        elif kind == 12:
+            x[:] = x[0]; y[:] = y[0]                     # one azimuth: zero horizontal range
+        elif kind == 13:
+            it[rng.integers(0, n)] = 255.5               # interp1d raises
+        elif kind == 14:
+            z[rng.integers(0, n)] = 0.9 * r              # elevation > 15 deg: IndexError
+        elif kind == 15:
+            z[rng.integers(0, n)] = -0.5 * r             # elevation < -15 deg: rows 0..14 still valid
+        crops.append(np.stack([x, y, z, it], 1)[:n].astype(np.float32))
+    return crops
+
+
+def cone_images():
+    to_image = reference_to_image()
+    z = np.load(os.path.join(HERE, "cone_crops.npz"))
+    off = np.concatenate([[0], np.cumsum(z["lengths"])])
+    real = [z["points"][off[i]:off[i + 1]] for i in range(len(z["lengths"]))]
+    synth = synthetic_crops()
+
+    def run(crops):
+        imgs, raised = np.zeros((len(crops), 15, 12), np.uint8), np.zeros(len(crops), np.uint8)
+        for i, c in enumerate(crops):
+            q = c.astype(np.float64)  # pc2.read_points yields Python floats
+            row = {"x": list(q[:, 0]), "y": list(q[:, 1]), "z": list(q[:, 2]), "intensity": list(q[:, 3])}
+            try:
+                imgs[i] = to_image(row)[:, :, 0]
+            except IndexError:
+                raised[i] = 2
+            except ValueError:
+                raised[i] = 4
+        return imgs, raised
+
+    real_img, real_raised = run(real)
+    syn_img, syn_raised = run(synth)
+    np.savez_compressed(os.path.join(HERE, "cone_images.npz"), real_images=real_img, real_raised=real_raised,
+                        synth_points=np.concatenate(synth), synth_lengths=np.array([len(c) for c in synth], np.int32),
+                        synth_images=syn_img, synth_raised=syn_raised)
+    print("cone_images:", len(real), "real (raised:", int((real_raised > 0).sum()), "),", len(synth),
+          "synthetic (raised:", int((syn_raised > 0).sum()), ")")
+
+
 def synthetic(idx, seed):
     cfg = scans.config(idx)
     frame = scans.generate_config5(1, seed)[0] if idx == 5 else scans.generate(cfg, 1, seed)[0]
@@ -57,5 +138,6 @@ def synthetic(idx, seed):
 
 if __name__ == "__main__":
     cone_crops()
+    cone_images()
     for idx, seed in ((1, 0), (2, 0), (2, 7), (4, 0), (5, 0)):
         synthetic(idx, seed)

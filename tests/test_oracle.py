@@ -348,3 +348,69 @@ def test_voxel_grid_matches_numpy_restatement():
     np.add.at(mean, inverse, xyz.astype(np.float64))
     mean /= counts[:, None]
     assert np.abs(vox_xyzi(st["vox"])[:, :3] - mean).max() < 2e-6
+
+
+# ---- colour path inputs: PINNED against the reference's own numpy code --------
+
+def _golden_images():
+    z = np.load(os.path.join(GOLD, "cone_images.npz"))
+    crops = np.load(os.path.join(GOLD, "cone_crops.npz"))
+    off = np.concatenate([[0], np.cumsum(crops["lengths"])])
+    real = [crops["points"][off[i]:off[i + 1]] for i in range(len(crops["lengths"]))]
+    soff = np.concatenate([[0], np.cumsum(z["synth_lengths"])])
+    synth = [z["synth_points"][soff[i]:soff[i + 1]] for i in range(len(z["synth_lengths"]))]
+    return z, real, synth
+
+
+def test_to_image_matches_reference_golden():
+    """cone_images.npz was produced by the reference's ColorClassifier.to_image itself
+    (tests/golden/make_golden.py::cone_images); the restatement must agree byte for byte."""
+    z, real, synth = _golden_images()
+    for i, c in enumerate(real):
+        img, fl = O.to_image(c)
+        assert fl == 0 and np.array_equal(img, z["real_images"][i]), i
+    n_raised = 0
+    for i, c in enumerate(synth):
+        img, fl = O.to_image(c)
+        raised = int(z["synth_raised"][i])
+        if raised:  # numpy IndexError (2) / interp1d ValueError (4): flagged, image cleared
+            assert fl & raised and not img.any(), (i, fl, raised)
+            n_raised += 1
+        else:
+            assert fl == 0 and np.array_equal(img, z["synth_images"][i]), i
+    assert n_raised >= 16
+    # repeated pixels are common in the real crops, so "the last point wins" is exercised
+    assert sum(len(c) for c in real) > 1.5 * int(np.count_nonzero(z["real_images"]))
+
+
+def test_to_image_empty_and_quirks():
+    img, fl = O.to_image(np.zeros((0, 4), np.float32))
+    assert fl == O.CONE_EMPTY and not img.any()
+    # slope_vert is negative: elevation +1 deg -> round(-0.5 * 16) = -8 -> numpy wraps to row 7
+    p = np.array([[10.0, 0.0, 10.0 * np.tan(np.radians(1.0)), 42.9]], np.float32)
+    img, fl = O.to_image(p)
+    assert fl == 0 and img[7, 0] == 42 and np.count_nonzero(img) == 1
+    # elevation -15 deg and +15 deg both land on row 0 (index 0 and index -15)
+    for elev in (-14.999, 14.999):
+        p = np.array([[10.0, 0.0, 10.0 * np.tan(np.radians(elev)), 7.0]], np.float32)
+        img, fl = O.to_image(p)
+        assert fl == 0 and img[0, 0] == 7
+
+
+def test_reconstruct_cone_box_is_inclusive_in_double():
+    cw = np.float32(0.228)
+    hw = float(cw) / 1.5
+    cx, cy = np.float32(3.25), np.float32(-1.5)
+    hi = np.float32(float(cx) + hw)
+    if float(hi) > float(cx) + hw:
+        hi = np.nextafter(hi, np.float32(-np.inf))
+    above = np.nextafter(hi, np.float32(np.inf))
+    lo = np.float32(float(cx) - hw)
+    if float(lo) < float(cx) - hw:
+        lo = np.nextafter(lo, np.float32(np.inf))
+    below = np.nextafter(lo, np.float32(-np.inf))
+    xs = np.array([hi, above, lo, below, cx, np.nan], np.float32)
+    pts = O.points32(np.stack([xs, np.full(6, cy), np.arange(6), np.arange(6) * 10], 1).astype(np.float32))
+    crop = O.reconstruct_cone(pts, float(cx), float(cy), float(cw))
+    assert list(crop["z"]) == [0.0, 2.0, 4.0]           # cloud order kept; NaN and the outer neighbours dropped
+    assert list(crop["intensity"]) == [0.0, 20.0, 40.0] and np.all(crop["pad"] == 1.0)
