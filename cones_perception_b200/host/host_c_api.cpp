@@ -1,6 +1,7 @@
 // host_c_api.cpp — a small C surface over the C++ host classes (nodes.hpp) so that pytest can
 // drive them through ctypes.  Not part of the drop-in boundary (that is include/conesgpu.h).
 #include <cstdio>
+#include <map>
 #include <string>
 
 #include "nodes.hpp"
@@ -71,6 +72,67 @@ int ch_tracker_update(void* tp, const float* xy, uint32_t n, int forced_color, f
 }
 
 // ---- ConeDetector / GroundRemover (GPU) -----------------------------------------------------
+}  // extern "C"
+namespace {
+// A deterministic stand-in for the color_classifier service, so the three colour-input modes can be
+// compared: colour = 1 + fnv1a(bytes) % 3; empty crops are skipped like the service does
+// (scripts/color_classifier_server.py:83-84), which shortens the answer.
+uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+  const uint8_t* b = static_cast<const uint8_t*>(data);
+  for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+struct ColorProbe {
+  uint64_t n_inputs = 0, n_points = 0, digest = 1469598103934665603ull;
+};
+std::vector<Color> probe_crops(ColorProbe* pr, const std::vector<std::vector<Point>>& crops) {
+  std::vector<Color> out;
+  for (const auto& c : crops) {
+    pr->n_inputs++;
+    if (c.empty()) continue;
+    uint64_t h = 1469598103934665603ull;
+    for (const Point& p : c) {
+      const float v[4] = {p.x, p.y, p.z, p.intensity};
+      h = fnv1a(v, sizeof(v), h);
+    }
+    pr->n_points += c.size();
+    pr->digest = fnv1a(&h, sizeof(h), pr->digest);
+    out.push_back(static_cast<Color>(1 + h % 3));
+  }
+  return out;
+}
+std::vector<Color> probe_images(ColorProbe* pr, const std::vector<uint8_t>& images, const std::vector<uint32_t>& flags) {
+  std::vector<Color> out;
+  for (size_t i = 0; i < flags.size(); ++i) {
+    pr->n_inputs++;
+    if (flags[i] & CP_CONE_EMPTY) continue;
+    const uint64_t h = fnv1a(images.data() + i * 180, 180);
+    pr->digest = fnv1a(&h, sizeof(h), pr->digest);
+    out.push_back(static_cast<Color>(1 + h % 3));
+  }
+  return out;
+}
+std::map<void*, ColorProbe> g_probes;
+}  // namespace
+extern "C" {
+
+// mode: ConeDetector::ColorInputs (0 host crops, 1 GPU crops, 2 GPU crops + range images)
+void ch_detector_set_color_inputs(void* dp, int mode) {
+  auto* det = static_cast<ConeDetector*>(dp);
+  det->color_inputs = static_cast<ConeDetector::ColorInputs>(mode);
+  ColorProbe* pr = &g_probes[dp];
+  det->get_colors = [pr](const std::vector<std::vector<Point>>& crops) { return probe_crops(pr, crops); };
+  det->get_colors_from_images = [pr](const std::vector<uint8_t>& im, const std::vector<uint32_t>& fl) {
+    return probe_images(pr, im, fl);
+  };
+}
+void ch_detector_color_probe(void* dp, uint64_t* n_inputs, uint64_t* n_points, uint64_t* digest) {
+  const ColorProbe& pr = g_probes[dp];
+  *n_inputs = pr.n_inputs;
+  *n_points = pr.n_points;
+  *digest = pr.digest;
+}
+
 void* ch_detector_create(uint64_t max_points, int device, const cp_detect_params* d, int classify_colors,
                          int use_points_buffer, int fused_ground) {
   try {
@@ -93,7 +155,10 @@ void* ch_detector_create(uint64_t max_points, int device, const cp_detect_params
     return nullptr;
   }
 }
-void ch_detector_destroy(void* d) { delete static_cast<ConeDetector*>(d); }
+void ch_detector_destroy(void* d) {
+  g_probes.erase(d);
+  delete static_cast<ConeDetector*>(d);
+}
 
 // one callback: compact xyzi cloud in, the four published clouds out (x, y per cone) plus the
 // layout facts of the published messages

@@ -98,6 +98,12 @@ class ConeTracker {
   // stands for the color_classifier ROS service (src/cone_detection.cpp:342-363): receives the
   // reconstructed raw-point crops (:222-238), returns one Color per crop
   std::function<std::vector<Color>(const std::vector<std::vector<Point>>&)> get_colors;
+  // optional: all crops of a frame at once (the GPU box gather, cp_cone_crops).  A crop depends only on
+  // its centre and the raw cloud, so gathering them after the loop equals the per-cone calls at :309.
+  std::function<std::vector<std::vector<Point>>(const std::vector<Point>&)> reconstruct_cones;
+  // optional: classify straight from the centres (the GPU crops + range images, cp_cone_images);
+  // replaces reconstruct + get_colors when set
+  std::function<std::vector<Color>(const std::vector<Point>&)> classify_centers;
 
   // centroids: cluster means (x, y) in the order the detector emitted them.
   // whole_cloud: the raw input cloud (only read when classify_colors, :309).
@@ -136,11 +142,7 @@ class ConeTracker {
                   if (!need_color) break;
                 }
               }
-              if (need_color) {  // :308-312
-                cones_clouds_for_color_classification.push_back(
-                    whole_cloud ? get_reconstructed_cone(p, *whole_cloud) : std::vector<Point>());
-                centroid_cloud_for_color_classification.push_back(p);
-              }
+              if (need_color) centroid_cloud_for_color_classification.push_back(p);  // :308-312, crops below
             } else {
               centroid_clouds[kUnknownColor].push_back(p);  // :315
             }
@@ -150,11 +152,24 @@ class ConeTracker {
       }
     }
     if (classify_colors) {  // :326-333
-      std::vector<Color> colors(cones_clouds_for_color_classification.size(), kUnknownColor);
-      if (get_colors && !colors.empty()) {
-        std::vector<Color> got = get_colors(cones_clouds_for_color_classification);
-        for (size_t i = 0; i < got.size() && i < colors.size(); ++i) colors[i] = got[i];
+      const std::vector<Point>& need = centroid_cloud_for_color_classification;
+      std::vector<Color> colors(need.size(), kUnknownColor);
+      std::vector<Color> got;
+      if (classify_centers && !need.empty()) {
+        got = classify_centers(need);
+      } else if (!need.empty()) {
+        if (reconstruct_cones) {
+          cones_clouds_for_color_classification = reconstruct_cones(need);
+        } else {
+          for (const Point& p : need)  // :309
+            cones_clouds_for_color_classification.push_back(
+                whole_cloud ? get_reconstructed_cone(p, *whole_cloud) : std::vector<Point>());
+        }
+        if (get_colors) got = get_colors(cones_clouds_for_color_classification);
       }
+      // :352-353 std::transform over the response: a service that answers fewer colours than crops
+      // (it skips empty crops) fills the front of the vector only
+      for (size_t i = 0; i < got.size() && i < colors.size(); ++i) colors[i] = got[i];
       for (size_t i = 0; i < colors.size(); i++) centroid_clouds[colors[i]].push_back(centroid_cloud_for_color_classification[i]);
     }
     for (int i = 0; i < kNumberOfColors; i++)  // :335-337
@@ -218,6 +233,15 @@ class ConeDetector {
   int num_of_sectors = 16;
   float default_lowest_point = -0.1f;
   std::function<std::vector<Color>(const std::vector<std::vector<Point>>&)> get_colors;
+  // not in the reference: where the colour-path inputs are produced.
+  //   kHostCrops  the reference's host loop over the whole cloud per cone (:222-238)
+  //   kGpuCrops   cp_cone_crops on the cloud the detection call already staged; get_colors sees the same crops
+  //   kGpuImages  cp_cone_images: crops and ColorClassifier.to_image both on the device; the classifier
+  //               hook get_colors_from_images receives 15x12 uint8 images + CP_CONE_* flags (180 B per cone)
+  enum ColorInputs { kHostCrops = 0, kGpuCrops = 1, kGpuImages = 2 };
+  ColorInputs color_inputs = kGpuCrops;
+  std::function<std::vector<Color>(const std::vector<uint8_t>& images, const std::vector<uint32_t>& flags)>
+      get_colors_from_images;
 
   explicit ConeDetector(uint64_t max_points = 4u << 20, int device = 0, uint32_t max_point_step = 64) {
     cp_config cfg{};
@@ -261,9 +285,18 @@ class ConeDetector {
     tracker_.cones_matching_dist_theshold = cones_matching_dist_theshold;
     tracker_.cone_position_extension_length = cone_position_extension_length;
     tracker_.get_colors = get_colors;
+    tracker_.reconstruct_cones = nullptr;
+    tracker_.classify_centers = nullptr;
     std::vector<Point> whole;
-    if (classify_colors) whole = from_msg(cloud_msg, in);  // :158 copyPointCloud, colour path only
-    std::vector<std::vector<Point>> clouds = tracker_.update(centroids, classify_colors ? &whole : nullptr);
+    if (classify_colors && color_inputs == kHostCrops) {
+      whole = from_msg(cloud_msg, in);  // :158 copyPointCloud, colour path only
+    } else if (classify_colors && color_inputs == kGpuCrops) {
+      tracker_.reconstruct_cones = [this](const std::vector<Point>& need) { return gpu_crops(need); };
+    } else if (classify_colors) {
+      tracker_.classify_centers = [this](const std::vector<Point>& need) { return gpu_classify(need); };
+    }
+    std::vector<std::vector<Point>> clouds =
+        tracker_.update(centroids, classify_colors && color_inputs == kHostCrops ? &whole : nullptr);
     std::vector<PointCloud2> out(kNumberOfColors);
     for (int i = 0; i < kNumberOfColors; i++) {  // :177-186
       out[i] = to_msg(clouds[i]);
@@ -289,8 +322,48 @@ class ConeDetector {
       }
     return out;
   }
+  static std::vector<cp_cone_center> centers_of(const std::vector<Point>& need) {
+    std::vector<cp_cone_center> c(need.size());
+    for (size_t i = 0; i < need.size(); ++i) c[i] = {need[i].x, need[i].y};
+    return c;
+  }
+  // get_reconstructed_cone for every cone that needs a colour, on the cloud cp_detect left on the device
+  std::vector<std::vector<Point>> gpu_crops(const std::vector<Point>& need) {
+    const std::vector<cp_cone_center> c = centers_of(need);
+    std::vector<uint32_t> off(c.size() + 1);
+    cp_status st = cp_cone_crops(gpu_, nullptr, 0, c.data(), static_cast<uint32_t>(c.size()), CONE_WIDTH, off.data(),
+                                 crop_buf_.data(), static_cast<uint32_t>(crop_buf_.size() / 4));
+    if (st == CP_E_CAPACITY) {  // offsets are complete: size the buffer and fetch again
+      crop_buf_.resize(static_cast<size_t>(off.back()) * 4);
+      st = cp_cone_crops(gpu_, nullptr, 0, c.data(), static_cast<uint32_t>(c.size()), CONE_WIDTH, off.data(),
+                         crop_buf_.data(), static_cast<uint32_t>(crop_buf_.size() / 4));
+    }
+    if (st != CP_OK) throw GpuError(st, cp_last_error(gpu_));
+    std::vector<std::vector<Point>> crops(c.size());
+    for (size_t k = 0; k < c.size(); ++k) {
+      crops[k].resize(off[k + 1] - off[k]);
+      for (uint32_t i = off[k]; i < off[k + 1]; ++i) {
+        Point& p = crops[k][i - off[k]];  // `Point p;` then four fields (:224-233)
+        p.x = crop_buf_[4 * i];
+        p.y = crop_buf_[4 * i + 1];
+        p.z = crop_buf_[4 * i + 2];
+        p.intensity = crop_buf_[4 * i + 3];
+      }
+    }
+    return crops;
+  }
+  std::vector<Color> gpu_classify(const std::vector<Point>& need) {
+    const std::vector<cp_cone_center> c = centers_of(need);
+    std::vector<uint8_t> images(c.size() * CP_CONE_IMG_ROWS * CP_CONE_IMG_COLS);
+    std::vector<uint32_t> flags(c.size());
+    cp_status st = cp_cone_images(gpu_, nullptr, 0, c.data(), static_cast<uint32_t>(c.size()), CONE_WIDTH,
+                                  images.data(), nullptr, flags.data());
+    if (st != CP_OK) throw GpuError(st, cp_last_error(gpu_));
+    return get_colors_from_images ? get_colors_from_images(images, flags) : std::vector<Color>();
+  }
   cp_handle* gpu_ = nullptr;
   bool intensity_in_cloud_checked_ = false, intensity_in_cloud_ = true;
+  std::vector<float> crop_buf_ = std::vector<float>(4 * 16384);
   std::vector<cp_cluster> clusters_;
   cp_frame_counters counters_{};
   ConeTracker tracker_;

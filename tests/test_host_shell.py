@@ -28,6 +28,10 @@ def host():
     lib.ch_detector_destroy.argtypes = [C.c_void_p]
     lib.ch_detector_handle.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ch_detector_set_color_inputs.argtypes = [C.c_void_p, C.c_int]
+    lib.ch_detector_set_color_inputs.restype = None
+    lib.ch_detector_color_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ch_detector_color_probe.restype = None
     lib.ch_ground_create.restype = C.c_void_p
     lib.ch_ground_create.argtypes = [C.c_uint64, C.c_int]
     lib.ch_ground_destroy.argtypes = [C.c_void_p]
@@ -106,6 +110,87 @@ def test_cone_detector_cloud_handler_sequence(host, fused_ground, with_intensity
         assert nsec.value == 123456789                                         # header copied verbatim
     assert published > 0
     host.ch_detector_destroy(det)
+
+
+FNV0, FNVP, M64 = 1469598103934665603, 1099511628211, (1 << 64) - 1
+
+
+def fnv1a(data: bytes, h: int = FNV0) -> int:
+    for b in data:
+        h = ((h ^ b) * FNVP) & M64
+    return h
+
+
+@pytest.mark.gpu
+def test_cone_detector_colour_inputs_three_ways(host):
+    """classify_colors:=true.  The colour-path inputs produced (0) by the reference's host loop, (1) by
+    cp_cone_crops and (2) by cp_cone_images must drive the tracker identically; a deterministic stand-in
+    for the classifier service (colour from a hash of its input, empty crops skipped) makes any differing
+    crop or image change the published clouds."""
+    cfg = scans.config(1)
+    frames = scans.generate(cfg, 4, base_seed=40)
+    frames[2] = frames[2].copy()
+    d = cfg.detect
+    cd = to_c_detect(d)
+    raw = {}
+
+    def crops_of(need):
+        return [O.reconstruct_cone(raw["pts"], float(p[0]), float(p[1]), 0.228) for p in need]
+
+    def colours_from_crops(need):
+        out = []
+        for c in crops_of(need):
+            if len(c) == 0:
+                continue
+            h = fnv1a(np.stack([c["x"], c["y"], c["z"], c["intensity"]], 1).astype(np.float32).tobytes())
+            raw["digest"] = fnv1a(h.to_bytes(8, "little"), raw["digest"])
+            out.append(1 + h % 3)
+        return out
+
+    def colours_from_images(need):
+        out = []
+        for c in crops_of(need):
+            img, fl = O.to_image(np.stack([c["x"], c["y"], c["z"], c["intensity"]], 1).astype(np.float32))
+            if fl & O.CONE_EMPTY:
+                continue
+            h = fnv1a(img.tobytes())
+            raw["digest"] = fnv1a(h.to_bytes(8, "little"), raw["digest"])
+            out.append(1 + h % 3)
+        return out
+
+    results = []
+    for mode in (0, 1, 2):
+        det = host.ch_detector_create(cfg.points_per_frame, 0, C.byref(cd), 1, 1, 0)
+        assert det, host.ch_last_error()
+        host.ch_detector_set_color_inputs(det, mode)
+        raw["digest"] = FNV0
+        ref = TrackerReference(True, True, d.cones_matching_dist_theshold, d.cone_position_extension_length,
+                               color_fn=colours_from_images if mode == 2 else colours_from_crops)
+        seq = []
+        for f in frames:
+            out = np.zeros((4, CAP, 2), np.float32)
+            counts = np.zeros(4, np.uint32)
+            step, nf, nsec = C.c_uint32(), C.c_uint32(), C.c_uint32()
+            rc = host.ch_detector_handle(det, f.ctypes.data, len(f), 1, out.ctypes.data, counts.ctypes.data, CAP,
+                                         C.byref(step), C.byref(nf), C.byref(nsec))
+            assert rc == 0, host.ch_last_error()
+            raw["pts"] = O.from_msg(O.view_of_xyzi(f))
+            cl, _, _ = O.detect(O.view_of_xyzi(f), d, None, O.CANONICAL)
+            exp = as_arrays(ref.update([(c["x"], c["y"]) for c in cl]))
+            for k in range(4):
+                assert counts[k] == len(exp[k]), (mode, k)
+                assert np.array_equal(out[k, :counts[k]].view(np.uint32), exp[k].view(np.uint32))
+            seq.append([out[k, :counts[k]].copy() for k in range(4)])
+        n_in, n_pts, dig = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        host.ch_detector_color_probe(det, C.byref(n_in), C.byref(n_pts), C.byref(dig))
+        assert dig.value == raw["digest"] and n_in.value > 5           # the service saw exactly these inputs
+        results.append((seq, n_in.value, n_pts.value, dig.value))
+        host.ch_detector_destroy(det)
+    # host crops and GPU crops: identical service inputs, identical published clouds
+    assert results[0][1:] == results[1][1:] and results[0][2] > 30
+    for a, b in zip(results[0][0], results[1][0]):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert sum(len(c) for fr in results[2][0] for c in fr[1:]) > 0      # colours were assigned from images
 
 
 @pytest.mark.gpu

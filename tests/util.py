@@ -152,9 +152,13 @@ class TrackerReference:
     """src/cone_detection.cpp:276-340 (radial extension, temporal gate / points buffer, colour
     routing) on numpy float32 scalars with the reference's float/double promotion rules."""
 
-    def __init__(self, classify_colors=False, use_points_buffer=False, match=0.5, ext=0.05, forced_color=0):
+    def __init__(self, classify_colors=False, use_points_buffer=False, match=0.5, ext=0.05, forced_color=0,
+                 color_fn=None):
         self.classify_colors, self.use_points_buffer = classify_colors, use_points_buffer
         self.match, self.ext, self.forced_color = match, ext, forced_color
+        # color_fn(centres) -> colours, possibly FEWER than centres (the service skips empty crops,
+        # scripts/color_classifier_server.py:83-84); std::transform then fills the front only (:352-353)
+        self.color_fn = color_fn
         self.prev = None                      # prev_detected_cones (NULL before the first frame)
         self.prev_col = [None] * 4            # prev_centroid_clouds
 
@@ -193,9 +197,13 @@ class TrackerReference:
                         else:
                             clouds[0].append(p)                                        # :315
                         break                                                          # :317
-        if self.classify_colors:
-            for p in need:                                                             # :326-333
-                clouds[self.forced_color].append(p)
+        if self.classify_colors:                                                       # :326-333
+            colors = [self.forced_color if self.color_fn is None else 0] * len(need)
+            if self.color_fn is not None and need:
+                got = self.color_fn(need)
+                colors[:len(got)] = got[:len(need)]
+            for p, c in zip(need, colors):
+                clouds[c].append(p)
         self.prev_col = [list(c) for c in clouds]                                      # :335-337
         self.prev = current                                                            # :339
         return clouds
