@@ -39,36 +39,34 @@ template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads) cone_box_mask_kernel(
     const uint8_t* __restrict__ in, Layout L, u64 first_point, u32 n_points, const __grid_constant__ ConeBoxes B,
     u32 n_rows, u32 n_tiles, u32* __restrict__ mask, u32* __restrict__ tile_count) {
+  // one 32-point row per warp (a single frame is small: many short CTAs beat 64 long ones)
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const u32 tile = blockIdx.x;
-#pragma unroll 2
-  for (int r = 0; r < kStreamRows; ++r) {
-    const u32 row = tile * kTileWords + warp * kStreamRows + r;
-    const u32 idx = row * 32 + lane;
-    if (row >= n_rows) break;
-    const bool valid = idx < n_points;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) p = load_point<MODE>(in, first_point + idx, L);
-    u32 m0 = 0, m1 = 0;
-    for (u32 k = 0; k < B.n; ++k) {
-      // NaN coordinates fail every comparison, like the reference's double comparisons
-      const bool inside = valid && p.x >= B.xlo[k] && p.x <= B.xhi[k] && p.y >= B.ylo[k] && p.y <= B.yhi[k];
-      if (k < 32) m0 |= (u32)inside << k;
-      else m1 |= (u32)inside << (k - 32);
+  const u32 row = blockIdx.x * kStreamWarps + warp;
+  if (row >= n_rows) return;
+  const u32 tile = row / kTileWords;
+  const u32 idx = row * 32 + lane;
+  const bool valid = idx < n_points;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) p = load_point<MODE>(in, first_point + idx, L);
+  u32 m0 = 0, m1 = 0;
+  for (u32 k = 0; k < B.n; ++k) {
+    // NaN coordinates fail every comparison, like the reference's double comparisons
+    const bool inside = valid && p.x >= B.xlo[k] && p.x <= B.xhi[k] && p.y >= B.ylo[k] && p.y <= B.yhi[k];
+    if (k < 32) m0 |= (u32)inside << k;
+    else m1 |= (u32)inside << (k - 32);
+  }
+  u32 any0 = __reduce_or_sync(0xFFFFFFFFu, m0), any1 = __reduce_or_sync(0xFFFFFFFFu, m1);
+  while (any0 | any1) {
+    const bool hi = any0 == 0;
+    const u32 bit = hi ? __ffs(any1) - 1 : __ffs(any0) - 1;
+    const u32 b = __ballot_sync(0xFFFFFFFFu, ((hi ? m1 : m0) >> bit) & 1u);
+    const u32 k = bit + (hi ? 32u : 0u);
+    if (lane == 0) {
+      mask[(size_t)k * n_rows + row] = b;
+      atomicAdd(&tile_count[(size_t)k * n_tiles + tile], (u32)__popc(b));
     }
-    u32 any0 = __reduce_or_sync(0xFFFFFFFFu, m0), any1 = __reduce_or_sync(0xFFFFFFFFu, m1);
-    while (any0 | any1) {
-      const bool hi = any0 == 0;
-      const u32 bit = hi ? __ffs(any1) - 1 : __ffs(any0) - 1;
-      const u32 b = __ballot_sync(0xFFFFFFFFu, ((hi ? m1 : m0) >> bit) & 1u);
-      const u32 k = bit + (hi ? 32u : 0u);
-      if (lane == 0) {
-        mask[(size_t)k * n_rows + row] = b;
-        atomicAdd(&tile_count[(size_t)k * n_tiles + tile], (u32)__popc(b));
-      }
-      if (hi) any1 &= any1 - 1;
-      else any0 &= any0 - 1;
-    }
+    if (hi) any1 &= any1 - 1;
+    else any0 &= any0 - 1;
   }
 }
 

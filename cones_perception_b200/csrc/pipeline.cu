@@ -112,6 +112,8 @@ struct cp_handle {
     float4* pts = nullptr;
     uint8_t* img = nullptr;
     size_t mask_n = 0, tile_n = 0, texcl_n = 0, off_n = 0, flags_n = 0, pts_n = 0, img_n = 0;
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
   } color;
   const uint8_t* in_ptr = nullptr;  // current batch input (d_in or caller memory)
   Layout layout{};
@@ -1113,6 +1115,7 @@ cp_status device_errors(cp_handle* h) {
 
 // ======================================================================== C ABI
 // ---- colour path inputs (color_kernels.cuh) ----------------------------------------------
+constexpr size_t kColorPrefetch = 16384;  // crop points copied back speculatively with the offsets
 template <typename T>
 cp_status grow(cp_handle* h, T** p, size_t* have, size_t need) {
   if (need <= *have && *p) return CP_OK;
@@ -1191,11 +1194,12 @@ cp_status enqueue_cone_crops(cp_handle* h, const cp_cloud_view* cloud, u32 frame
     }
     CK(cudaMemsetAsync(cb.mask, 0, sizeof(u32) * (size_t)B.n * std::max<u32>(n_rows, 1), h->stream));
     CK(cudaMemsetAsync(cb.tcount, 0, sizeof(u32) * (size_t)B.n * n_tiles, h->stream));
+    const u32 mgrid = (n_rows + kStreamWarps - 1) / kStreamWarps;
     if (n_points) {
       switch (h->layout.mode) {
-        case 0: cone_box_mask_kernel<0><<<n_tiles, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, n_points, B, n_rows, n_tiles, cb.mask, cb.tcount); break;
-        case 1: cone_box_mask_kernel<1><<<n_tiles, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, n_points, B, n_rows, n_tiles, cb.mask, cb.tcount); break;
-        default: cone_box_mask_kernel<2><<<n_tiles, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, n_points, B, n_rows, n_tiles, cb.mask, cb.tcount); break;
+        case 0: cone_box_mask_kernel<0><<<mgrid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, n_points, B, n_rows, n_tiles, cb.mask, cb.tcount); break;
+        case 1: cone_box_mask_kernel<1><<<mgrid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, n_points, B, n_rows, n_tiles, cb.mask, cb.tcount); break;
+        default: cone_box_mask_kernel<2><<<mgrid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, first_point, n_points, B, n_rows, n_tiles, cb.mask, cb.tcount); break;
       }
     }
     cone_box_scan_kernel<<<1, 1024, 0, h->stream>>>(B.n, k0, n_tiles, cb.tcount, cb.texcl, cb.off);
@@ -1422,6 +1426,7 @@ void cp_destroy(cp_handle* h) {
   for (void* q : {(void*)h->color.mask, (void*)h->color.tcount, (void*)h->color.texcl, (void*)h->color.off,
                   (void*)h->color.flags, (void*)h->color.pts, (void*)h->color.img})
     if (q) cudaFree(q);
+  if (h->color.pin) cudaFreeHost(h->color.pin);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -2010,6 +2015,34 @@ cp_status cp_debug_sort(cp_handle* h, uint64_t* keys, uint32_t* vals, uint32_t n
   return CP_OK;
 }
 
+// pinned mirror of the colour-path results: [offsets n+1][flags n][images 180 n][first crop points], so that a
+// call costs one stream synchronisation
+static cp_status color_pin(cp_handle* h, u32 n_centers) {
+  cp_handle::ColorBufs& cb = h->color;
+  const size_t need = sizeof(u32) * (2 * (size_t)n_centers + 2) + (size_t)n_centers * kImgPix + 16 +
+                      sizeof(float4) * kColorPrefetch;
+  if (cb.pin && cb.pin_bytes >= need) return CP_OK;
+  if (cb.pin) {
+    cudaStreamSynchronize(h->stream);
+    cudaFreeHost(cb.pin);
+    cb.pin = nullptr;
+  }
+  if (cudaMallocHost(&cb.pin, need) != cudaSuccess) {
+    cudaGetLastError();
+    h->err = "cudaMallocHost failed (colour path)";
+    return CP_E_NOMEM;
+  }
+  cb.pin_bytes = need;
+  return CP_OK;
+}
+static u32* pin_off(cp_handle* h) { return reinterpret_cast<u32*>(h->color.pin); }
+static u32* pin_flags(cp_handle* h, u32 n) { return pin_off(h) + n + 1; }
+static uint8_t* pin_img(cp_handle* h, u32 n) { return reinterpret_cast<uint8_t*>(pin_flags(h, n) + n); }
+static float4* pin_pts(cp_handle* h, u32 n) {
+  uintptr_t p = reinterpret_cast<uintptr_t>(pin_img(h, n) + (size_t)n * kImgPix);
+  return reinterpret_cast<float4*>((p + 15) & ~(uintptr_t)15);
+}
+
 cp_status cp_cone_crops(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame, const cp_cone_center* centers,
                         uint32_t n_centers, float cone_width, uint32_t* crop_offsets, float* crop_xyzi,
                         uint32_t cap_points) {
@@ -2019,18 +2052,26 @@ cp_status cp_cone_crops(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame
     return CP_E_PARAM;
   }
   CK(cudaSetDevice(h->cfg.device));
-  cp_status st = enqueue_cone_crops(h, cloud, frame, centers, n_centers, cone_width, crop_xyzi ? cap_points : 0);
+  cp_status st = color_pin(h, n_centers);
   if (st) return st;
-  CK(cudaMemcpyAsync(crop_offsets, h->color.off, sizeof(u32) * ((size_t)n_centers + 1), cudaMemcpyDeviceToHost, h->stream));
+  st = enqueue_cone_crops(h, cloud, frame, centers, n_centers, cone_width, crop_xyzi ? cap_points : 0);
+  if (st) return st;
+  CK(cudaMemcpyAsync(pin_off(h), h->color.off, sizeof(u32) * ((size_t)n_centers + 1), cudaMemcpyDeviceToHost, h->stream));
+  // the first crop points ride along speculatively: a typical frame's crops fit, so one synchronisation serves
+  const u32 spec = crop_xyzi ? (u32)std::min<size_t>({(size_t)cap_points, (size_t)kColorPrefetch, h->color.pts_n}) : 0u;
+  if (spec) CK(cudaMemcpyAsync(pin_pts(h, n_centers), h->color.pts, sizeof(float4) * spec, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  memcpy(crop_offsets, pin_off(h), sizeof(u32) * ((size_t)n_centers + 1));
   const u32 total = crop_offsets[n_centers];
   if (crop_xyzi) {
     if (total > cap_points) {
       h->err = "cone crops hold " + std::to_string(total) + " points, more than cap_points";
       return CP_E_CAPACITY;
     }
-    if (total) {
-      CK(cudaMemcpyAsync(crop_xyzi, h->color.pts, sizeof(float4) * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+    memcpy(crop_xyzi, pin_pts(h, n_centers), sizeof(float4) * std::min(total, spec));
+    if (total > spec) {
+      CK(cudaMemcpyAsync(crop_xyzi + 4 * (size_t)spec, h->color.pts + spec, sizeof(float4) * (size_t)(total - spec),
+                         cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
     }
   }
@@ -2045,31 +2086,36 @@ cp_status cp_cone_images(cp_handle* h, const cp_cloud_view* cloud, uint32_t fram
     return CP_E_PARAM;
   }
   CK(cudaSetDevice(h->cfg.device));
-  std::vector<u32> off((size_t)n_centers + 1);
+  cp_status st = color_pin(h, n_centers);
+  if (st) return st;
   size_t want = h->color.pts_n;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    // the cloud is staged by the first attempt only; a retry (crop buffer too small) reuses it
-    cp_status st = enqueue_cone_crops(h, attempt == 0 ? cloud : nullptr, attempt == 0 ? frame : (cloud ? 0 : frame),
-                                      centers, n_centers, cone_width, want);
+    // the cloud is staged by the first attempt only; a retry (crop buffer too small) reuses it.
+    // Crops, raster and the copies go out back to back; the crop total is checked after the one sync.
+    st = enqueue_cone_crops(h, attempt == 0 ? cloud : nullptr, attempt == 0 ? frame : (cloud ? 0 : frame), centers,
+                            n_centers, cone_width, want);
     if (st) return st;
-    CK(cudaMemcpyAsync(off.data(), h->color.off, sizeof(u32) * off.size(), cudaMemcpyDeviceToHost, h->stream));
+    if ((st = enqueue_raster(h, n_centers))) return st;
+    CK(cudaMemcpyAsync(pin_off(h), h->color.off, sizeof(u32) * ((size_t)n_centers + 1), cudaMemcpyDeviceToHost, h->stream));
+    if (n_centers) {
+      CK(cudaMemcpyAsync(pin_flags(h, n_centers), h->color.flags, sizeof(u32) * n_centers, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(pin_img(h, n_centers), h->color.img, (size_t)n_centers * kImgPix, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
-    if (off[n_centers] <= h->color.pts_n) break;
-    if (off[n_centers] == 0xFFFFFFFFu || attempt == 1) {
+    const u32 total = pin_off(h)[n_centers];
+    if (total <= h->color.pts_n) break;
+    if (total == 0xFFFFFFFFu || attempt == 1) {
       h->err = "cone crops exceed the addressable crop buffer";
       return CP_E_CAPACITY;
     }
-    want = off[n_centers];
+    want = total;
   }
-  cp_status st = enqueue_raster(h, n_centers);
-  if (st) return st;
   if (n_centers) {
-    CK(cudaMemcpyAsync(images, h->color.img, (size_t)n_centers * kImgPix, cudaMemcpyDeviceToHost, h->stream));
-    if (flags) CK(cudaMemcpyAsync(flags, h->color.flags, sizeof(u32) * n_centers, cudaMemcpyDeviceToHost, h->stream));
+    memcpy(images, pin_img(h, n_centers), (size_t)n_centers * kImgPix);
+    if (flags) memcpy(flags, pin_flags(h, n_centers), sizeof(u32) * n_centers);
   }
-  CK(cudaStreamSynchronize(h->stream));
   if (counts)
-    for (u32 c = 0; c < n_centers; ++c) counts[c] = off[c + 1] - off[c];
+    for (u32 c = 0; c < n_centers; ++c) counts[c] = pin_off(h)[c + 1] - pin_off(h)[c];
   return CP_OK;
 }
 
