@@ -9,6 +9,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -17,6 +18,7 @@
 #include "cluster_kernels.cuh"
 #include "color_kernels.cuh"
 #include "common.cuh"
+#include "copy_pool.hpp"
 #include "frame_kernels.cuh"
 #include "radix_sort.cuh"
 #include "stream_kernels.cuh"
@@ -148,6 +150,9 @@ struct cp_handle {
   i32* d_tap_labels = nullptr;
   // pinned host mirrors
   uint8_t* h_stage[2] = {nullptr, nullptr};
+  bool stage_streaming = true;  // non-temporal stores into the pinned staging buffer (CONESGPU_STAGE_NT=0: memcpy)
+  int stage_threads = 1;  // threads (caller included) that copy a pageable cloud into the pinned staging buffer
+  std::unique_ptr<CopyPool> copy_pool;
   Ctl* h_ctl = nullptr;
   u32* h_frame_u32 = nullptr;  // scratch for per-frame readback
   std::vector<void*> dev_allocs, pin_allocs;
@@ -1056,6 +1061,48 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   return CP_OK;
 }
 
+// A pageable cloud of a megabyte or more: one core's memcpy into pinned memory (about 10 GB/s) costs more than
+// the DMA and the kernels together.  Helper threads share the copy in 64 KB pieces; the calling thread copies too
+// and issues one DMA per group of pieces as soon as the group is complete, so copies and DMAs overlap.
+constexpr size_t kParallelStageMin = 512ull << 10;
+constexpr size_t kStagePiece = 64ull << 10;
+cp_status stage_parallel(cp_handle* h, const uint8_t* src, size_t total, size_t dst_off, int* ring) {
+  if (!h->copy_pool) h->copy_pool.reset(new CopyPool(h->stage_threads - 1));
+  size_t done = 0;
+  while (done < total) {
+    const size_t chunk = std::min(kStageChunk, total - done);
+    const int r = *ring;
+    CK(cudaEventSynchronize(h->ev_stage[r]));
+    // 4+ DMAs per cloud, each 256 KB .. 2 MB
+    const size_t group_bytes = std::min<size_t>(2ull << 20, std::max<size_t>(256ull << 10, (chunk / 4 + kStagePiece - 1) / kStagePiece * kStagePiece));
+    const u32 ppg = (u32)(group_bytes / kStagePiece);
+    std::shared_ptr<CopyPool::Batch> b = h->copy_pool->start(h->h_stage[r], src + done, chunk, kStagePiece, ppg, h->stage_streaming);
+    u32 issued = 0;
+    cudaError_t err = cudaSuccess;
+    auto issue_ready = [&](bool block) {
+      while (issued < b->n_groups) {
+        if (!b->group_done(issued)) {
+          if (!block) return;
+          std::this_thread::yield();
+          continue;
+        }
+        const size_t off = (size_t)issued * group_bytes;
+        const size_t len = std::min(group_bytes, chunk - off);
+        if (err == cudaSuccess)
+          err = cudaMemcpyAsync(h->d_in + dst_off + done + off, h->h_stage[r] + off, len, cudaMemcpyHostToDevice, h->stream);
+        ++issued;
+      }
+    };
+    while (b->take_one()) issue_ready(false);
+    issue_ready(true);  // every piece is copied when this returns: no helper touches the buffers afterwards
+    CK(err);
+    CK(cudaEventRecord(h->ev_stage[r], h->stream));
+    *ring = r ^ 1;
+    done += chunk;
+  }
+  return CP_OK;
+}
+
 // copy a host cloud into the device input buffer at byte offset `dst_off`
 cp_status stage_view(cp_handle* h, const cp_cloud_view* v, size_t dst_off, int* ring) {
   const u64 n = (u64)v->width * v->height;
@@ -1074,6 +1121,7 @@ cp_status stage_view(cp_handle* h, const cp_cloud_view* v, size_t dst_off, int* 
   }
   // pageable (or row-padded) source: pack through the pinned ring, chunk by chunk
   const size_t total = row_bytes * v->height;
+  if (contiguous && h->stage_threads > 1 && total >= kParallelStageMin) return stage_parallel(h, v->data, total, dst_off, ring);
   size_t done = 0;
   while (done < total) {
     // a cloud is cut into at least 4 pieces so the host memcpy of piece k+1 overlaps the DMA of piece k
@@ -1082,7 +1130,8 @@ cp_status stage_view(cp_handle* h, const cp_cloud_view* v, size_t dst_off, int* 
     const int r = *ring;
     CK(cudaEventSynchronize(h->ev_stage[r]));
     if (contiguous) {
-      memcpy(h->h_stage[r], v->data + done, chunk);
+      if (h->stage_streaming) copy_streaming(h->h_stage[r], v->data + done, chunk);
+      else memcpy(h->h_stage[r], v->data + done, chunk);
     } else {
       size_t w = 0;
       while (w < chunk) {  // row-wise pack (rows are row_step apart in the source)
@@ -1310,6 +1359,14 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   if (mode_env && mode_env[0] >= '0' && mode_env[0] <= '3') h->back_mode = mode_env[0] - '0';
   const char* sc_env = getenv("CONESGPU_STREAM_CTAS");
   if (sc_env && atoi(sc_env) >= 1 && atoi(sc_env) <= 8) h->stream_ctas_per_sm = atoi(sc_env);
+  {
+    const unsigned hw = std::thread::hardware_concurrency();
+    h->stage_threads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    const char* nt_env = getenv("CONESGPU_STAGE_NT");
+    if (nt_env) h->stage_streaming = nt_env[0] != '0';
+    const char* st_env = getenv("CONESGPU_STAGE_THREADS");
+    if (st_env && atoi(st_env) >= 1 && atoi(st_env) <= 16) h->stage_threads = atoi(st_env);
+  }
   const char* rs_env = getenv("CONESGPU_ROWSKIP");
   if (rs_env) h->use_rowskip = rs_env[0] != '0';
   const char* cl_env = getenv("CONESGPU_CLUSTER_FRONT");  // "1": single-pass 16-CTA-cluster front end
