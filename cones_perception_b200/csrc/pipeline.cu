@@ -501,10 +501,16 @@ void launch_keep_mask(cp_handle* h, const Geom& g, const CropK& c, const GroundK
   cudaMemsetAsync(h->d_mask, 0, sizeof(u32) * (size_t)g.n_tiles * kTileWords, h->stream);
   cudaMemsetAsync(h->d_tile_count, 0, sizeof(u32) * g.n_tiles, h->stream);
   if (h->stage_timing) cudaEventRecord(h->ev_k[2], h->stream);
+  // few frames: share each 32-row group between up to 8 warps so the whole GPU works on the batch
+  const u32 total_warps = (u32)h->sms * 4u * kStreamWarps;
+  u32 split_log2 = 0;
+  while (split_log2 < 3 && (((u64)g.n_tiles * 2u) << (split_log2 + 1)) <= total_warps) ++split_log2;
+  if (split_log2) grid = grid_for((((u64)g.n_tiles * 2u) << split_log2) * 32u, kStreamThreads, h->sms, h->stream_ctas_per_sm);
+  const u32* rm = h->rowmax_valid ? h->d_rowmax : nullptr;
   switch (h->layout.mode) {
-    case 0: keep_mask_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_thr_f, h->rowmax_valid ? h->d_rowmax : nullptr, mo); break;
-    case 1: keep_mask_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_thr_f, h->rowmax_valid ? h->d_rowmax : nullptr, mo); break;
-    default: keep_mask_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_thr_f, h->rowmax_valid ? h->d_rowmax : nullptr, mo); break;
+    case 0: keep_mask_kernel<0><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_thr_f, rm, mo, split_log2); break;
+    case 1: keep_mask_kernel<1><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_thr_f, rm, mo, split_log2); break;
+    default: keep_mask_kernel<2><<<grid, kStreamThreads, 0, h->stream>>>(h->in_ptr, h->layout, g, c, gk, h->d_thr_f, rm, mo, split_log2); break;
   }
   if (h->stage_timing) cudaEventRecord(h->ev_k[3], h->stream);
   h->launches++;
@@ -981,7 +987,32 @@ cp_status enqueue_back(cp_handle* h, bool retry) {
 // head of the result block (offsets + the first records) go to pinned mirrors, so reading results
 // costs ONE stream synchronisation.  Issued when the host asks for results (cp_sync), not per run:
 // a caller that keeps results on the device (multi-GPU gather) pays no PCIe traffic per step.
+// Small batches (a ROS node's single frame): one kernel stores the control block, the per-frame counters,
+// the offsets and the K cluster records straight into the pinned host mirrors (zero-copy writes over PCIe)
+// instead of three DMA copies with their per-copy latency, and only K records travel, not a fixed prefix.
+__global__ void __launch_bounds__(256) result_publish_kernel(const Ctl* __restrict__ ctl, u32* __restrict__ h_ctl,
+                                                             const u32* __restrict__ fc, u32* __restrict__ h_fc,
+                                                             u32 fc_words, const u32* __restrict__ k_off,
+                                                             u32* __restrict__ h_res, u32 off_words, u32 max_records) {
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const u32 K = ctl->n_clusters < max_records ? ctl->n_clusters : max_records;
+  for (u32 i = tid; i < sizeof(Ctl) / 4; i += nth) h_ctl[i] = reinterpret_cast<const u32*>(ctl)[i];
+  for (u32 i = tid; i < fc_words; i += nth) h_fc[i] = fc[i];
+  const u32 res_words = off_words + 4u * K;
+  for (u32 i = tid; i < res_words; i += nth) h_res[i] = k_off[i];
+}
+constexpr u32 kPublishMaxFrames = 64;
+
 cp_status enqueue_result_fetch(cp_handle* h) {
+  if (h->hg.n_frames <= kPublishMaxFrames) {
+    h->prefetched = h->prefetch_cap;
+    result_publish_kernel<<<4, 256, 0, h->stream>>>(h->d_ctl, reinterpret_cast<u32*>(h->h_ctl), h->d_fc, h->h_fc,
+                                                    8u * h->hg.n_frames, h->d_k_off, h->h_result, (u32)h->off_words,
+                                                    (u32)std::min<u64>(h->prefetch_cap, 0xFFFFFFFFu));
+    CK(cudaGetLastError());
+    h->fetched = true;
+    return CP_OK;
+  }
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_fc, h->d_fc, sizeof(u32) * 8 * h->hg.n_frames, cudaMemcpyDeviceToHost, h->stream));
   h->prefetched = std::min<u64>(h->prefetch_cap, std::max<u64>(4096, 64ull * h->hg.n_frames));

@@ -436,7 +436,7 @@ __global__ void ground_thresholds_kernel(u32 n_frames, const u32* __restrict__ l
 template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads, 4)
 keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, GroundK gk,
-                 const float* __restrict__ thr_f, const u32* __restrict__ rowmax, MaskOut o) {
+                 const float* __restrict__ thr_f, const u32* __restrict__ rowmax, MaskOut o, u32 split_log2) {
   constexpr int kBatch = 4;
   const int lane = lane_id();
   const u32 nwarps = gridDim.x * kStreamWarps;
@@ -448,9 +448,15 @@ keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, Grou
   // contiguous split would leave most warps idle while a few do all the work
   // (the warp slot is rotated by an odd step every round: with a plain stride the same warps would
   // meet the same ring of every frame whenever the warp count is a multiple of the frame's groups)
-  for (u32 round = 0, g0 = 0; g0 < ngroups; ++round, g0 += nwarps) {
-    const u32 grp = g0 + (gw + round * 37u) % nwarps;
-    if (grp >= ngroups) continue;
+  // (a batch of a few frames has fewer groups than the GPU has warps: each group is then shared by
+  // 2, 4 or 8 warps, one slice of its rows each, so a single frame is not bound by one warp's 32 rows)
+  const u32 nvg = ngroups << split_log2;
+  const u32 slice_rows = 32u >> split_log2;
+  for (u32 round = 0, g0 = 0; g0 < nvg; ++round, g0 += nwarps) {
+    const u32 vg = g0 + (gw + round * 37u) % nwarps;
+    if (vg >= nvg) continue;
+    const u32 grp = vg >> split_log2, sub = vg & ((1u << split_log2) - 1u);
+    const u32 slice = split_log2 ? (((1u << slice_rows) - 1u) << (sub * slice_rows)) : 0xFFFFFFFFu;
     const u32 rk = skipping ? rowmax[(u64)grp * 32 + lane] : 0xFFFFFFFFu;   // lane = row within the group
     const u32 tile = grp >> 1;
     u32 frame, local0, count;
@@ -459,15 +465,15 @@ keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, Grou
     const float* thr = thr_f + (size_t)frame * kSectStride;
     const float thr_min = gk.do_ground ? __ldg(thr + 31) : -__int_as_float(0x7f800000);
     const u32 half0 = (grp & 1u) * (kStreamTile / 2);          // tile-local index of the group's first point
-    if (gk.pad_survives && (grp & 1u) && lane == 0 &&
+    if (gk.pad_survives && (grp & 1u) && lane == 0 && sub == 0 &&
         (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]))
       atomicAdd(&o.tile_count[tile], 1u);                      // the record standing for the zero padding
-    u32 todo = __ballot_sync(kFull, rk >= f2ord(thr_min));     // bit r: row r of the group must be evaluated
+    u32 todo = __ballot_sync(kFull, rk >= f2ord(thr_min)) & slice;  // bit r: row r of the group must be evaluated
     if (todo == 0) continue;
     nrows += __popc(todo);
     const u32 live = todo;
     u32 myword = 0, gcount = 0, gkept = 0;
-    if (todo == 0xFFFFFFFFu) {
+    if (todo == 0xFFFFFFFFu) {  // (whole groups only: a slice never has all 32 bits)
       // a fully live group (e.g. a ring above the horizon): straight-line, eight rows per round
 #pragma unroll 1
       for (u32 b = 0; b < 4; ++b) {
