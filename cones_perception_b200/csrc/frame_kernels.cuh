@@ -59,6 +59,8 @@ struct FrameArgs {
   u32* kcount_f;             // [F]
   u32* ncrop_f;              // [F] survivors per frame
   ClusterRec* slots;         // [F][VMAX] per-frame result slots, canonical order inside a frame
+  ClusterRec* direct_out;    // single-frame batches: the packed result list itself (no pack kernel); else NULL
+  u32 direct_cap;
   u32* nvox_f;               // [F] voxels per frame
   u32* fc;                   // [F][8] cp_frame_counters records
   int counted_ground;
@@ -606,12 +608,19 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
       fc[5] = K;
       fc[6] = s.vfr.bits;
       fc[7] = s.vfr.passthrough;
+      if (a.direct_out) {            // what pack_clusters_kernel would write for a one-frame batch
+        a.k_off[0] = 0;
+        a.k_off[1] = K;
+        a.ctl->n_clusters = K;
+        if (K > a.direct_cap) atomicOr(&a.ctl->error, kErrVoxels);
+      }
     }
     // ---- S8/S9: centroid (src/cone_detection.cpp:261-273) and canonical rank, warp per cluster.
     // Lanes find the members 32 voxels at a time; the fp32 sums stay sequential in ascending
     // voxel index (every lane carries the same running sum).
     if (K > 0) {
-      ClusterRec* slot = a.slots + (u64)f * VMAX;
+      ClusterRec* slot = a.direct_out ? a.direct_out : a.slots + (u64)f * VMAX;
+      const u32 slot_cap = a.direct_out ? a.direct_cap : (u32)VMAX;
       for (u32 k = warp; k < K; k += kFrameThreads / 32) {
         const u32 root = s.vstart[k];
         const u32 size = s.u.vox.csize[root];
@@ -641,7 +650,7 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
           o.y = __fdiv_rn(y, cnt);
           o.size = size;
           o.min_index = root;
-          slot[rank] = o;
+          if (rank < slot_cap) slot[rank] = o;
         }
       }
     }

@@ -893,6 +893,9 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   fa.kcount_f = h->d_kcount_f;
   fa.ncrop_f = h->d_ncrop_f;
   fa.slots = h->d_slots;
+  const bool direct = fa.n_frames == 1;  // a node's single frame: the frame kernel writes the result list itself
+  fa.direct_out = direct ? reinterpret_cast<ClusterRec*>(h->d_clusters) : nullptr;
+  fa.direct_cap = (u32)std::min<u64>(h->cap_v, 0xFFFFFFFFu);
   fa.fc = h->d_fc;
   fa.counted_ground = h->counted_ground ? 1 : 0;
   fa.nvox_f = h->d_nvox_f;
@@ -912,9 +915,11 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
     case 1: launch_frame_kernel<CMAX, VMAX, 1, T>(h, fa); break;
     default: launch_frame_kernel<CMAX, VMAX, 2, T>(h, fa); break;
   }
-  pack_clusters_kernel<<<fa.n_frames, 256, 0, h->stream>>>(fa.n_frames, VMAX, h->d_kcount_f, h->d_slots, h->d_k_off,
-                                                           h->d_clusters, (u32)h->cap_v, h->d_ctl);
-  h->launches++;
+  if (!direct) {
+    pack_clusters_kernel<<<fa.n_frames, 256, 0, h->stream>>>(fa.n_frames, VMAX, h->d_kcount_f, h->d_slots, h->d_k_off,
+                                                             h->d_clusters, (u32)h->cap_v, h->d_ctl);
+    h->launches++;
+  }
 }
 
 // ---- result path over peer memory (NVLink): every rank's publish kernel stores its packed cone
