@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
       // eight lanes per row, candidates strided over them: a few dozen rows run side by side per
       // warp and a crowded cell (many candidates) does not stall the warp the way one thread per row
       // does (measured: rows average 26 candidates but the longest have > 100).  The lanes of a row
-      // need no communication: each carries the row's root in a register, a hit costs one find.
+      // need no communication: each carries the row's root (or an ancestor of it) in a register.
       constexpr u32 kLanesPerRow = 8;
       for (u32 r = tid / kLanesPerRow; r < V; r += kFrameThreads / kLanesPerRow) {
         const u32 i = s.u.vox.perm[r];
@@ -533,20 +533,41 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
 #endif
         for (u32 jp = lo + tid % kLanesPerRow; jp < r; jp += kLanesPerRow) {
           const u32 j = s.u.vox.perm[jp];
+#ifndef CP_UNION_LEVEL
+          // j already hangs under i's root: the edge cannot change anything, so neither the distance nor a
+          // find is needed.  The voxels of one cone are mutual neighbours (a clique of up to ~100 at close
+          // range); after its first rows almost every candidate takes this one-load exit.
+          if (((volatile u32*)s.u.vox.parent)[j] == ri) continue;
+#endif
           if (l2_simple(xi, yi, zi, s.u.vox.vx[j], s.u.vox.vy[j], s.u.vox.vz[j]) < a.ck.r2) {
 #if defined(CP_UNION_LEVEL) && CP_UNION_LEVEL == 0
             dbg_hits++;
 #elif defined(CP_UNION_LEVEL) && CP_UNION_LEVEL == 1
             dbg_hits += smem_find(s.u.vox.parent, j);
 #else
-            const u32 rj = smem_find(s.u.vox.parent, j);
-            if (rj != ri) {
-              smem_union(s.u.vox.parent, rj, ri);
-              ri = smem_find(s.u.vox.parent, i);
+            // link the larger root under the smaller with one CAS on what we believe are the two roots; only
+            // when the larger one has been linked meanwhile do we climb again (from where the CAS pointed us).
+            // Linking under a node that is no longer a root is still sound: parents always have smaller
+            // indices, so there are no cycles and every tree's root is the smallest index of its component.
+            u32 rj = smem_find(s.u.vox.parent, j);
+            if (rj != j) ((volatile u32*)s.u.vox.parent)[j] = rj;  // j is not a root: point it at its root
+            while (rj != ri) {
+              const u32 hi = ri > rj ? ri : rj, sm = ri > rj ? rj : ri;
+              const u32 old = atomicCAS(&s.u.vox.parent[hi], hi, sm);
+              if (old == hi) {
+                ri = sm;
+                break;
+              }
+              if (hi == ri) ri = smem_find(s.u.vox.parent, old);
+              else rj = smem_find(s.u.vox.parent, old);
             }
 #endif
           }
         }
+#ifndef CP_UNION_LEVEL
+        // ri is i itself or one of its ancestors: later rows that meet i take the one-load exit above
+        if (ri != i) ((volatile u32*)s.u.vox.parent)[i] = ri;
+#endif
 #ifdef CP_UNION_LEVEL
         if (f == 0) {
           atomicAdd(&dbg_cnt[0], dbg_cand);
