@@ -1865,6 +1865,21 @@ cp_status cp_set_stage_timing(cp_handle* h, int on) {
   return CP_OK;
 }
 
+cp_status cp_debug_timeline(cp_handle* h, const cp_handle* base, float out_ms[6]) {
+  if (!h || !out_ms) return CP_E_PARAM;
+  if (!h->ran || !h->stage_timing || !h->ran_ground || h->ran_fused || h->ran_cluster) {
+    h->err = "cp_debug_timeline needs cp_set_stage_timing(1) and a two-kernel run with ground removal";
+    return CP_E_STATE;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->ev1));
+  const cudaEvent_t t0 = base ? base->ev0 : h->ev0;
+  if (base) CK(cudaEventSynchronize(base->ev1));
+  const cudaEvent_t ev[6] = {h->ev0, h->ev_k[0], h->ev_k[1], h->ev_k[2], h->ev_k[3], h->ev1};
+  for (int i = 0; i < 6; ++i) CK(cudaEventElapsedTime(&out_ms[i], t0, ev[i]));
+  return CP_OK;
+}
+
 cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms) {
   if (!h || !ms) return CP_E_PARAM;
   if (!h->ran || !h->stage_timing) {

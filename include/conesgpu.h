@@ -167,6 +167,10 @@ typedef enum cp_stage {
 } cp_stage;
 cp_status cp_set_stage_timing(cp_handle* h, int on);
 cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms);
+/* Device timestamps of the last run (stage timing on), in ms after the start of `base`'s last run (NULL: this
+ * handle's own): [0] run start, [1]/[2] pass 1 start/end, [3]/[4] pass 2 start/end, [5] run end.  With two
+ * handles alternating this shows how consecutive batches overlap (tools/timeline_probe.py). */
+cp_status cp_debug_timeline(cp_handle* h, const cp_handle* base, float out_ms[6]);
 /* Device pointers of the last run's results (valid until the next run on this handle):
  * packed cp_cluster records, n_frames+1 cluster offsets, and the total cluster count.
  * Lets a multi-GPU caller hand the cone lists to NCCL without a host round trip: offsets and
