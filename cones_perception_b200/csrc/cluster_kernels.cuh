@@ -168,13 +168,31 @@ __global__ void neighbour_union_kernel(const Ctl* __restrict__ ctl, ClusterK k, 
     }
     const u32 v = vals[pos];
     const float4 p = vox[v];
+    u32 rv = uf_find(parent, v);  // v's root, or (after other threads' links) one of v's ancestors
     for (u32 j = b; j < e; ++j) {
       const u32 u = vals[j];
       if (nb != 13u && u > v) continue;  // each cross-cell pair is seen from both sides: test once
+      // u already hangs under v's root: the edge cannot change anything.  In a solid blob (thousands of mutual
+      // neighbours per voxel) almost every candidate leaves here after one 4-byte load.
+      if (((volatile u32*)parent)[u] == rv) continue;
       const float4 q = vox[u];
       // FLANN: dist = L2_Simple(query, point); accepted iff dist < radius (strict)
-      if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < k.r2) uf_union(parent, v, u);
+      if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < k.r2) {
+        u32 ru = uf_find(parent, u);
+        if (ru != u) ((volatile u32*)parent)[u] = ru;  // u is not a root: point it at its root for later visitors
+        while (ru != rv) {  // larger root under the smaller; parents always have smaller indices
+          const u32 hi = rv > ru ? rv : ru, sm = rv > ru ? ru : rv;
+          const u32 old = atomicCAS(&parent[hi], hi, sm);
+          if (old == hi) {
+            rv = sm;
+            break;
+          }
+          if (hi == rv) rv = uf_find(parent, old);
+          else ru = uf_find(parent, old);
+        }
+      }
     }
+    if (rv != v) ((volatile u32*)parent)[v] = rv;
   }
 }
 

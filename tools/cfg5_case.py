@@ -1,0 +1,22 @@
+"""One adversarial frame (config 5) through the general back half, for profiling: python tools/cfg5_case.py [reps]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from cones_perception_b200 import api, scans  # noqa: E402
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+cfg = scans.config(5)
+fr = scans.generate_config5(1, 0)
+N = fr.shape[1]
+dev = torch.from_numpy(np.ascontiguousarray(fr)).cuda()
+with api.ConesGpu(max_points=N, max_frames=1) as g:
+    g.set_device_input(dev.data_ptr(), np.full(1, N, np.uint32), keep=dev)
+    for _ in range(reps):
+        g.run(cfg.detect, cfg.ground)
+        g.sync()
+    print("launches", g.last_launch_count())
