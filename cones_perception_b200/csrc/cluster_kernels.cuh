@@ -133,66 +133,73 @@ __device__ __forceinline__ void uf_union(u32* parent, u32 a, u32 b) {
   }
 }
 
-// one thread per (sorted voxel position, neighbour cell): 27 * V work items
-__global__ void neighbour_union_kernel(const Ctl* __restrict__ ctl, ClusterK k, const u64* keys_a,
-                                       const u64* keys_b, const u32* vals_a, const u32* vals_b,
-                                       const u32* __restrict__ cstart, const u64* __restrict__ hkeys,
-                                       const u32* __restrict__ hvals, const float4* __restrict__ vox,
-                                       u32* __restrict__ parent) {
+// One warp per sorted voxel position.  Lanes 0..26 look up the 27 neighbour cells (one hash probe each, in
+// parallel); then the warp walks the cells one after the other with its lanes strided over the candidates, so the
+// index and parent loads of a crowded cell (a solid blob puts ~1000 voxels into one tolerance cell) are coalesced
+// instead of 32 lanes each walking a list of their own.
+__global__ void __launch_bounds__(256) neighbour_union_kernel(const Ctl* __restrict__ ctl, ClusterK k,
+                                                              const u64* keys_a, const u64* keys_b, const u32* vals_a,
+                                                              const u32* vals_b, const u32* __restrict__ cstart,
+                                                              const u64* __restrict__ hkeys,
+                                                              const u32* __restrict__ hvals,
+                                                              const float4* __restrict__ vox, u32* __restrict__ parent) {
   const u32 nv = ctl->n_vox, nc = ctl->n_cells, mask = ctl->hash_mask;
   const bool inb = sorted_in_b(ctl->csort_bits);
   const u64* keys = inb ? keys_b : keys_a;
   const u32* vals = inb ? vals_b : vals_a;
-  const u64 total = (u64)nv * 27ull;
-  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (u64)gridDim.x * blockDim.x) {
-    const u32 pos = (u32)(w / 27ull);
-    const u32 nb = (u32)(w - (u64)pos * 27ull);
-    const i32 dx = (i32)(nb % 3u) - 1, dy = (i32)((nb / 3u) % 3u) - 1, dz = (i32)(nb / 9u) - 1;
+  const u32 lane = threadIdx.x & 31u;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 pos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pos < nv; pos += nwarps) {
     const u64 ck = keys[pos];
     const u32 cx = (u32)(ck % k.nx), cy = (u32)((ck / k.nx) % k.nx), cz = (u32)((ck / ((u64)k.nx * k.nx)) % k.nx);
-    const i32 qx = (i32)cx + dx, qy = (i32)cy + dy, qz = (i32)cz + dz;
-    if (qx < 0 || qy < 0 || qz < 0 || qx >= (i32)k.nx || qy >= (i32)k.nx || qz >= (i32)k.nx) continue;
-    const u64 nk = (u64)((long long)ck + dx + (long long)dy * (long long)k.nx +
-                         (long long)dz * (long long)k.nx * (long long)k.nx);
-    const u32 c = (nb == 13u) ? 0u : hash_find(hkeys, hvals, mask, nk);
-    u32 b, e;
-    if (nb == 13u) {
-      // own cell: it is contiguous around pos; only earlier positions need testing
-      b = pos;
-      while (b > 0 && keys[b - 1] == ck) --b;
-      e = pos;
-    } else {
-      if (c == 0xFFFFFFFFu) continue;
-      b = cstart[c];
-      e = (c + 1 < nc) ? cstart[c + 1] : nv;
-    }
-    const u32 v = vals[pos];
-    const float4 p = vox[v];
-    u32 rv = uf_find(parent, v);  // v's root, or (after other threads' links) one of v's ancestors
-    for (u32 j = b; j < e; ++j) {
-      const u32 u = vals[j];
-      if (nb != 13u && u > v) continue;  // each cross-cell pair is seen from both sides: test once
-      // u already hangs under v's root: the edge cannot change anything.  In a solid blob (thousands of mutual
-      // neighbours per voxel) almost every candidate leaves here after one 4-byte load.
-      if (((volatile u32*)parent)[u] == rv) continue;
-      const float4 q = vox[u];
-      // FLANN: dist = L2_Simple(query, point); accepted iff dist < radius (strict)
-      if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < k.r2) {
-        u32 ru = uf_find(parent, u);
-        if (ru != u) ((volatile u32*)parent)[u] = ru;  // u is not a root: point it at its root for later visitors
-        while (ru != rv) {  // larger root under the smaller; parents always have smaller indices
-          const u32 hi = rv > ru ? rv : ru, sm = rv > ru ? ru : rv;
-          const u32 old = atomicCAS(&parent[hi], hi, sm);
-          if (old == hi) {
-            rv = sm;
-            break;
-          }
-          if (hi == rv) rv = uf_find(parent, old);
-          else ru = uf_find(parent, old);
+    u32 b = 0, e = 0;  // lane nb: candidate positions [b, e) of neighbour cell nb
+    if (lane < 27u) {
+      const i32 dx = (i32)(lane % 3u) - 1, dy = (i32)((lane / 3u) % 3u) - 1, dz = (i32)(lane / 9u) - 1;
+      const i32 qx = (i32)cx + dx, qy = (i32)cy + dy, qz = (i32)cz + dz;
+      if (qx >= 0 && qy >= 0 && qz >= 0 && qx < (i32)k.nx && qy < (i32)k.nx && qz < (i32)k.nx) {
+        const u64 nk = (u64)((long long)ck + dx + (long long)dy * (long long)k.nx +
+                             (long long)dz * (long long)k.nx * (long long)k.nx);
+        const u32 c = hash_find(hkeys, hvals, mask, nk);
+        if (c != 0xFFFFFFFFu) {
+          b = cstart[c];
+          // own cell: only earlier positions (each pair once); other cells: the whole cell, filtered by u < v
+          e = (lane == 13u) ? pos : ((c + 1 < nc) ? cstart[c + 1] : nv);
         }
       }
     }
-    if (rv != v) ((volatile u32*)parent)[v] = rv;
+    const u32 v = vals[pos];
+    const float4 p = vox[v];
+    u32 rv = uf_find(parent, v);  // v's root, or (after other lanes' / warps' links) one of v's ancestors
+    for (u32 nb = 0; nb < 27u; ++nb) {
+      const u32 cb = __shfl_sync(kFull, b, nb), ce = __shfl_sync(kFull, e, nb);
+      if (cb >= ce) continue;  // uniform over the warp
+      for (u32 j = cb + lane; j < ce; j += 32u) {
+        const u32 u = vals[j];
+        if (nb != 13u && u > v) continue;  // each cross-cell pair is seen from both sides: test once
+        // u already hangs under v's root: the edge cannot change anything.  In a solid blob (thousands of
+        // mutual neighbours per voxel) almost every candidate leaves here after one 4-byte load.
+        if (((volatile u32*)parent)[u] == rv) continue;
+        const float4 q = vox[u];
+        // FLANN: dist = L2_Simple(query, point); accepted iff dist < radius (strict)
+        if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < k.r2) {
+          u32 ru = uf_find(parent, u);
+          if (ru != u) ((volatile u32*)parent)[u] = ru;  // u is not a root: point it at its root for later visitors
+          while (ru != rv) {  // larger root under the smaller; parents always have smaller indices
+            const u32 hi = rv > ru ? rv : ru, sm = rv > ru ? ru : rv;
+            const u32 old = atomicCAS(&parent[hi], hi, sm);
+            if (old == hi) {
+              rv = sm;
+              break;
+            }
+            if (hi == rv) rv = uf_find(parent, old);
+            else ru = uf_find(parent, old);
+          }
+        }
+      }
+      __syncwarp();
+      rv = __reduce_min_sync(kFull, rv);  // every lane holds v or an ancestor of v: the smallest is the highest
+    }
+    if (lane == 0 && rv != v) ((volatile u32*)parent)[v] = rv;
   }
 }
 

@@ -803,7 +803,7 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   hash_clear_kernel<<<grid_for(h->hash_cap, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_ctl, h->d_hkeys);
   hash_insert_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_cstart, h->d_hkeys,
                                                    h->d_hvals);
-  neighbour_union_kernel<<<grid_for(h->cap_v * 27ull, 256, h->sms, 8), 256, 0, h->stream>>>(
+  neighbour_union_kernel<<<grid_for(h->cap_v * 32ull, 256, h->sms, 8), 256, 0, h->stream>>>(
       h->d_ctl, ck, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b, h->d_cstart, h->d_hkeys, h->d_hvals,
       h->d_vox, h->d_parent);
   flatten_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_parent, h->d_label, h->d_keys_a, h->d_vals_a);
