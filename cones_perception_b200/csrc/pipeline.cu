@@ -1661,8 +1661,7 @@ static RunKey make_key(const cp_handle* h, const cp_detect_params* d, const cp_g
 cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_params* ground) {
   if (!h) return CP_E_PARAM;
   CK(cudaSetDevice(h->cfg.device));
-  const bool eligible = h->use_graph && d && h->batch_ready && !h->taps && !h->stage_timing && h->back_mode < 3 &&
-                        h->hg.uniform_n != 0;
+  const bool eligible = h->use_graph && d && h->batch_ready && !h->taps && !h->stage_timing && h->hg.uniform_n != 0;
   if (!eligible) {
     h->key_valid = false;
     return enqueue_pipeline(h, d, ground);

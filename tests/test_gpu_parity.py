@@ -375,3 +375,28 @@ def test_every_back_half_variant_gives_the_same_cones(mode):
         assert int(ctr["n_cropped"][f]) == octr.n_cropped and int(ctr["n_voxels"][f]) == octr.n_voxels
         assert int(ctr["n_components"][f]) == octr.n_components and int(ctr["key_bits"][f]) == octr.key_bits
     assert np.array_equal(single.view(np.uint32), cl[off[0]:off[1]].view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+def test_graph_replay_follows_the_data(mode):
+    """A repeated identical run is captured into a CUDA graph on its second sighting and replayed afterwards.
+    The replays must read the input afresh: the device buffer is overwritten in place between runs and every
+    run must match the oracle of what is in the buffer at that time (per-frame kernel and general back half)."""
+    import torch
+    cfg = scans.config(3)
+    a = scans.generate(cfg, 3, base_seed=300)
+    b = scans.generate(cfg, 3, base_seed=400)
+    F, N = a.shape[0], a.shape[1]
+    dev = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    exp = {}
+    for name, fr in (("a", a), ("b", b)):
+        exp[name] = [O.detect(O.view_of_xyzi(f), cfg.detect, cfg.ground, O.CANONICAL)[0] for f in fr]
+    with api.ConesGpu(max_points=F * N, max_frames=F, back_mode=mode) as h:
+        h.set_device_input(dev.data_ptr(), np.full(F, N, np.uint32), keep=dev)
+        for rep, name in enumerate(["a", "a", "a", "b", "b", "a", "b"]):   # direct, capture, replay, replays on new data
+            dev.copy_(torch.from_numpy(np.ascontiguousarray(a if name == "a" else b)))
+            torch.cuda.synchronize()
+            h.run(cfg.detect, cfg.ground)
+            ctr, off, cl = h.results()
+            for f in range(F):
+                assert np.array_equal(cl[off[f]:off[f + 1]].view(np.uint32), exp[name][f].view(np.uint32)), (rep, name, f)

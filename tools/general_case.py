@@ -1,4 +1,4 @@
-"""One adversarial frame (config 5) through the general back half, for profiling: python tools/cfg5_case.py [reps]"""
+"""One frame of config 4 or 5 through the general back half, for profiling: python tools/general_case.py [reps] [config]"""
 import os
 import sys
 
@@ -10,8 +10,9 @@ import torch  # noqa: E402
 from cones_perception_b200 import api, scans  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-cfg = scans.config(5)
-fr = scans.generate_config5(1, 0)
+idx = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+cfg = scans.config(idx)
+fr = scans.generate_config5(1, 0) if idx == 5 else scans.generate(cfg, 1, 0)
 N = fr.shape[1]
 dev = torch.from_numpy(np.ascontiguousarray(fr)).cuda()
 with api.ConesGpu(max_points=N, max_frames=1) as g:
