@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "cp_strerror", "cp_last_error", "cp_abi_version", "cp_create_error", "cp_create", "cp_destroy",
     "cp_ground_remove", "cp_detect", "cp_batch_set_device_input", "cp_batch_set_host_input", "cp_batch_run",
     "cp_sync", "cp_batch_results", "cp_detect_batch", "cp_last_run_ms", "cp_last_launch_count", "cp_stream",
-    "cp_debug_tap", "cp_debug_sort", "cp_set_stage_timing", "cp_stage_ms", "cp_debug_timeline", "cp_device_results",
+    "cp_debug_tap", "cp_debug_sort", "cp_set_stage_timing", "cp_stage_ms", "cp_debug_timeline", "cp_debug_atan2f", "cp_device_results",
     "cp_gather_create", "cp_gather_open", "cp_gather_seq", "cp_gather_wait", "cp_gather_read",
     "cp_last_rows_loaded", "cp_cone_crops", "cp_cone_images", "cp_rasterize_crops",
 ]
@@ -95,6 +95,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cp_set_stage_timing.argtypes = [vp, C.c_int]
     lib.cp_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     lib.cp_debug_timeline.argtypes = [vp, vp, vp]
+    lib.cp_debug_atan2f.argtypes = [vp, vp, vp, u32, vp]
     lib.cp_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.cp_gather_create.argtypes = [vp, u32, u32, vp]
     lib.cp_gather_open.argtypes = [vp, vp, u32, u32, u32]
@@ -297,6 +298,13 @@ class ConesGpu:
         run start, pass 1 start/end, pass 2 start/end, run end (stage timing must be on)."""
         out = np.zeros(6, np.float32)
         self._ck(self.lib.cp_debug_timeline(self._h, base._h if base is not None else None, out.ctypes.data))
+        return out
+
+    def debug_atan2f(self, y: np.ndarray, x: np.ndarray) -> np.ndarray:
+        y = np.ascontiguousarray(y, np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty_like(y)
+        self._ck(self.lib.cp_debug_atan2f(self._h, y.ctypes.data, x.ctypes.data, len(y), out.ctypes.data))
         return out
 
     def device_results(self):

@@ -1864,6 +1864,31 @@ cp_status cp_set_stage_timing(cp_handle* h, int on) {
   return CP_OK;
 }
 
+__global__ void debug_atan2f_kernel(const float* __restrict__ y, const float* __restrict__ x, u32 n, float* __restrict__ out) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = atan2_exact(y[i], x[i]);
+}
+
+cp_status cp_debug_atan2f(cp_handle* h, const float* y, const float* x, uint32_t n, float* out) {
+  if (!h || !y || !x || !out) return CP_E_PARAM;
+  if (n == 0) return CP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  float* d = nullptr;
+  if (cudaMalloc(&d, sizeof(float) * 3 * (size_t)n) != cudaSuccess) {
+    cudaGetLastError();
+    h->err = "cudaMalloc failed (cp_debug_atan2f)";
+    return CP_E_NOMEM;
+  }
+  cudaMemcpyAsync(d, y, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(d + n, x, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream);
+  debug_atan2f_kernel<<<grid_for(n, 256, h->sms, 8), 256, 0, h->stream>>>(d, d + n, n, d + 2 * (size_t)n);
+  cudaMemcpyAsync(out, d + 2 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream);
+  const cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  CK(e);
+  CK(cudaGetLastError());
+  return CP_OK;
+}
+
 cp_status cp_debug_timeline(cp_handle* h, const cp_handle* base, float out_ms[6]) {
   if (!h || !out_ms) return CP_E_PARAM;
   if (!h->ran || !h->stage_timing || !h->ran_ground || h->ran_fused || h->ran_cluster) {

@@ -105,9 +105,108 @@ __device__ __forceinline__ float4 load_point(const uint8_t* base, u64 idx, const
 }
 
 // ---- angle / sector arithmetic --------------------------------------------------------
-// Oracle definition of the reference's atan2f: (float)atan2((double)y,(double)x).
+// The reference's atan2(float, float) is libm's atan2f: up to glibc 2.40 the classic fdlibm single-precision
+// routine, which is not correctly rounded (e.g. atan2f(1.7f, -1.7e-8f) is one float below pi/2).  Parity means
+// reproducing that routine, so the exact path restates it operation by operation in IEEE fp32 (explicit _rn
+// intrinsics: no FMA contraction).  oracle/cones_oracle.cpp holds the same restatement, checked against libm
+// exhaustively (atanf) / on 4.8e9 pairs (atan2f).  Only guard-band points ever come here.
+__device__ __forceinline__ float fd_poly(float x, float& s1, float& s2) {
+  const float z = __fmul_rn(x, x), w = __fmul_rn(z, z);
+  float a = __fmul_rn(w, 1.6285819933e-02f);
+  a = __fmul_rn(w, __fadd_rn(4.9768779427e-02f, a));
+  a = __fmul_rn(w, __fadd_rn(6.6610731184e-02f, a));
+  a = __fmul_rn(w, __fadd_rn(9.0908870101e-02f, a));
+  a = __fmul_rn(w, __fadd_rn(1.4285714924e-01f, a));
+  s1 = __fmul_rn(z, __fadd_rn(3.3333334327e-01f, a));
+  float b = __fmul_rn(w, -3.6531571299e-02f);
+  b = __fmul_rn(w, __fadd_rn(-5.8335702866e-02f, b));
+  b = __fmul_rn(w, __fadd_rn(-7.6918758452e-02f, b));
+  b = __fmul_rn(w, __fadd_rn(-1.1111110449e-01f, b));
+  s2 = __fmul_rn(w, __fadd_rn(-2.0000000298e-01f, b));
+  return x;
+}
+__device__ __noinline__ float fdlibm_atanf(float x) {
+  const u32 hx = __float_as_uint(x), ix = hx & 0x7fffffffu;
+  float hi, lo;
+  int id;
+  if (ix >= 0x4c000000u) {  // |x| >= 2^25
+    if (ix > 0x7f800000u) return __fadd_rn(x, x);
+    const float r = __fadd_rn(1.5707962513e+00f, 7.5497894159e-08f);
+    return (hx >> 31) ? -r : r;
+  }
+  if (ix < 0x3ee00000u) {  // |x| < 0.4375
+    if (ix < 0x31000000u) return x;
+    id = -1;
+    hi = lo = 0.f;
+  } else {
+    x = fabsf(x);
+    if (ix < 0x3f980000u) {
+      if (ix < 0x3f300000u) {
+        id = 0; hi = 4.6364760399e-01f; lo = 5.0121582440e-09f;
+        x = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, x), -1.0f), __fadd_rn(2.0f, x));
+      } else {
+        id = 1; hi = 7.8539812565e-01f; lo = 3.7748947079e-08f;
+        x = __fdiv_rn(__fadd_rn(x, -1.0f), __fadd_rn(x, 1.0f));
+      }
+    } else {
+      if (ix < 0x401c0000u) {
+        id = 2; hi = 9.8279368877e-01f; lo = 3.4473217170e-08f;
+        x = __fdiv_rn(__fadd_rn(x, -1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x)));
+      } else {
+        id = 3; hi = 1.5707962513e+00f; lo = 7.5497894159e-08f;
+        x = __fdiv_rn(-1.0f, x);
+      }
+    }
+  }
+  float s1, s2;
+  fd_poly(x, s1, s2);
+  const float xs = __fmul_rn(x, __fadd_rn(s1, s2));
+  if (id < 0) return __fsub_rn(x, xs);
+  const float r = __fsub_rn(hi, __fsub_rn(__fsub_rn(xs, lo), x));
+  return (hx >> 31) ? -r : r;
+}
 __device__ __noinline__ float atan2_exact(float y, float x) {
-  return (float)atan2((double)y, (double)x);
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+              pi_lo = -8.7422776573e-08f;
+  const i32 hx = __float_as_int(x), hy = __float_as_int(y);
+  const i32 ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return __fadd_rn(x, y);
+  if (hx == 0x3f800000) return fdlibm_atanf(y);
+  const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+  if (iy == 0) {
+    if (m < 2) return y;
+    return m == 2 ? __fadd_rn(pi, tiny) : __fsub_rn(-pi, tiny);
+  }
+  if (ix == 0) return (hy < 0) ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+  if (ix == 0x7f800000) {
+    if (iy == 0x7f800000) {
+      const float q3 = __fmul_rn(3.0f, pi_o_4);
+      switch (m) {
+        case 0: return __fadd_rn(pi_o_4, tiny);
+        case 1: return __fsub_rn(-pi_o_4, tiny);
+        case 2: return __fadd_rn(q3, tiny);
+        default: return __fsub_rn(-q3, tiny);
+      }
+    }
+    switch (m) {
+      case 0: return 0.0f;
+      case 1: return -0.0f;
+      case 2: return __fadd_rn(pi, tiny);
+      default: return __fsub_rn(-pi, tiny);
+    }
+  }
+  if (iy == 0x7f800000) return (hy < 0) ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+  const i32 k = (iy - ix) >> 23;
+  float z;
+  if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+  else if (hx < 0 && k < -60) z = 0.0f;
+  else z = fdlibm_atanf(fabsf(__fdiv_rn(y, x)));
+  switch (m) {
+    case 0: return z;
+    case 1: return __uint_as_float(__float_as_uint(z) ^ 0x80000000u);
+    case 2: return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+    default: return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+  }
 }
 // src/ground_removal.cpp:20 evaluated at survey time: float((360/16) * M_PI / 180)
 #define CP_SECTOR_ANGLE 0.38397244f

@@ -170,6 +170,8 @@ cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms);
 /* Device timestamps of the last run (stage timing on), in ms after the start of `base`'s last run (NULL: this
  * handle's own): [0] run start, [1]/[2] pass 1 start/end, [3]/[4] pass 2 start/end, [5] run end.  With two
  * handles alternating this shows how consecutive batches overlap (tools/timeline_probe.py). */
+/* The exact-path atan2f (the reference's libm atan2f, restated) on n pairs: parity test hook. */
+cp_status cp_debug_atan2f(cp_handle* h, const float* y, const float* x, uint32_t n, float* out);
 cp_status cp_debug_timeline(cp_handle* h, const cp_handle* base, float out_ms[6]);
 /* Device pointers of the last run's results (valid until the next run on this handle):
  * packed cp_cluster records, n_frames+1 cluster offsets, and the total cluster count.

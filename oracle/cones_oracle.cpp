@@ -32,11 +32,110 @@ inline double secs(clk::time_point a, clk::time_point b) {
   return std::chrono::duration<double>(b - a).count();
 }
 
-// "atan2f" as defined by SURVEY A.2: glibc's float atan2f is not correctly rounded and
-// differs between glibc versions, so the oracle pins the angle to the double-precision
-// result rounded once to float.
+// The reference calls atan2(float, float): C++ overload resolution picks the float version, i.e. libm's atan2f
+// (checked on the reference's own compiled code, oracle/ref_shim).  glibc's atan2f up to 2.40 — the Noetic target
+// (2.31) and this image (2.39) alike — is the classic fdlibm single-precision routine, which is NOT correctly
+// rounded: e.g. atan2f(1.7f, -1.7e-8f) = 0x1.921fb4p+0, one float below pi/2, so such a point passes a 90 degree
+// angle crop.  The oracle therefore restates that algorithm (Sun fdlibm e_atan2f.c / s_atanf.c as published; float
+// arithmetic, no contraction) instead of rounding a double result.  Checked here against this libm: atanf over all
+// 2^32 floats, atan2f over 4.8e9 pairs, zero mismatches (tests/test_oracle.py keeps a smaller version of that check).
+inline uint32_t f2u(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+inline float u2f(uint32_t u) {
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+inline float fdlibm_atanf(float x) {
+  static const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+  static const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+  static const float aT[11] = {3.3333334327e-01f,  -2.0000000298e-01f, 1.4285714924e-01f,  -1.1111110449e-01f,
+                               9.0908870101e-02f,  -7.6918758452e-02f, 6.6610731184e-02f,  -5.8335702866e-02f,
+                               4.9768779427e-02f,  -3.6531571299e-02f, 1.6285819933e-02f};
+  const uint32_t hx = f2u(x), ix = hx & 0x7fffffffu;
+  int id;
+  if (ix >= 0x4c000000u) {  // |x| >= 2^25
+    if (ix > 0x7f800000u) return x + x;
+    return (hx >> 31) ? -atanhi[3] - atanlo[3] : atanhi[3] + atanlo[3];
+  }
+  if (ix < 0x3ee00000u) {  // |x| < 0.4375
+    if (ix < 0x31000000u) return x;  // |x| < 2^-29
+    id = -1;
+  } else {
+    x = std::fabs(x);
+    if (ix < 0x3f980000u) {    // |x| < 1.1875
+      if (ix < 0x3f300000u) {  // 7/16 <= |x| < 11/16
+        id = 0;
+        x = (2.0f * x - 1.0f) / (2.0f + x);
+      } else {                 // 11/16 <= |x| < 19/16
+        id = 1;
+        x = (x - 1.0f) / (x + 1.0f);
+      }
+    } else {
+      if (ix < 0x401c0000u) {  // |x| < 2.4375
+        id = 2;
+        x = (x - 1.5f) / (1.0f + 1.5f * x);
+      } else {                 // 2.4375 <= |x| < 2^25
+        id = 3;
+        x = -1.0f / x;
+      }
+    }
+  }
+  const float z = x * x, w = z * z;
+  const float s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+  const float s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+  if (id < 0) return x - x * (s1 + s2);
+  const float r = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+  return (hx >> 31) ? -r : r;
+}
 inline float oracle_atan2f(float y, float x) {
-  return static_cast<float>(std::atan2(static_cast<double>(y), static_cast<double>(x)));
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+              pi_lo = -8.7422776573e-08f;
+  const int32_t hx = static_cast<int32_t>(f2u(x)), hy = static_cast<int32_t>(f2u(y));
+  const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;  // NaN
+  if (hx == 0x3f800000) return fdlibm_atanf(y);          // x == 1.0
+  const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);     // 2*sign(x) + sign(y)
+  if (iy == 0) {
+    switch (m) {
+      case 0:
+      case 1: return y;  // atan(+-0, +anything) = +-0
+      case 2: return pi + tiny;
+      default: return -pi - tiny;
+    }
+  }
+  if (ix == 0) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  if (ix == 0x7f800000) {
+    if (iy == 0x7f800000) {
+      switch (m) {
+        case 0: return pi_o_4 + tiny;
+        case 1: return -pi_o_4 - tiny;
+        case 2: return 3.0f * pi_o_4 + tiny;
+        default: return -3.0f * pi_o_4 - tiny;
+      }
+    }
+    switch (m) {
+      case 0: return 0.0f;
+      case 1: return -0.0f;
+      case 2: return pi + tiny;
+      default: return -pi - tiny;
+    }
+  }
+  if (iy == 0x7f800000) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  const int32_t k = (iy - ix) >> 23;
+  float z;
+  if (k > 60) z = pi_o_2 + 0.5f * pi_lo;      // |y/x| > 2^60
+  else if (hx < 0 && k < -60) z = 0.0f;       // |y|/x < -2^60
+  else z = fdlibm_atanf(std::fabs(y / x));
+  switch (m) {
+    case 0: return z;
+    case 1: return u2f(f2u(z) ^ 0x80000000u);
+    case 2: return pi - (z - pi_lo);
+    default: return (z - pi_lo) - pi;
+  }
 }
 
 // src/ground_removal.cpp:20 — (360 / 16) is integer division = 22, then * M_PI / 180 in
@@ -334,6 +433,8 @@ extern "C" {
 
 float orc_r2(const orc_detect_params* d) { return tolerance(*d).r2; }
 
+float orc_atan2f(float y, float x) { return oracle_atan2f(y, x); }
+
 int orc_from_msg(const orc_view* v, orc_point* out) {
   if (!v || v->off_x < 0 || v->off_y < 0 || v->off_z < 0 || v->is_bigendian) return 2;
   const uint64_t n = static_cast<uint64_t>(v->width) * v->height;
@@ -510,13 +611,38 @@ int orc_voxel_grid(const orc_point* p, uint32_t n, const orc_detect_params* d, i
   return 0;
 }
 
+static int extract_clusters_impl(const orc_point* vox, uint32_t n_vox, const Tol t, const orc_detect_params* d, int mode,
+                                 int32_t* labels, orc_cluster* clusters, uint32_t cap, uint32_t* n_clusters,
+                                 uint32_t* n_components, uint32_t* members);
+
 int orc_extract_clusters(const orc_point* vox, uint32_t n_vox, const orc_detect_params* d, int mode, int32_t* labels,
                 orc_cluster* clusters, uint32_t cap, uint32_t* n_clusters, uint32_t* n_components,
                 uint32_t* members) {
+  return extract_clusters_impl(vox, n_vox, tolerance(*d), d, mode, labels, clusters, cap, n_clusters, n_components,
+                               members);
+}
+
+int orc_extract_clusters_tol(const orc_point* vox, uint32_t n_vox, double cluster_tolerance, int32_t min_size,
+                             int32_t max_size, int mode, orc_cluster* clusters, uint32_t cap, uint32_t* n_clusters,
+                             uint32_t* members) {
+  // what EuclideanClusterExtraction does with setClusterTolerance(double): static_cast<float>(tolerance) goes to
+  // the search, which squares it in double and narrows again (KdTreeFLANN::radiusSearch)
+  Tol t;
+  t.tol_f = static_cast<float>(cluster_tolerance);
+  t.r2 = static_cast<float>(static_cast<double>(t.tol_f) * static_cast<double>(t.tol_f));
+  orc_detect_params d;
+  std::memset(&d, 0, sizeof(d));
+  d.min_cluster_size = min_size;
+  d.max_cluster_size = max_size;
+  return extract_clusters_impl(vox, n_vox, t, &d, mode, nullptr, clusters, cap, n_clusters, nullptr, members);
+}
+
+static int extract_clusters_impl(const orc_point* vox, uint32_t n_vox, const Tol t, const orc_detect_params* d, int mode,
+                                 int32_t* labels, orc_cluster* clusters, uint32_t cap, uint32_t* n_clusters,
+                                 uint32_t* n_components, uint32_t* members) {
   *n_clusters = 0;
   if (n_components) *n_components = 0;
   if (n_vox == 0) return 0;
-  const Tol t = tolerance(*d);
   std::vector<Cluster> cl;
   uint32_t comps = 0;
   std::vector<int32_t> tmp;

@@ -73,6 +73,9 @@ typedef struct orc_counters {
 /* A.1  pcl::fromROSMsg (src/cone_detection.cpp:151,153; src/ground_removal.cpp:54) */
 int orc_from_msg(const orc_view* v, orc_point* out /* width*height */);
 
+/* the reference's atan2(float, float) = libm atan2f = fdlibm's single-precision routine (not correctly rounded) */
+float orc_atan2f(float y, float x);
+
 /* A.2  src/ground_removal.cpp:58-68 (pass 1) */
 int orc_sector_of(float x, float y);
 void orc_ground_minima(const orc_point* p, uint32_t n, float default_lowest, float* low /*17*/);
@@ -100,6 +103,12 @@ int orc_voxel_grid(const orc_point* p, uint32_t n, const orc_detect_params* d, i
 int orc_extract_clusters(const orc_point* vox, uint32_t n_vox, const orc_detect_params* d, int mode,
                 int32_t* labels, orc_cluster* clusters, uint32_t cap, uint32_t* n_clusters,
                 uint32_t* n_components, uint32_t* members /* n_vox or NULL */);
+
+/* the same with the tolerance handed over as pcl::EuclideanClusterExtraction::setClusterTolerance receives it
+ * (used by oracle/ref_shim, where the reference's own code computes that double) */
+int orc_extract_clusters_tol(const orc_point* vox, uint32_t n_vox, double cluster_tolerance, int32_t min_size,
+                             int32_t max_size, int mode, orc_cluster* clusters, uint32_t cap, uint32_t* n_clusters,
+                             uint32_t* members /* n_vox or NULL */);
 
 /* independent O(V^2) labeller used to cross-check orc_extract_clusters */
 void orc_label_bruteforce(const orc_point* vox, uint32_t n_vox, const orc_detect_params* d,

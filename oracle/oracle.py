@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
         vp, u32 = C.c_void_p, C.c_uint32
         L.orc_from_msg.argtypes = [C.POINTER(View), vp]
         L.orc_sector_of.argtypes = [C.c_float, C.c_float]
+        L.orc_atan2f.argtypes = [C.c_float, C.c_float]
+        L.orc_atan2f.restype = C.c_float
         L.orc_ground_minima.argtypes = [vp, u32, C.c_float, vp]
         L.orc_ground_minima.restype = None
         L.orc_ground_mask.argtypes = [vp, u32, vp, vp]

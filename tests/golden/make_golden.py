@@ -10,6 +10,11 @@
   (/root/reference/scripts/color_classifier_server.py:130-156, plain numpy/scipy, executed
   here from its source) on the 577 real crops and on seeded synthetic crops, including the
   inputs on which it raises (IndexError / interp1d ValueError -> flag, zero image).
+* reference_nodes.npz — PINNED golden: outputs of the reference's own node sources compiled unmodified
+  (oracle/_ref/libconesref.so via oracle/ref_shim, -O0 like the reference's catkin build): the ground node on
+  config-2 scans (sha256 of the published cloud + survivors), the crop lambda's verdict for every point of the
+  threshold-boundary clouds of the three presets, and the clouds the detection node publishes over 5-frame
+  sequences (PCL's VoxelGrid / clustering inside it are the oracle's restatement).
 * cfg*_golden.npz — outputs of the CPU oracle (canonical mode) on seeded synthetic scans.
   The reference has no golden vectors of its own ("parity unpinned"); these pin OUR oracle
   against regressions and give the GPU tests a second, committed target.
@@ -124,6 +129,57 @@ def cone_images():
           "synthetic (raised:", int((syn_raised > 0).sum()), ")")
 
 
+def reference_nodes():
+    """Runs the real reference nodes (oracle/_ref) and stores what they publish."""
+    from cones_perception_b200.params import PRESETS
+    from oracle import ref as R
+    from tests.test_reference_pin import node_params, outside_sector_16
+    from tests.util import boundary_cloud
+    out = {}
+    # ground_removal node: config 2, azimuths of the undefined 17th sector slot left out (Appendix C Q2)
+    for seed in (0, 9):
+        frame = outside_sector_16(scans.generate(scans.config(2), 1, base_seed=seed)[0])
+        node = R.GroundNode()
+        cloud32, meta = node.handle(frame)
+        node.close()
+        kept = int((cloud32[:, 3] == 1.0).sum() if False else np.count_nonzero(np.any(cloud32[:, :3] != 0, axis=1)))
+        out[f"ground_seed{seed}_sha256"] = np.array(hashlib.sha256(cloud32.tobytes()).hexdigest())
+        out[f"ground_seed{seed}_input_sha256"] = np.array(hashlib.sha256(frame.tobytes()).hexdigest())
+        out[f"ground_seed{seed}_kept"] = np.array(kept)
+        out[f"ground_seed{seed}_head"] = cloud32[:256].copy()
+        out[f"ground_seed{seed}_meta"] = np.array(meta)
+    # the crop lambda (src/cone_detection.cpp:191-203), one verdict per point, via single-point clouds
+    for name in ("our", "fsai", "simulation"):
+        d = PRESETS[name]
+        cloud = boundary_cloud(d, seed=2, n_random=2000)
+        cloud = np.ascontiguousarray(cloud[np.isfinite(cloud).all(1)])
+        node = R.DetectNode(service=False, **node_params(d, classify_colors=False, use_points_buffer=False,
+                                                        min_cluster_size=1, max_cluster_size=100000))
+        # a point inside every preset's crop keeps prev_detected_cones non-empty, so a surviving point is published
+        prime = np.array([[max(d.distance_treshold_min, 0.0) + 0.5, 0.0, max(d.level_threshold, -1.0) + 0.3, 1.0]], np.float32)
+        assert len(node.handle(prime)[0]) == 0 and len(node.handle(prime)[0]) == 1
+        keep = np.zeros(len(cloud), np.uint8)
+        for i, p in enumerate(cloud):
+            got = node.handle(p[None, :].copy())
+            keep[i] = len(got[0]) == 1
+            if not keep[i]:
+                node.handle(prime)
+        node.close()
+        out[f"crop_{name}_cloud"] = cloud
+        out[f"crop_{name}_keep"] = keep
+    # cone_detection node over a sequence (config 1, `our` preset), both gate modes
+    cfg = scans.config(1)
+    frames = scans.generate(cfg, 5, base_seed=40)
+    for buffer in (True, False):
+        node = R.DetectNode(service=False, **node_params(cfg.detect, classify_colors=False, use_points_buffer=buffer))
+        for fi, f in enumerate(frames):
+            got = node.handle(f)
+            out[f"detect_buffer{int(buffer)}_frame{fi}"] = got[0]
+        node.close()
+    np.savez_compressed(os.path.join(HERE, "reference_nodes.npz"), **out)
+    print("reference_nodes:", {k: (v.shape if v.ndim else v.item()) for k, v in out.items() if "cloud" not in k and "head" not in k})
+
+
 def synthetic(idx, seed):
     cfg = scans.config(idx)
     frame = scans.generate_config5(1, seed)[0] if idx == 5 else scans.generate(cfg, 1, seed)[0]
@@ -139,5 +195,6 @@ def synthetic(idx, seed):
 if __name__ == "__main__":
     cone_crops()
     cone_images()
+    reference_nodes()
     for idx, seed in ((1, 0), (2, 0), (2, 7), (4, 0), (5, 0)):
         synthetic(idx, seed)

@@ -400,3 +400,67 @@ def test_graph_replay_follows_the_data(mode):
             ctr, off, cl = h.results()
             for f in range(F):
                 assert np.array_equal(cl[off[f]:off[f + 1]].view(np.uint32), exp[name][f].view(np.uint32)), (rep, name, f)
+
+
+def test_exact_path_atan2f_is_the_references(gpu):
+    """The guard-band fallback of the kernels must be libm's atan2f as the reference calls it (fdlibm's routine,
+    not correctly rounded), bit for bit: 1.2 M pairs against the oracle's restatement (itself pinned to libm)."""
+    from tests.test_oracle import atan2_cases
+    y, x = atan2_cases(seed=1)
+    got = gpu.debug_atan2f(y, x)
+    import ctypes as C
+    f = O.lib().orc_atan2f
+    exp = np.array([f(a, b) for a, b in zip(y.tolist(), x.tolist())], np.float32)
+    same = (got.view(np.uint32) == exp.view(np.uint32)) | (np.isnan(got) & np.isnan(exp))
+    assert same.all(), (y[~same][:5], x[~same][:5], got[~same][:5], exp[~same][:5])
+
+
+# ---- the CUDA path against goldens produced by the reference's own compiled node sources ----
+
+def _ref_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_nodes.npz"))
+
+
+@pytest.mark.parametrize("seed", [0, 9])
+def test_ground_remove_matches_reference_node_golden(gpu, seed):
+    """cp_ground_remove against what the real ground_removal node published (sha256 of the 32-byte cloud)."""
+    import hashlib
+    from tests.test_oracle import _outside_sector_16
+    z = _ref_golden()
+    frame = _outside_sector_16(scans.generate(scans.config(2), 1, base_seed=seed)[0])
+    assert hashlib.sha256(frame.tobytes()).hexdigest() == str(z[f"ground_seed{seed}_input_sha256"])
+    out, kept, _ = gpu.ground_remove(PointCloud2.from_xyzi(frame), GroundParams())
+    assert kept == int(z[f"ground_seed{seed}_kept"])
+    assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == str(z[f"ground_seed{seed}_sha256"])
+
+
+@pytest.mark.parametrize("preset", ["our", "fsai", "simulation"])
+def test_crop_matches_reference_lambda_golden(gpu, preset):
+    """The crop kernel's keep bits against the verdicts of the reference's compiled crop lambda on the
+    threshold-boundary clouds (fast paths + guard-band fallbacks, libm atan2f semantics included)."""
+    z = _ref_golden()
+    cloud, keep = z[f"crop_{preset}_cloud"], z[f"crop_{preset}_keep"].astype(bool)
+    ctr, k_off, clusters, offs, taps = run_batch_with_taps(gpu, [cloud], PRESETS[preset], None)
+    got = np.zeros(len(cloud), bool)
+    got[taps["crop_index"][offs["c_off"][0]:offs["c_off"][1]]] = True
+    assert np.array_equal(got, keep)
+
+
+@pytest.mark.parametrize("buffer", [True, False])
+def test_detect_sequence_matches_reference_node_golden(gpu, buffer):
+    """cp_detect + the tracker restatement against the clouds the real cone_detection node published.  The node's
+    voxel means use PCL's (implementation-defined) summation order, the CUDA path the canonical one: same cones,
+    centroids within north_star's 1e-5 m."""
+    from tests.util import TrackerReference
+    z = _ref_golden()
+    cfg = scans.config(1)
+    d = cfg.detect
+    ref = TrackerReference(False, buffer, d.cones_matching_dist_theshold, d.cone_position_extension_length)
+    for fi, f in enumerate(scans.generate(cfg, 5, base_seed=40)):
+        cl, _ = gpu.detect(PointCloud2.from_xyzi(f), d, None)
+        got = np.array([(p[0], p[1]) for p in ref.update([(c["x"], c["y"]) for c in cl])[0]], np.float32).reshape(-1, 2)
+        exp = z[f"detect_buffer{int(buffer)}_frame{fi}"]
+        assert got.shape == exp.shape, fi
+        if len(exp):
+            a, b = got[np.lexsort(got.T)], exp[np.lexsort(exp.T)]
+            assert np.allclose(a, b, rtol=0, atol=1e-5), fi

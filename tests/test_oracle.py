@@ -414,3 +414,86 @@ def test_reconstruct_cone_box_is_inclusive_in_double():
     crop = O.reconstruct_cone(pts, float(cx), float(cy), float(cw))
     assert list(crop["z"]) == [0.0, 2.0, 4.0]           # cloud order kept; NaN and the outer neighbours dropped
     assert list(crop["intensity"]) == [0.0, 20.0, 40.0] and np.all(crop["pad"] == 1.0)
+
+
+def atan2_cases(seed=0, n=400000):
+    """Pairs for the atan2f checks: random bit patterns, lidar-like magnitudes, near-axis ratios, specials."""
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 1 << 32, (n, 2), dtype=np.uint64).astype(np.uint32).view(np.float32)
+    xy = rng.uniform(-60, 60, (n, 2)).astype(np.float32)
+    near = xy.copy()
+    near[: n // 2, 0] *= np.float32(1e-7)
+    near[n // 2:, 1] *= np.float32(1e-7)
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3e38, -3e38, 1.7, -1.7e-8, 2.4375,
+                   0.4375, 0.6875, 1.1875, 2.0 ** 25, 2.0 ** -29], np.float32)
+    grid = np.array([(a, b) for a in sp for b in sp], np.float32)
+    allp = np.concatenate([bits, xy, near, grid])
+    return np.ascontiguousarray(allp[:, 0]), np.ascontiguousarray(allp[:, 1])
+
+
+def test_atan2f_restatement_matches_libm():
+    """The reference's atan2(float, float) is libm atan2f.  The oracle restates fdlibm's routine; on glibc <= 2.40
+    (this image: 2.39; Noetic: 2.31) it must be libm's result bit for bit, including where that is not the
+    correctly rounded value."""
+    import ctypes as C
+    import platform
+    libm = C.CDLL("libm.so.6")
+    libm.atan2f.argtypes = [C.c_float, C.c_float]
+    libm.atan2f.restype = C.c_float
+    ver = tuple(int(v) for v in platform.libc_ver()[1].split(".")[:2])
+    if ver >= (2, 41):
+        pytest.skip("glibc >= 2.41 ships a correctly rounded atan2f; the reference's target (2.31) does not")
+    y, x = atan2_cases(n=60000)
+    f = O.lib().orc_atan2f
+    for a, b in zip(y.tolist(), x.tolist()):
+        got, exp = np.float32(f(a, b)), np.float32(libm.atan2f(a, b))
+        assert got.view(np.uint32) == exp.view(np.uint32) or (np.isnan(got) and np.isnan(exp)), (a, b)
+    # the case that separates it from a correctly rounded atan2: one float BELOW pi/2
+    assert np.float32(f(1.7, np.float32(-1.7e-8))).view(np.uint32) == 0x3fc90fda
+    assert np.float32(np.arctan2(np.float64(np.float32(1.7)), np.float64(np.float32(-1.7e-8)))).view(np.uint32) == 0x3fc90fdb
+
+
+# ---- goldens produced by the reference's own compiled node sources (tests/golden/reference_nodes.npz) ----
+
+def _ref_golden():
+    return np.load(os.path.join(GOLD, "reference_nodes.npz"))
+
+
+def _outside_sector_16(xyzi):
+    az = np.degrees(np.arctan2(xyzi[:, 1].astype(np.float64), xyzi[:, 0].astype(np.float64)))
+    return np.ascontiguousarray(xyzi[~((az > -8.5) & (az < 0.5))])
+
+
+@pytest.mark.parametrize("seed", [0, 9])
+def test_ground_node_matches_reference_golden(seed):
+    z = _ref_golden()
+    frame = _outside_sector_16(scans.generate(scans.config(2), 1, base_seed=seed)[0])
+    assert hashlib.sha256(frame.tobytes()).hexdigest() == str(z[f"ground_seed{seed}_input_sha256"])
+    exp, kept, _, _ = O.ground_node(O.view_of_xyzi(frame), GroundParams())
+    e = np.stack([exp[n] for n in ("x", "y", "z", "pad", "intensity", "c1", "c2", "c3")], 1)
+    assert kept == int(z[f"ground_seed{seed}_kept"])
+    assert hashlib.sha256(np.ascontiguousarray(e).tobytes()).hexdigest() == str(z[f"ground_seed{seed}_sha256"])
+
+
+@pytest.mark.parametrize("preset", ["our", "fsai", "simulation"])
+def test_crop_matches_reference_lambda_golden(preset):
+    """One verdict per point from the reference's compiled crop lambda, on clouds that sit on and one ulp around
+    every threshold (including the x < 0, |y/x| huge points where libm's atan2f is one float off)."""
+    z = _ref_golden()
+    cloud, keep = z[f"crop_{preset}_cloud"], z[f"crop_{preset}_keep"].astype(bool)
+    got = O.crop_mask(O.points32(cloud), PRESETS[preset]).astype(bool)
+    assert np.array_equal(got, keep)
+    assert 100 < keep.sum() < len(keep) - 100
+
+
+@pytest.mark.parametrize("buffer", [True, False])
+def test_detect_sequence_matches_reference_golden(buffer):
+    from tests.util import TrackerReference
+    z = _ref_golden()
+    cfg = scans.config(1)
+    d = cfg.detect
+    ref = TrackerReference(False, buffer, d.cones_matching_dist_theshold, d.cone_position_extension_length)
+    for fi, f in enumerate(scans.generate(cfg, 5, base_seed=40)):
+        cl, _, _ = O.detect(O.view_of_xyzi(f), d, None, O.PCL_FAITHFUL)
+        exp = np.array([(p[0], p[1]) for p in ref.update([(c["x"], c["y"]) for c in cl])[0]], np.float32).reshape(-1, 2)
+        assert np.array_equal(exp.view(np.uint32), z[f"detect_buffer{int(buffer)}_frame{fi}"].view(np.uint32)), fi
