@@ -1,6 +1,9 @@
 // cones_oracle.cpp — CPU ORACLE. TEST INFRASTRUCTURE ONLY (see cones_oracle.h).
 //
-// PARITY UNPINNED: no golden vectors exist in the reference; PCL/FLANN are absent.
+// PARITY: everything the reference wrote itself (ground node, crop, centroid loop, radial extension, box gather)
+// is pinned against the reference's own sources compiled unmodified (oracle/_ref, tests/test_reference_pin.py);
+// the range image against the reference's own numpy code.  PARITY UNPINNED for pcl::VoxelGrid and
+// pcl::EuclideanClusterExtraction: PCL/FLANN are absent and the reference has no golden vectors for them.
 // Every function cites the reference file:line (relative to the upstream repo) and
 // the SURVEY.md appendix paragraph it restates.  Nothing here is copied from the
 // reference or from PCL; the semantics are re-derived from the call sites.

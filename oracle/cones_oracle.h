@@ -7,10 +7,11 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this library.
  * The product (libconesgpu.so) never links, loads or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- *  and its arithmetic lives in PCL 1.10 / FLANN 1.9.1, which
- * are not vendored and not installed here.  The restatement follows the
- * reference call sites cited per function and SURVEY.md Appendix A.
+ * PARITY: the reference ships no tests, golden vectors or fixtures.  What the reference
+ * wrote itself is pinned against its own node sources compiled unmodified (oracle/ref_shim -> oracle/_ref,
+ * tests/test_reference_pin.py, tests/golden/reference_nodes.npz).  PARITY UNPINNED for pcl::VoxelGrid and
+ * pcl::EuclideanClusterExtraction: PCL 1.10 / FLANN 1.9.1 are not vendored and not installed here; those two are
+ * restated from the published algorithms at the reference's call sites.
  */
 #ifndef CONES_ORACLE_H
 #define CONES_ORACLE_H

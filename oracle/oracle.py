@@ -1,8 +1,9 @@
 """ctypes wrapper of the CPU oracle (oracle/cones_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
 
 Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs — never by the product package.  PARITY UNPINNED: the reference ships no golden
-vectors and PCL/FLANN are not available here (see cones_oracle.h).
+legs — never by the product package.  Pinned against the reference's own compiled node sources
+(oracle/ref.py, oracle/_ref) for everything the reference wrote itself; PARITY UNPINNED for PCL's
+VoxelGrid / EuclideanClusterExtraction, which are not available here (see cones_oracle.h).
 """
 from __future__ import annotations
 

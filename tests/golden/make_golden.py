@@ -16,8 +16,8 @@
   threshold-boundary clouds of the three presets, and the clouds the detection node publishes over 5-frame
   sequences (PCL's VoxelGrid / clustering inside it are the oracle's restatement).
 * cfg*_golden.npz — outputs of the CPU oracle (canonical mode) on seeded synthetic scans.
-  The reference has no golden vectors of its own ("parity unpinned"); these pin OUR oracle
-  against regressions and give the GPU tests a second, committed target.
+  The reference has no golden vectors of its own; these pin OUR oracle against regressions (PCL stages
+  included) and give the GPU tests a second, committed target.
 """
 import hashlib
 import os
