@@ -1103,7 +1103,14 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
 constexpr size_t kParallelStageMin = 512ull << 10;
 constexpr size_t kStagePiece = 64ull << 10;
 cp_status stage_parallel(cp_handle* h, const uint8_t* src, size_t total, size_t dst_off, int* ring) {
-  if (!h->copy_pool) h->copy_pool.reset(new CopyPool(h->stage_threads - 1));
+  if (!h->copy_pool) {
+    try {
+      h->copy_pool.reset(new CopyPool(h->stage_threads - 1));
+    } catch (...) {  // no helper threads to be had: nothing may cross the C ABI, copy on the calling thread instead
+      h->stage_threads = 1;
+      return CP_E_STATE;
+    }
+  }
   size_t done = 0;
   while (done < total) {
     const size_t chunk = std::min(kStageChunk, total - done);
@@ -1157,7 +1164,10 @@ cp_status stage_view(cp_handle* h, const cp_cloud_view* v, size_t dst_off, int* 
   }
   // pageable (or row-padded) source: pack through the pinned ring, chunk by chunk
   const size_t total = row_bytes * v->height;
-  if (contiguous && h->stage_threads > 1 && total >= kParallelStageMin) return stage_parallel(h, v->data, total, dst_off, ring);
+  if (contiguous && h->stage_threads > 1 && total >= kParallelStageMin) {
+    const cp_status sp = stage_parallel(h, v->data, total, dst_off, ring);
+    if (sp != CP_E_STATE) return sp;  // CP_E_STATE: the helper pool could not be created; fall through
+  }
   size_t done = 0;
   while (done < total) {
     // a cloud is cut into at least 4 pieces so the host memcpy of piece k+1 overlaps the DMA of piece k
