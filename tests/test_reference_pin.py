@@ -155,9 +155,12 @@ def test_detect_node_crop_thresholds():
     assert 10 < ctr.n_cropped < len(cloud)
 
 
-def test_detect_node_colour_path():
+@pytest.mark.parametrize("intensity_field", [True, False])
+def test_detect_node_colour_path(intensity_field):
     """classify_colors:=true with a deterministic stand-in service: get_reconstructed_cone (:222-238), the
-    colour routing (:287-313, :326-333) and the shortened answer for empty crops are the reference's code."""
+    colour routing (:287-313, :326-333) and the shortened answer for empty crops are the reference's code.
+    Without an intensity field the node fakes one at offset 0 (:142-151), so the crops carry x's bits as
+    intensity — the service's hash sees that too."""
     cfg = scans.config(1)
     d = cfg.detect
     node = R.DetectNode(service=True, **node_params(d, classify_colors=True, use_points_buffer=True))
@@ -179,13 +182,18 @@ def test_detect_node_colour_path():
     ref = TrackerReference(True, True, d.cones_matching_dist_theshold, d.cone_position_extension_length, color_fn=colours)
     coloured = 0
     for f in scans.generate(cfg, 4, base_seed=40):
-        raw["pts"] = O.from_msg(O.view_of_xyzi(f))
-        got = node.handle(f)
-        cl, _, _ = O.detect(O.view_of_xyzi(f), d, None, O.PCL_FAITHFUL)
+        view = O.view_of_xyzi(f)
+        if not intensity_field:
+            view.off_intensity = 0
+        raw["pts"] = O.from_msg(view)
+        got = node.handle(f, with_intensity_field=intensity_field)
+        cl, _, _ = O.detect(view, d, None, O.PCL_FAITHFUL)
         exp = as_arrays(ref.update([(c["x"], c["y"]) for c in cl]))
         for k in range(4):
             assert np.array_equal(got[k].view(np.uint32), exp[k].view(np.uint32)), k
         coloured += sum(len(g) for g in got[1:])
+        if not intensity_field:
+            assert np.array_equal(raw["pts"]["intensity"].view(np.uint32), raw["pts"]["x"].view(np.uint32))
     node.close()
     assert coloured > 10
 
