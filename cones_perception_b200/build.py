@@ -12,6 +12,7 @@ LIB_DIR = os.path.join(HERE, "_lib")
 GPU_LIB = os.path.join(LIB_DIR, "libconesgpu.so")
 SCAN_LIB = os.path.join(HERE, "scangen", "libconesscan.so")
 HOST_LIB = os.path.join(LIB_DIR, "libconeshost.so")
+ROS_SHELL_LIB = os.path.join(LIB_DIR, "libconesrosshell.so")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -67,10 +68,29 @@ def build_host(force: bool = False) -> str:
     return HOST_LIB
 
 
+def build_ros_shell(force: bool = False) -> str:
+    """Test infrastructure: the drop-in node shells (ros_shell/*.cpp) compiled against the stand-in ROS surface and
+    message pump of oracle/ref_shim, so they can be run next to the reference's own nodes (ROS is not installed)."""
+    shell = os.path.join(ROOT, "ros_shell")
+    shim = os.path.join(ROOT, "oracle", "ref_shim")
+    srcs = [os.path.join(shell, f) for f in sorted(os.listdir(shell))]
+    srcs += [os.path.join(shim, "pump_impl.hpp"), os.path.join(shim, "include", "shim_core.hpp"),
+             os.path.join(HERE, "host", "nodes.hpp"), os.path.join(HERE, "host", "pointcloud2.hpp"),
+             os.path.join(ROOT, "include", "conesgpu.h")]
+    if not force and _fresh(ROS_SHELL_LIB, srcs + [GPU_LIB]):
+        return ROS_SHELL_LIB
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", shim, "-I", os.path.join(shim, "include"),
+                    "-I", os.path.join(ROOT, "include"), "-I", shell, "-o", ROS_SHELL_LIB,
+                    os.path.join(shell, "shim_harness.cpp"), "-L" + LIB_DIR, "-lconesgpu", "-Wl,-rpath,$ORIGIN"],
+                   check=True)
+    return ROS_SHELL_LIB
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_gpu(force, verbose)
     build_scangen(force)
     build_host(force)
+    build_ros_shell(force)
 
 
 if __name__ == "__main__":
@@ -78,3 +98,4 @@ if __name__ == "__main__":
     print(GPU_LIB)
     print(SCAN_LIB)
     print(HOST_LIB)
+    print(ROS_SHELL_LIB)

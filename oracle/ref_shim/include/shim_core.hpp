@@ -88,6 +88,8 @@ bool parse(const std::string& s, bool& v);
 
 inline void init(int&, char**, const std::string&) {}
 inline void spin() {}
+inline void shutdown() {}
+inline bool ok() { return true; }
 namespace param {
 template <typename T>
 bool get(const std::string& key, T& value) {
@@ -131,7 +133,10 @@ struct NodeHandle {
   }
 };
 }  // namespace ros
+#include <sstream>
 #define ROS_INFO(...) do { } while (0)
+#define ROS_INFO_STREAM(args) do { std::ostringstream ros_shim_os; ros_shim_os << args; } while (0)
+#define ROS_FATAL(...) do { std::fprintf(stderr, "[ROS_FATAL] " __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
 #define ROS_WARN(...) do { } while (0)
 #define ROS_ERROR(...) do { std::fprintf(stderr, "[ref ROS_ERROR] " __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
 
@@ -145,7 +150,8 @@ struct aligned_allocator {  // 16-byte aligned allocation, like Eigen's
   aligned_allocator(const aligned_allocator<U>&) {}
   T* allocate(std::size_t n) {
     void* p = nullptr;
-    if (posix_memalign(&p, 16, n * sizeof(T) ? n * sizeof(T) : 16) != 0) throw std::bad_alloc();
+    const std::size_t bytes = n * sizeof(T);
+    if (posix_memalign(&p, 16, bytes != 0 ? bytes : 16) != 0) throw std::bad_alloc();
     return static_cast<T*>(p);
   }
   void deallocate(T* p, std::size_t) { free(p); }

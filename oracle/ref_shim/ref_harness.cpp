@@ -18,38 +18,10 @@
 // `float x` (src/cone_detection.cpp:264) start at 0, the behaviour the oracle defines.
 // The 17th sector slot the reference writes past its 16-float vector (Q2) stays undefined here: the tests and
 // golden generators keep azimuths (-8 deg, 0) out of the clouds they feed to this library.
-#include <cstdlib>
-#include <sstream>
-
 #include "../cones_oracle.h"
 #include "shim_core.hpp"
 
-// ---------------------------------------------------------------- ros pump state
-namespace ros {
-namespace shim {
-std::map<std::string, std::string>& params() {
-  static std::map<std::string, std::string> m;
-  return m;
-}
-std::map<std::string, std::function<void(const sensor_msgs::PointCloud2ConstPtr&)>>& subscribers() {
-  static std::map<std::string, std::function<void(const sensor_msgs::PointCloud2ConstPtr&)>> m;
-  return m;
-}
-std::map<std::string, std::vector<sensor_msgs::PointCloud2>>& published() {
-  static std::map<std::string, std::vector<sensor_msgs::PointCloud2>> m;
-  return m;
-}
-std::function<bool(const std::vector<sensor_msgs::PointCloud2>&, std::vector<uint8_t>&)>& color_service() {
-  static std::function<bool(const std::vector<sensor_msgs::PointCloud2>&, std::vector<uint8_t>&)> f;
-  return f;
-}
-bool parse(const std::string& s, std::string& v) { v = s; return true; }
-bool parse(const std::string& s, int& v) { v = std::atoi(s.c_str()); return true; }
-bool parse(const std::string& s, float& v) { v = std::strtof(s.c_str(), nullptr); return true; }
-bool parse(const std::string& s, double& v) { v = std::strtod(s.c_str(), nullptr); return true; }
-bool parse(const std::string& s, bool& v) { v = (s == "1" || s == "true"); return true; }
-}  // namespace shim
-}  // namespace ros
+#include "pump_impl.hpp"
 
 // ---------------------------------------------------------------- pcl stand-ins
 namespace pcl {
@@ -168,51 +140,9 @@ void EuclideanClusterExtraction<PointXYZI>::extract(std::vector<PointIndices>& c
 
 // ---------------------------------------------------------------- C surface for the tests / golden scripts
 namespace {
-typedef std::function<void(const sensor_msgs::PointCloud2ConstPtr&)> Callback;
-
-void set_params(const char* kv) {  // "~name=value;~name=value"
-  ros::shim::params().clear();
-  if (!kv) return;
-  std::stringstream ss(kv);
-  std::string item;
-  while (std::getline(ss, item, ';')) {
-    const size_t eq = item.find('=');
-    if (eq != std::string::npos) ros::shim::params()[item.substr(0, eq)] = item.substr(eq + 1);
-  }
-}
-Callback take_callback() {
-  Callback cb;
-  if (!ros::shim::subscribers().empty()) cb = ros::shim::subscribers().begin()->second;
-  ros::shim::subscribers().clear();
-  return cb;
-}
-sensor_msgs::PointCloud2Ptr make_msg(const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step,
-                                     uint32_t row_step, int32_t ox, int32_t oy, int32_t oz, int32_t oi, uint32_t sec,
-                                     uint32_t nsec) {
-  auto m = std::make_shared<sensor_msgs::PointCloud2>();
-  m->header.seq = 1;
-  m->header.stamp.sec = sec;
-  m->header.stamp.nsec = nsec;
-  m->header.frame_id = "cloud";
-  m->width = width;
-  m->height = height;
-  m->point_step = point_step;
-  m->row_step = row_step;
-  m->is_dense = 1;
-  const char* names[4] = {"x", "y", "z", "intensity"};
-  const int32_t offs[4] = {ox, oy, oz, oi};
-  for (int i = 0; i < 4; ++i)
-    if (offs[i] >= 0) {
-      sensor_msgs::PointField f;
-      f.name = names[i];
-      f.offset = static_cast<uint32_t>(offs[i]);
-      f.datatype = sensor_msgs::PointField::FLOAT32;
-      f.count = 1;
-      m->fields.push_back(f);
-    }
-  m->data.assign(data, data + static_cast<size_t>(row_step) * height);
-  return m;
-}
+using shim_pump::Callback;
+using shim_pump::set_params;
+using shim_pump::take_callback;
 struct GroundNode {
   GroundRemover node;
   Callback cb;
@@ -221,7 +151,6 @@ struct DetectNode {
   ConeDetector node;
   Callback cb;
 };
-const char* kConeTopics[4] = {"cones_cloud_unknowns", "cones_cloud_yellows", "cones_cloud_blues", "cones_cloud_oranges"};
 }  // namespace
 
 extern "C" {
@@ -244,17 +173,8 @@ void ref_ground_destroy(void* p) { delete static_cast<GroundNode*>(p); }
 int64_t ref_ground_handle(void* p, const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step,
                           uint32_t row_step, int32_t ox, int32_t oy, int32_t oz, int32_t oi, uint8_t* out32,
                           uint32_t* out_point_step, uint32_t* out_n_fields, uint32_t* out_stamp_nsec) {
-  auto* g = static_cast<GroundNode*>(p);
-  ros::shim::published().clear();
-  g->cb(make_msg(data, width, height, point_step, row_step, ox, oy, oz, oi, 100, 123456789));
-  auto& q = ros::shim::published()["groundless_cloud"];
-  if (q.empty()) return -1;
-  const sensor_msgs::PointCloud2& m = q.back();
-  if (out32 && !m.data.empty()) std::memcpy(out32, m.data.data(), m.data.size());
-  if (out_point_step) *out_point_step = m.point_step;
-  if (out_n_fields) *out_n_fields = static_cast<uint32_t>(m.fields.size());
-  if (out_stamp_nsec) *out_stamp_nsec = m.header.stamp.nsec;
-  return static_cast<int64_t>(m.width) * m.height;
+  return shim_pump::pump_ground(static_cast<GroundNode*>(p)->cb, data, width, height, point_step, row_step, ox, oy, oz,
+                                oi, out32, out_point_step, out_n_fields, out_stamp_nsec);
 }
 
 // forced_color: < 0 -> the service call fails (ROS_ERROR path); otherwise a deterministic stand-in for the
@@ -263,26 +183,7 @@ void* ref_detect_create(const char* params, int service_mode) {
   set_params(params);
   auto* d = new DetectNode();
   d->cb = take_callback();
-  if (service_mode >= 0)
-    ros::shim::color_service() = [](const std::vector<sensor_msgs::PointCloud2>& crops, std::vector<uint8_t>& colors) {
-      for (const auto& c : crops) {
-        const size_t n = static_cast<size_t>(c.width) * c.height;
-        if (n == 0) continue;
-        uint64_t h = 1469598103934665603ull;
-        for (size_t i = 0; i < n; ++i) {
-          const uint8_t* src = c.data.data() + i * c.point_step;
-          float v[4];
-          std::memcpy(&v[0], src + 0, 4);
-          std::memcpy(&v[1], src + 4, 4);
-          std::memcpy(&v[2], src + 8, 4);
-          std::memcpy(&v[3], src + 16, 4);
-          const uint8_t* b = reinterpret_cast<const uint8_t*>(v);
-          for (size_t k = 0; k < sizeof(v); ++k) h = (h ^ b[k]) * 1099511628211ull;
-        }
-        colors.push_back(static_cast<uint8_t>(1 + h % 3));
-      }
-      return true;
-    };
+  if (service_mode >= 0) ros::shim::color_service() = shim_pump::hash_color_service;
   else
     ros::shim::color_service() = nullptr;
   return d;
@@ -294,24 +195,8 @@ void ref_detect_destroy(void* p) { delete static_cast<DetectNode*>(p); }
 int ref_detect_handle(void* p, const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step,
                       uint32_t row_step, int32_t ox, int32_t oy, int32_t oz, int32_t oi, float* out_xy,
                       uint32_t* counts, uint32_t cap, uint32_t* out_point_step, uint32_t* out_n_fields) {
-  auto* d = static_cast<DetectNode*>(p);
-  ros::shim::published().clear();
-  d->cb(make_msg(data, width, height, point_step, row_step, ox, oy, oz, oi, 100, 123456789));
-  for (int k = 0; k < 4; ++k) {
-    auto& q = ros::shim::published()[kConeTopics[k]];
-    counts[k] = 0;
-    if (q.empty()) continue;
-    const sensor_msgs::PointCloud2& m = q.back();
-    const uint32_t n = m.width * m.height;
-    counts[k] = n;
-    if (n > cap) return 3;
-    for (uint32_t i = 0; i < n; ++i) {
-      std::memcpy(&out_xy[(static_cast<size_t>(k) * cap + i) * 2], m.data.data() + static_cast<size_t>(i) * m.point_step, 8);
-    }
-    if (out_point_step) *out_point_step = m.point_step;
-    if (out_n_fields) *out_n_fields = static_cast<uint32_t>(m.fields.size());
-  }
-  return 0;
+  return shim_pump::pump_detect(static_cast<DetectNode*>(p)->cb, data, width, height, point_step, row_step, ox, oy, oz,
+                                oi, out_xy, counts, cap, out_point_step, out_n_fields);
 }
 
 }  // extern "C"

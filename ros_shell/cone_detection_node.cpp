@@ -2,7 +2,8 @@
 // (src/cone_detection.cpp): same node name, subscriber (queue 2), four publishers (queue 1),
 // private parameter names (typos included) and colour service; crop -> VoxelGrid -> clustering
 // -> centroid mean run on the GPU through cones_host::ConeDetector -> cp_detect.
-// Build on a ROS Noetic box; not compiled in the build container.
+// Build on a ROS Noetic box.  In the build container (no ROS) it is compiled against the
+// stand-in ROS surface of oracle/ref_shim and run next to the reference's own node (ros_shell/shim_harness.cpp).
 #include "cones_perception/ClassifyColorSrv.h"
 #include "ros_bridge.hpp"
 

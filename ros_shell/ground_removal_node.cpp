@@ -1,7 +1,8 @@
 // ground_removal_node.cpp — drop-in for the reference's `ground_removal` executable
 // (src/ground_removal.cpp): same node name, topics, queue sizes and private parameters; the
 // handler body runs on the GPU through cones_host::GroundRemover -> cp_ground_remove.
-// Build on a ROS Noetic box; not compiled in the build container.
+// Build on a ROS Noetic box.  In the build container (no ROS) it is compiled against the
+// stand-in ROS surface of oracle/ref_shim and run next to the reference's own node (ros_shell/shim_harness.cpp).
 #include "ros_bridge.hpp"
 
 class GroundRemoverNode {

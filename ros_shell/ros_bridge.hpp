@@ -1,5 +1,6 @@
 // ros_bridge.hpp — sensor_msgs/PointCloud2 <-> cones_host::PointCloud2 (1:1 field copy).
-// Needs ROS Noetic headers; it is NOT compiled in the build container (no ROS there).
+// Needs ROS Noetic headers — or, for the tests in the build container (no ROS there), the stand-in headers of
+// oracle/ref_shim/include, which provide the same names.
 #pragma once
 #include <ros/ros.h>
 #include <sensor_msgs/PointCloud2.h>

@@ -237,3 +237,91 @@ def test_cone_detector_matches_real_reference_node(host, buffer):
         if len(exp):
             assert np.allclose(got[np.lexsort(got.T)], exp[np.lexsort(exp.T)], rtol=0, atol=1e-5), fi
     host.ch_detector_destroy(det)
+
+
+# ---- drop-in check at the message level: the reference's own nodes and this repository's node shells behind the
+# ---- same in-process ROS pump (oracle/ref_shim), fed the same PointCloud2 messages
+
+def _shell_lib():
+    from cones_perception_b200.build import ROS_SHELL_LIB
+    lib = C.CDLL(ROS_SHELL_LIB)
+    vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int32
+    lib.shell_last_error.restype = C.c_char_p
+    lib.shell_ground_create.argtypes = [C.c_char_p]
+    lib.shell_ground_create.restype = vp
+    lib.shell_ground_destroy.argtypes = [vp]
+    lib.shell_ground_handle.argtypes = [vp, vp, u32, u32, u32, u32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.shell_ground_handle.restype = C.c_int64
+    lib.shell_detect_create.argtypes = [C.c_char_p, C.c_int]
+    lib.shell_detect_create.restype = vp
+    lib.shell_detect_destroy.argtypes = [vp]
+    lib.shell_detect_handle.argtypes = [vp, vp, u32, u32, u32, u32, i32, i32, i32, i32, vp, vp, u32, vp, vp]
+    return lib
+
+
+@pytest.mark.gpu
+def test_ground_removal_node_shell_is_a_drop_in():
+    """Same message into the reference's ground_removal node (its own source, oracle/_ref) and into
+    ros_shell/ground_removal_node.cpp on libconesgpu: the published groundless_cloud must be identical —
+    data bytes, point_step, field count, microsecond-truncated stamp."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libconesref.so not available")
+    from tests.test_reference_pin import outside_sector_16
+    shell = _shell_lib()
+    node = shell.shell_ground_create(b"")
+    assert node, shell.shell_last_error()
+    real = R.GroundNode()
+    for seed in (0, 3):
+        f = outside_sector_16(scans.generate(scans.config(2), 1, base_seed=seed)[0])
+        n = len(f)
+        exp, emeta = real.handle(f)
+        out = np.zeros((n, 8), np.float32)
+        step, nf, nsec = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        got = shell.shell_ground_handle(node, f.ctypes.data, n, 1, 16, 16 * n, 0, 4, 8, 12, out.ctypes.data,
+                                        C.byref(step), C.byref(nf), C.byref(nsec))
+        assert got == n
+        assert np.array_equal(out.view(np.uint32), exp.view(np.uint32))
+        assert (step.value, nf.value, nsec.value) == emeta
+    real.close()
+    shell.shell_ground_destroy(node)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("classify,buffer", [(False, True), (False, False), (True, True)])
+def test_cone_detection_node_shell_is_a_drop_in(classify, buffer):
+    """Same 5-message sequence into the reference's cone_detection node and into
+    ros_shell/cone_detection_node.cpp: the same cones on the same four topics (centroids within north_star's
+    1e-5 m: PCL's voxel summation order is implementation-defined), same message layout.  With classify_colors the
+    stand-in colour service hashes every crop it is sent, so the routing only matches if the crops do."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libconesref.so not available")
+    from tests.test_reference_pin import node_params
+    cfg = scans.config(1)
+    p = node_params(cfg.detect, classify_colors=classify, use_points_buffer=buffer)
+    real = R.DetectNode(service=classify, **p)
+    shell = _shell_lib()
+    node = shell.shell_detect_create(R._params(p), 0 if classify else -1)
+    assert node, shell.shell_last_error()
+    total = 0
+    for fi, f in enumerate(scans.generate(cfg, 5, base_seed=40)):
+        exp = real.handle(f)
+        n = len(f)
+        out = np.zeros((4, CAP, 2), np.float32)
+        counts = np.zeros(4, np.uint32)
+        step, nf = C.c_uint32(), C.c_uint32()
+        rc = shell.shell_detect_handle(node, f.ctypes.data, n, 1, 16, 16 * n, 0, 4, 8, 12, out.ctypes.data,
+                                       counts.ctypes.data, CAP, C.byref(step), C.byref(nf))
+        assert rc == 0
+        for k in range(4):
+            got = out[k, :counts[k]]
+            assert got.shape == exp[k].shape, (fi, k, counts.tolist(), [len(e) for e in exp])
+            if len(got):
+                assert np.allclose(got[np.lexsort(got.T)], exp[k][np.lexsort(exp[k].T)], rtol=0, atol=1e-5), (fi, k)
+        total += int(counts.sum())
+        if counts.sum():
+            assert step.value == 32 and nf.value == 4
+    assert total > 20
+    real.close()
+    shell.shell_detect_destroy(node)
