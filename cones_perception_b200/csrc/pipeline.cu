@@ -857,16 +857,20 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
 template <int CMAX, int VMAX, int MODE, int T>
 void launch_frame_kernel(cp_handle* h, const FrameArgs& fa) {
   const size_t smem = sizeof(FrameSmem<CMAX, VMAX, T>);
-  static bool attr_set = false;
-  static int per_sm = 1;
-  if (!attr_set) {
+  // function attributes are per device: a process may hold handles on several GPUs
+  constexpr int kMaxDevices = 64;
+  static int per_sm_dev[kMaxDevices] = {0};  // 0 = not set up on that device yet
+  const int dev = (h->cfg.device >= 0 && h->cfg.device < kMaxDevices) ? h->cfg.device : 0;
+  if (per_sm_dev[dev] == 0) {
+    int per_sm = 1;
     cudaFuncSetAttribute(frame_backend_kernel<CMAX, VMAX, MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_backend_kernel<CMAX, VMAX, MODE, T>, T, smem) !=
             cudaSuccess || per_sm < 1)
       per_sm = 1;
-    attr_set = true;
+    per_sm_dev[dev] = per_sm;
   }
+  const int per_sm = per_sm_dev[dev];
   const u32 grid = std::min<u32>(fa.n_frames, (u32)h->sms * (u32)per_sm);
   frame_backend_kernel<CMAX, VMAX, MODE, T><<<grid, T, smem, h->stream>>>(fa);
   h->launches++;

@@ -464,3 +464,20 @@ def test_detect_sequence_matches_reference_node_golden(gpu, buffer):
         if len(exp):
             a, b = got[np.lexsort(got.T)], exp[np.lexsort(exp.T)]
             assert np.allclose(a, b, rtol=0, atol=1e-5), fi
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_two_devices_in_one_process(mode):
+    """One process holding handles on two GPUs (kernel function attributes are per device): the larger
+    shared-memory variants of the per-frame kernel must work on both."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    cfg = scans.config(3)
+    frames = list(scans.generate(cfg, 3, base_seed=500))
+    exp = [O.detect(O.view_of_xyzi(f), cfg.detect, cfg.ground, O.CANONICAL)[0] for f in frames]
+    for dev in (0, 1, 0):
+        with api.ConesGpu(max_points=3 * cfg.points_per_frame, max_frames=3, device=dev, back_mode=mode) as h:
+            ctr, off, cl = h.detect_batch([PointCloud2.from_xyzi(f) for f in frames], cfg.detect, cfg.ground)
+        for f in range(3):
+            assert np.array_equal(cl[off[f]:off[f + 1]].view(np.uint32), exp[f].view(np.uint32)), (dev, f)
