@@ -1737,6 +1737,7 @@ cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_
 
 cp_status cp_sync(cp_handle* h) {
   if (!h) return CP_E_PARAM;
+  CK(cudaSetDevice(h->cfg.device));  // it may launch (result publish, back-half retry): be on the handle's device
   if (h->ran && !h->fetched) {
     cp_status sf = enqueue_result_fetch(h);
     if (sf) return sf;
@@ -2087,6 +2088,7 @@ void* cp_stream(cp_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 cp_status cp_debug_tap(cp_handle* h, cp_tap which, void* out, uint64_t cap_bytes, uint64_t* count) {
   if (!h || !out || !count) return CP_E_PARAM;
+  CK(cudaSetDevice(h->cfg.device));
   if (!h->ran) {
     h->err = "cp_debug_tap before a batch ran";
     return CP_E_STATE;

@@ -481,3 +481,27 @@ def test_two_devices_in_one_process(mode):
             ctr, off, cl = h.detect_batch([PointCloud2.from_xyzi(f) for f in frames], cfg.detect, cfg.ground)
         for f in range(3):
             assert np.array_equal(cl[off[f]:off[f + 1]].view(np.uint32), exp[f].view(np.uint32)), (dev, f)
+
+
+def test_interleaved_handles_on_two_devices():
+    """Two handles on different GPUs used alternately from one thread: every entry point that may launch
+    (cp_sync publishes results with a kernel) must select its handle's device first."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    cfg = scans.config(2)
+    fa, fb = scans.generate(cfg, 1, base_seed=600)[0], scans.generate(cfg, 1, base_seed=601)[0]
+    ea = O.detect(O.view_of_xyzi(fa), cfg.detect, cfg.ground, O.CANONICAL)[0]
+    eb = O.detect(O.view_of_xyzi(fb), cfg.detect, cfg.ground, O.CANONICAL)[0]
+    with api.ConesGpu(max_points=len(fa), device=0) as a, api.ConesGpu(max_points=len(fb), device=1) as b:
+        for _ in range(4):
+            a.set_host_input([PointCloud2.from_xyzi(fa)])
+            b.set_host_input([PointCloud2.from_xyzi(fb)])
+            a.run(cfg.detect, cfg.ground)
+            b.run(cfg.detect, cfg.ground)
+            a.sync()                         # current device is 1 here
+            _, _, ca = a.results()
+            b.sync()
+            _, _, cb = b.results()
+            assert np.array_equal(ca.view(np.uint32), ea.view(np.uint32))
+            assert np.array_equal(cb.view(np.uint32), eb.view(np.uint32))
