@@ -1325,6 +1325,21 @@ cp_status enqueue_raster(cp_handle* h, u32 n_cones) {
   return CP_OK;
 }
 
+// Nothing may propagate through the C ABI: host-side allocation failures and the like become a status.
+static cp_status abi_exception(cp_handle* h) noexcept {
+  try {
+    throw;
+  } catch (const std::bad_alloc&) {
+    try { if (h) h->err = "out of host memory"; } catch (...) {}
+    return CP_E_NOMEM;
+  } catch (const std::exception& e) {
+    try { if (h) h->err = std::string("internal error: ") + e.what(); } catch (...) {}
+    return CP_E_STATE;
+  } catch (...) {
+    return CP_E_STATE;
+  }
+}
+
 extern "C" {
 
 const char* cp_strerror(cp_status s) {
@@ -1346,7 +1361,7 @@ uint32_t cp_abi_version(void) { return kAbiVersion; }
 static std::string g_create_error;
 const char* cp_create_error(void) { return g_create_error.c_str(); }
 
-cp_status cp_create(cp_handle** out, const cp_config* cfg) {
+cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
   if (!out || !cfg) return CP_E_PARAM;
   *out = nullptr;
   if (cfg->max_points == 0 || cfg->max_frames == 0 || cfg->max_points >= (1ull << 31)) {
@@ -1520,6 +1535,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) {
   memset(h->h_ctl, 0, sizeof(Ctl));
   *out = h;
   return CP_OK;
+} catch (...) {
+  return abi_exception(nullptr);
 }
 
 void cp_destroy(cp_handle* h) {
@@ -1547,7 +1564,7 @@ void cp_destroy(cp_handle* h) {
 
 cp_status cp_batch_set_device_input(cp_handle* h, const void* d_points, uint32_t n_frames,
                                     const uint32_t* frame_points, uint32_t point_step, int32_t off_x,
-                                    int32_t off_y, int32_t off_z, int32_t off_intensity) {
+                                    int32_t off_y, int32_t off_z, int32_t off_intensity) try {
   if (!h) return CP_E_PARAM;
   if (!d_points || !frame_points) {
     h->err = "NULL device pointer or frame_points";
@@ -1568,9 +1585,11 @@ cp_status cp_batch_set_device_input(cp_handle* h, const void* d_points, uint32_t
   h->batch_ready = true;
   h->ran = false;
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_batch_set_host_input(cp_handle* h, const cp_cloud_view* frames, uint32_t n_frames) {
+cp_status cp_batch_set_host_input(cp_handle* h, const cp_cloud_view* frames, uint32_t n_frames) try {
   if (!h) return CP_E_PARAM;
   if (!frames || n_frames == 0) {
     h->err = "NULL frames or n_frames == 0";
@@ -1641,6 +1660,8 @@ cp_status cp_batch_set_host_input(cp_handle* h, const cp_cloud_view* frames, uin
   h->batch_ready = true;
   h->ran = false;
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 // A run is replayed from a CUDA graph when it repeats the previous one exactly (same batch
@@ -1672,7 +1693,7 @@ static RunKey make_key(const cp_handle* h, const cp_detect_params* d, const cp_g
   return k;
 }
 
-cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_params* ground) {
+cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_params* ground) try {
   if (!h) return CP_E_PARAM;
   CK(cudaSetDevice(h->cfg.device));
   const bool eligible = h->use_graph && d && h->batch_ready && !h->taps && !h->stage_timing && h->hg.uniform_n != 0;
@@ -1733,9 +1754,11 @@ cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_
   cudaEventRecord(h->ev1, h->stream);
   h->ran = true;
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_sync(cp_handle* h) {
+cp_status cp_sync(cp_handle* h) try {
   if (!h) return CP_E_PARAM;
   CK(cudaSetDevice(h->cfg.device));  // it may launch (result publish, back-half retry): be on the handle's device
   if (h->ran && !h->fetched) {
@@ -1761,10 +1784,12 @@ cp_status cp_sync(cp_handle* h) {
     CK(cudaGetLastError());
   }
   return device_errors(h);
+} catch (...) {
+  return abi_exception(h);
 }
 
 cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* cluster_offsets, cp_cluster* out,
-                           uint64_t cap, uint64_t* n_total) {
+                           uint64_t cap, uint64_t* n_total) try {
   if (!h) return CP_E_PARAM;
   if (!h->ran) {
     h->err = "cp_batch_results before cp_batch_run";
@@ -1792,20 +1817,24 @@ cp_status cp_batch_results(cp_handle* h, cp_frame_counters* counters, uint32_t* 
     }
   }
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 cp_status cp_detect_batch(cp_handle* h, const cp_cloud_view* frames, uint32_t n_frames, const cp_detect_params* d,
                           const cp_ground_params* ground, cp_frame_counters* counters, uint32_t* cluster_offsets,
-                          cp_cluster* out, uint64_t cap, uint64_t* n_total) {
+                          cp_cluster* out, uint64_t cap, uint64_t* n_total) try {
   cp_status st = cp_batch_set_host_input(h, frames, n_frames);
   if (st) return st;
   st = cp_batch_run(h, d, ground);
   if (st) return st;
   return cp_batch_results(h, counters, cluster_offsets, out, cap, n_total);
+} catch (...) {
+  return abi_exception(h);
 }
 
 cp_status cp_detect(cp_handle* h, const cp_cloud_view* in, const cp_detect_params* d, const cp_ground_params* ground,
-                    cp_cluster* out, uint32_t cap, uint32_t* n_clusters, cp_frame_counters* counters) {
+                    cp_cluster* out, uint32_t cap, uint32_t* n_clusters, cp_frame_counters* counters) try {
   if (!h) return CP_E_PARAM;
   if (!n_clusters) {
     h->err = "NULL n_clusters";
@@ -1815,10 +1844,12 @@ cp_status cp_detect(cp_handle* h, const cp_cloud_view* in, const cp_detect_param
   cp_status st = cp_detect_batch(h, in, 1, d, ground, counters, nullptr, out, cap, &total);
   *n_clusters = (uint32_t)total;
   return st;
+} catch (...) {
+  return abi_exception(h);
 }
 
 cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_ground_params* g, void* out_xyzi32,
-                           uint32_t* n_kept, float* low17) {
+                           uint32_t* n_kept, float* low17) try {
   if (!h) return CP_E_PARAM;
   if (!g || !out_xyzi32) {
     h->err = "NULL ground params or output";
@@ -1860,9 +1891,11 @@ cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_groun
     for (int s = 0; s < kNSect; ++s) low17[s] = ord2f(h->h_frame_u32[s]);
   h->ran = false;
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_last_run_ms(cp_handle* h, float* ms) {
+cp_status cp_last_run_ms(cp_handle* h, float* ms) try {
   if (!h || !ms) return CP_E_PARAM;
   if (!h->ran) {
     h->err = "no batch has run";
@@ -1871,19 +1904,23 @@ cp_status cp_last_run_ms(cp_handle* h, float* ms) {
   CK(cudaEventSynchronize(h->ev1));
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_set_stage_timing(cp_handle* h, int on) {
+cp_status cp_set_stage_timing(cp_handle* h, int on) try {
   if (!h) return CP_E_PARAM;
   h->stage_timing = on != 0;
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 __global__ void debug_atan2f_kernel(const float* __restrict__ y, const float* __restrict__ x, u32 n, float* __restrict__ out) {
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = atan2_exact(y[i], x[i]);
 }
 
-cp_status cp_debug_atan2f(cp_handle* h, const float* y, const float* x, uint32_t n, float* out) {
+cp_status cp_debug_atan2f(cp_handle* h, const float* y, const float* x, uint32_t n, float* out) try {
   if (!h || !y || !x || !out) return CP_E_PARAM;
   if (n == 0) return CP_OK;
   CK(cudaSetDevice(h->cfg.device));
@@ -1902,9 +1939,11 @@ cp_status cp_debug_atan2f(cp_handle* h, const float* y, const float* x, uint32_t
   CK(e);
   CK(cudaGetLastError());
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_debug_timeline(cp_handle* h, const cp_handle* base, float out_ms[6]) {
+cp_status cp_debug_timeline(cp_handle* h, const cp_handle* base, float out_ms[6]) try {
   if (!h || !out_ms) return CP_E_PARAM;
   if (!h->ran || !h->stage_timing || !h->ran_ground || h->ran_fused || h->ran_cluster) {
     h->err = "cp_debug_timeline needs cp_set_stage_timing(1) and a two-kernel run with ground removal";
@@ -1917,9 +1956,11 @@ cp_status cp_debug_timeline(cp_handle* h, const cp_handle* base, float out_ms[6]
   const cudaEvent_t ev[6] = {h->ev0, h->ev_k[0], h->ev_k[1], h->ev_k[2], h->ev_k[3], h->ev1};
   for (int i = 0; i < 6; ++i) CK(cudaEventElapsedTime(&out_ms[i], t0, ev[i]));
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms) {
+cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms) try {
   if (!h || !ms) return CP_E_PARAM;
   if (!h->ran || !h->stage_timing) {
     h->err = "cp_stage_ms needs cp_set_stage_timing(1) before the run";
@@ -1958,10 +1999,12 @@ cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms) {
     return CP_E_PARAM;
   }
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 cp_status cp_device_results(cp_handle* h, const void** d_clusters, const uint32_t** d_cluster_offsets,
-                            const uint32_t** d_n_clusters) {
+                            const uint32_t** d_n_clusters) try {
   if (!h) return CP_E_PARAM;
   if (!h->ran) {
     h->err = "cp_device_results before cp_batch_run";
@@ -1971,9 +2014,11 @@ cp_status cp_device_results(cp_handle* h, const void** d_clusters, const uint32_
   if (d_cluster_offsets) *d_cluster_offsets = h->d_k_off;
   if (d_n_clusters) *d_n_clusters = &h->d_ctl->n_clusters;
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_gather_create(cp_handle* h, uint32_t world, uint32_t slot_words, uint8_t handle_out[64]) {
+cp_status cp_gather_create(cp_handle* h, uint32_t world, uint32_t slot_words, uint8_t handle_out[64]) try {
   if (!h || !handle_out || world == 0 || slot_words == 0 || slot_words % 4) return CP_E_PARAM;
   CK(cudaSetDevice(h->cfg.device));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
@@ -2006,9 +2051,11 @@ cp_status cp_gather_create(cp_handle* h, uint32_t world, uint32_t slot_words, ui
   if (st) return st;
   g.open = true;
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, uint32_t world, uint32_t slot_words) {
+cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, uint32_t world, uint32_t slot_words) try {
   if (!h || !handle || rank == 0 || rank >= world || slot_words == 0 || slot_words % 4) return CP_E_PARAM;
   CK(cudaSetDevice(h->cfg.device));
   auto& g = h->gather;
@@ -2034,6 +2081,8 @@ cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, 
   CK(cudaMemset(g.d_seq, 0, sizeof(u32)));
   g.open = true;
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 uint32_t cp_gather_seq(const cp_handle* h) { return h ? h->gather.seq : 0; }
@@ -2041,7 +2090,7 @@ uint32_t cp_gather_seq(const cp_handle* h) { return h ? h->gather.seq : 0; }
 // rows of 32 points the keep-mask pass read in the last synchronised run (others were skipped)
 uint64_t cp_last_rows_loaded(const cp_handle* h) { return h ? h->h_ctl->rows_loaded : 0; }
 
-cp_status cp_gather_wait(cp_handle* h, uint32_t seq, uint32_t timeout_ms) {
+cp_status cp_gather_wait(cp_handle* h, uint32_t seq, uint32_t timeout_ms) try {
   if (!h) return CP_E_PARAM;
   auto& g = h->gather;
   if (!g.open || !g.owner) {
@@ -2062,9 +2111,11 @@ cp_status cp_gather_wait(cp_handle* h, uint32_t seq, uint32_t timeout_ms) {
     struct timespec ts = {0, 100000};
     nanosleep(&ts, nullptr);
   }
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_gather_read(cp_handle* h, uint32_t seq, void* out_host, uint64_t cap_bytes) {
+cp_status cp_gather_read(cp_handle* h, uint32_t seq, void* out_host, uint64_t cap_bytes) try {
   if (!h || !out_host) return CP_E_PARAM;
   auto& g = h->gather;
   if (!g.open || !g.owner) {
@@ -2081,12 +2132,14 @@ cp_status cp_gather_read(cp_handle* h, uint32_t seq, void* out_host, uint64_t ca
   CK(cudaMemcpy(out_host, g.base + kGatherFlagWords + (size_t)parity * g.world * g.slot_words, bytes,
                 cudaMemcpyDeviceToHost));
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 uint32_t cp_last_launch_count(const cp_handle* h) { return h ? h->launches : 0; }
 void* cp_stream(cp_handle* h) { return h ? (void*)h->stream : nullptr; }
 
-cp_status cp_debug_tap(cp_handle* h, cp_tap which, void* out, uint64_t cap_bytes, uint64_t* count) {
+cp_status cp_debug_tap(cp_handle* h, cp_tap which, void* out, uint64_t cap_bytes, uint64_t* count) try {
   if (!h || !out || !count) return CP_E_PARAM;
   CK(cudaSetDevice(h->cfg.device));
   if (!h->ran) {
@@ -2137,9 +2190,11 @@ cp_status cp_debug_tap(cp_handle* h, cp_tap which, void* out, uint64_t cap_bytes
   if (n) CK(cudaMemcpy(out, src, n * esz, cudaMemcpyDeviceToHost));
   *count = n;
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
-cp_status cp_debug_sort(cp_handle* h, uint64_t* keys, uint32_t* vals, uint32_t n, uint32_t bits) {
+cp_status cp_debug_sort(cp_handle* h, uint64_t* keys, uint32_t* vals, uint32_t n, uint32_t bits) try {
   if (!h || !keys || !vals) return CP_E_PARAM;
   if (n > h->cap_v || bits > 64) {
     h->err = "cp_debug_sort: n exceeds max_voxels or bits > 64";
@@ -2161,6 +2216,8 @@ cp_status cp_debug_sort(cp_handle* h, uint64_t* keys, uint32_t* vals, uint32_t n
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 // pinned mirror of the colour-path results: [offsets n+1][flags n][images 180 n][first crop points], so that a
@@ -2193,7 +2250,7 @@ static float4* pin_pts(cp_handle* h, u32 n) {
 
 cp_status cp_cone_crops(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame, const cp_cone_center* centers,
                         uint32_t n_centers, float cone_width, uint32_t* crop_offsets, float* crop_xyzi,
-                        uint32_t cap_points) {
+                        uint32_t cap_points) try {
   if (!h) return CP_E_PARAM;
   if (!crop_offsets) {
     h->err = "NULL crop_offsets";
@@ -2224,10 +2281,12 @@ cp_status cp_cone_crops(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame
     }
   }
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 cp_status cp_cone_images(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame, const cp_cone_center* centers,
-                         uint32_t n_centers, float cone_width, uint8_t* images, uint32_t* counts, uint32_t* flags) {
+                         uint32_t n_centers, float cone_width, uint8_t* images, uint32_t* counts, uint32_t* flags) try {
   if (!h) return CP_E_PARAM;
   if (n_centers && !images) {
     h->err = "NULL images";
@@ -2265,10 +2324,12 @@ cp_status cp_cone_images(cp_handle* h, const cp_cloud_view* cloud, uint32_t fram
   if (counts)
     for (u32 c = 0; c < n_centers; ++c) counts[c] = pin_off(h)[c + 1] - pin_off(h)[c];
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 cp_status cp_rasterize_crops(cp_handle* h, const float* crop_xyzi, const uint32_t* crop_offsets, uint32_t n_crops,
-                             uint8_t* images, uint32_t* flags) {
+                             uint8_t* images, uint32_t* flags) try {
   if (!h) return CP_E_PARAM;
   if (!crop_offsets || (n_crops && !images)) {
     h->err = "NULL crop_offsets or images";
@@ -2299,6 +2360,8 @@ cp_status cp_rasterize_crops(cp_handle* h, const float* crop_xyzi, const uint32_
   }
   CK(cudaStreamSynchronize(h->stream));
   return CP_OK;
+} catch (...) {
+  return abi_exception(h);
 }
 
 }  // extern "C"
