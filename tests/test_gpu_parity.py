@@ -505,3 +505,19 @@ def test_interleaved_handles_on_two_devices():
             _, _, cb = b.results()
             assert np.array_equal(ca.view(np.uint32), ea.view(np.uint32))
             assert np.array_equal(cb.view(np.uint32), eb.view(np.uint32))
+
+
+@pytest.mark.parametrize("threads,nt", [("1", "0"), ("1", "1"), ("2", "1"), ("4", "0"), ("4", "1"), ("7", "1")])
+def test_pageable_staging_variants(threads, nt):
+    """Pageable host clouds go through the pinned staging ring: serial or shared with helper threads, plain or
+    non-temporal stores, one chunk (2 MB frame) or several (config 4's 42 MB frame exceeds the 32 MB ring half)."""
+    env = {"CONESGPU_STAGE_THREADS": threads, "CONESGPU_STAGE_NT": nt}
+    for idx in (2, 4):
+        cfg = scans.config(idx)
+        frame = scans.generate(cfg, 1, base_seed=11)[0]
+        frame = np.ascontiguousarray(frame[3:])            # odd point count, source not 64-byte aligned
+        exp, _, _ = O.detect(O.view_of_xyzi(frame), cfg.detect, cfg.ground, O.CANONICAL)
+        with api.ConesGpu(max_points=len(frame), max_frames=1, env=env) as h:
+            for _ in range(2):
+                cl, _ = h.detect(PointCloud2.from_xyzi(frame), cfg.detect, cfg.ground, cap=1 << 16)
+                assert np.array_equal(cl.view(np.uint32), exp.view(np.uint32)), (idx, threads, nt)
