@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "cp_debug_tap", "cp_debug_sort", "cp_set_stage_timing", "cp_stage_ms", "cp_debug_timeline", "cp_debug_atan2f", "cp_device_results",
     "cp_gather_create", "cp_gather_open", "cp_gather_seq", "cp_gather_wait", "cp_gather_read",
     "cp_last_rows_loaded", "cp_cone_crops", "cp_cone_images", "cp_rasterize_crops",
+    "cp_pinned_alloc", "cp_pinned_free",
 ]
 
 CONE_IMG_ROWS, CONE_IMG_COLS = 15, 12
@@ -108,9 +109,38 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cp_cone_crops.argtypes = [vp, C.POINTER(CCloudView), u32, vp, u32, C.c_float, vp, vp, u32]
     lib.cp_cone_images.argtypes = [vp, C.POINTER(CCloudView), u32, vp, u32, C.c_float, vp, vp, vp]
     lib.cp_rasterize_crops.argtypes = [vp, vp, vp, u32, vp, vp]
+    lib.cp_pinned_alloc.argtypes = [C.c_int32, C.c_size_t, C.c_int32, C.POINTER(vp)]
+    lib.cp_pinned_free.argtypes = [vp]
+    lib.cp_pinned_free.restype = None
     if path is None:
         _lib = lib
     return lib
+
+
+class PinnedBuffer:
+    """Page-locked host memory from cp_pinned_alloc, exposed as a numpy array (`.array`, uint8) — for message
+    buffers the library can DMA from directly.  Allocate it AFTER binding the thread next to the GPU."""
+
+    def __init__(self, nbytes: int, device: int = 0, write_combined: bool = False):
+        self.lib = load_library()
+        self._p = C.c_void_p()
+        st = self.lib.cp_pinned_alloc(device, nbytes, 1 if write_combined else 0, C.byref(self._p))
+        if st != CP_OK:
+            raise ConesGpuError(st, "cp_pinned_alloc failed")
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self._p.value))
+
+    @property
+    def ptr(self) -> int:
+        return int(self._p.value)
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self.array = None
+            self.lib.cp_pinned_free(self._p)
+            self._p = C.c_void_p()
+
+    __del__ = close
 
 
 class ConesGpu:

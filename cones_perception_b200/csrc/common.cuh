@@ -35,7 +35,7 @@ struct Ctl {
   u32 rows_loaded;     // 32-point rows the keep-mask pass actually read (the rest were skipped as all-ground)
 };
 
-enum : u32 { kErrSurvivors = 1u, kErrVoxels = 2u, kErrHash = 4u, kErrInternal = 8u };
+enum : u32 { kErrSurvivors = 1u, kErrVoxels = 2u, kErrHash = 4u, kErrInternal = 8u, kErrGather = 16u };
 
 // monotone float <-> uint mapping for atomic min/max on floats
 __host__ __device__ __forceinline__ u32 f2ord(float f) {

@@ -3,6 +3,7 @@
 #pragma once
 #include <emmintrin.h>
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
@@ -108,9 +109,12 @@ class CopyPool {
       std::lock_guard<std::mutex> lk(m_);
       cur_ = b;
       ++gen_;
+      taken_ = 0;
     }
     // wake ONE helper; each helper wakes the next before it starts copying.  Waking a halted core costs the
     // waker tens of microseconds (an IPI, more under a hypervisor), so the caller pays for one, not for all.
+    // `to_wake_` counts the helpers that have not picked this generation up yet: a helper that is woken passes the
+    // wake on while any are left, so the chain cannot die on a helper whose predicate is already false.
     cv_.notify_one();
     return b;
   }
@@ -127,12 +131,24 @@ class CopyPool {
         if (stop_) return;
         seen = gen_;
         b = cur_;
+        ++taken_;
       }
+      // pass the wake on.  notify_one may land on a helper that has already taken this generation (its predicate
+      // is false, it goes back to sleep without passing anything on), so the chain is re-armed by every helper
+      // that still finds work: a helper keeps waking others until the batch is handed out.
       cv_.notify_one();
-      b->work();  // a batch object is never reused, so a slow worker can only find its own batch exhausted
+      while (b->take_one()) {
+        if (!chain_done(seen)) cv_.notify_one();
+      }
     }
   }
+  // true once every helper has picked generation `gen` up (then nobody is left to wake)
+  bool chain_done(uint64_t gen) {
+    std::lock_guard<std::mutex> lk(m_);
+    return gen != gen_ || taken_ >= th_.size();
+  }
   std::vector<std::thread> th_;
+  size_t taken_ = 0;  // helpers that have picked the current generation up (guarded by m_)
   std::mutex m_;
   std::condition_variable cv_;
   std::shared_ptr<Batch> cur_;

@@ -45,9 +45,16 @@ struct FrameArgs {
   const uint8_t* in;         // raw input points (the kernel gathers its frame's survivors itself)
   Layout layout;
   Geom geom;
-  const u32* mask;           // keep bits written by keep_mask_kernel
+  // keep bits: either read from `mask` (written by keep_mask_kernel), or — mask == NULL — evaluated by the
+  // frame's own CTA (pass 2 of the ground filter + the crop, fused in front of the back half)
+  const u32* mask;
+  const u32* rowmax;         // pass 1's per-row maxima (NULL: every row must be evaluated)
+  const u32* low_key;        // [F][32] per-sector minima of pass 1 (ground removal on)
+  CropK crop;
+  GroundK gk;
+  u32* rows_loaded;          // statistics: rows the fused pass 2 read
   const u32* c_off;          // [F+1] survivor offsets — only with taps (NULL otherwise)
-  const u32* gcount;
+  u32* gcount;               // [F] ground survivors per frame (written here when mask == NULL)
   int pad_survives;
   VoxelK vk;
   ClusterK ck;
@@ -98,6 +105,8 @@ struct FrameSmem {
   u32 wsum[T / 32];
   VoxelFrame vfr;
   u32 frame, slow, v_excl, n_comp;
+  u32 gkept, nlive;                    // fused pass 2: ground survivors / live rows of the frame
+  float thr[kSectStride];              // ground thresholds of the frame; [31] their minimum, [30] their maximum
   u32 bbox[8];
   u32 sw_axis, sw_ncell;
   float sw_min, sw_inv;
@@ -152,7 +161,7 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* wsum, u32& total) {
 }
 
 template <int CMAX, int VMAX, int MODE, int T>
-__global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
+__global__ void __launch_bounds__(T, T == 256 ? 4 : 1) frame_backend_kernel(FrameArgs a) {
   constexpr int kFrameThreads = T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FrameSmem<CMAX, VMAX, T>& s = *reinterpret_cast<FrameSmem<CMAX, VMAX, T>*>(smem_raw);
@@ -187,45 +196,143 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
     }
     const u32 c0 = a.c_off ? a.c_off[f] : 0u;
 
-    // ---- S0: ordered gather of the frame's survivors from the keep mask (8 words = 256
-    // points per thread and round) + bounding box
+    // ---- S0: keep bits of the frame, then the ordered gather of its survivors + bounding box.
+    // The frame is walked in chunks of CH = 4 * CMAX rows (one row = 32 consecutive points = one mask word);
+    // the chunk's mask words live in shared memory, aliased over the point arrays that are filled afterwards.
     if (tid < 8) s.bbox[tid] = tid < 4 ? 0xFFFFFFFFu : 0u;
-    if (tid == 0) s.slow = 0;
+    if (tid == 0) {
+      s.slow = 0;
+      s.gkept = 0;
+    }
+    const bool fused = a.mask == nullptr;
+    const bool do_ground = fused && a.gk.do_ground != 0;   // (with a ready-made mask the ground verdicts are in it)
+    if (warp == 0) {
+      // :75  p.z < low + 0.1 in double  <=>  z < roundup_to_float((double)low + 0.1)
+      float t = 0.0f;
+      if (do_ground && lane < kNSect) {
+        t = __double2float_ru((double)ord2f(__ldcg(&a.low_key[f * kSectStride + lane])) + 0.1);
+        s.thr[lane] = t;
+      }
+      float mn = (do_ground && lane < kNSect) ? t : __int_as_float(0x7f800000);
+      float mx = (do_ground && lane < kNSect) ? t : -__int_as_float(0x7f800000);
+#pragma unroll
+      for (int o2 = 16; o2; o2 >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(kFull, mn, o2));
+        mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o2));
+      }
+      if (lane == 0) {
+        s.thr[31] = do_ground ? mn : -__int_as_float(0x7f800000);
+        s.thr[30] = do_ground ? mx : -__int_as_float(0x7f800000);
+      }
+    }
     __syncthreads();
     u32 C = 0;
     {
-      const u32 nwords = ntiles * kTileWords;
+      constexpr u32 CH = 4u * CMAX;                       // rows per chunk
+      constexpr u32 RPT = CH / kFrameThreads;             // rows (mask words) per thread: 8, 16 or 32
+      static_assert(CH % kFrameThreads == 0 && RPT % 8 == 0 && RPT <= 32, "chunk rows per thread");
+      static_assert(sizeof(s.u) >= CH * sizeof(unsigned short), "live-row list must fit the scratch union");
+      u32* mword = reinterpret_cast<u32*>(&s.px[0]);      // [CH] aliases px, py, pz, pw (contiguous, 16 * CMAX bytes)
+      unsigned short* liverow = reinterpret_cast<unsigned short*>(&s.u);   // [CH] chunk-local indices of the live rows
+      const u32 nrows = (npts + 31u) >> 5;
+      const float thr_min = s.thr[31], thr_max = s.thr[30];
+      const u32 key_min = f2ord(thr_min);
+      const bool skipping = do_ground && a.rowmax != nullptr;
       u32 mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0, mxy = 0, mxz = 0;
-      for (u32 w0 = 0; w0 < nwords; w0 += kFrameThreads * 8) {
-        const u32 wb = w0 + tid * 8;
-        u32 w[8];
-        u32 cnt = 0;
-        if (wb < nwords) {
-          const uint4* mp = reinterpret_cast<const uint4*>(a.mask + (u64)tile0 * kTileWords + wb);
-          const uint4 m0 = mp[0], m1 = mp[1];
-          w[0] = m0.x; w[1] = m0.y; w[2] = m0.z; w[3] = m0.w;
-          w[4] = m1.x; w[5] = m1.y; w[6] = m1.z; w[7] = m1.w;
+      u32 gkept = 0;
+      for (u32 cb = 0; cb < nrows; cb += CH) {
+        const u32 nr = nrows - cb < CH ? nrows - cb : CH;
+        const u32 r0 = tid * RPT;                          // this thread's first row of the chunk
+        u32 w[RPT];
+        if (!fused) {
+          // keep bits from keep_mask_kernel
 #pragma unroll
-          for (int k = 0; k < 8; ++k) cnt += __popc(w[k]);
+          for (u32 q = 0; q < RPT; q += 4) {
+            uint4 m = make_uint4(0u, 0u, 0u, 0u);
+            if (r0 + q < nr) m = *reinterpret_cast<const uint4*>(a.mask + (u64)tile0 * kTileWords + cb + r0 + q);
+            w[q] = m.x; w[q + 1] = m.y; w[q + 2] = m.z; w[q + 3] = m.w;
+          }
+        } else {
+          // (a) which rows can hold a survivor: a row whose highest z lies below the lowest ground threshold of
+          // any sector is ground in every sector (z < thr_min <= thr[s], exact) and is never loaded
+          u32 live = 0;
+#pragma unroll
+          for (u32 q = 0; q < RPT; q += 4) {
+            uint4 m = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (skipping && r0 + q < nr)
+              m = __ldcg(reinterpret_cast<const uint4*>(a.rowmax + (u64)tile0 * kTileWords + cb + r0 + q));
+            live |= (m.x >= key_min ? 1u : 0u) << q;
+            live |= (m.y >= key_min ? 1u : 0u) << (q + 1);
+            live |= (m.z >= key_min ? 1u : 0u) << (q + 2);
+            live |= (m.w >= key_min ? 1u : 0u) << (q + 3);
+          }
+          if (r0 + RPT > nr) live &= r0 < nr ? (0xFFFFFFFFu >> (32u - (nr - r0))) : 0u;
+#pragma unroll
+          for (u32 q = 0; q < RPT; ++q) mword[r0 + q] = 0u;
+          u32 nlive;
+          u32 lp = block_excl_scan<T>(__popc(live), s.wsum, nlive);
+          while (live) {
+            const u32 b = (u32)__ffs(live) - 1u;
+            live &= live - 1;
+            liverow[lp++] = (unsigned short)(r0 + b);
+          }
+          if (tid == 0) s.nlive = nlive;
+          __syncthreads();
+          CP_PHASE("live rows");
+          // (b) evaluate the live rows, KB per warp and round: all loads of a round are in flight together
+          constexpr u32 KB = T == 256 ? 4 : 8;   // (the 256-thread variant runs 4 CTAs per SM: 64 registers)
+          for (u32 e0 = (u32)warp * KB; e0 < nlive; e0 += (kFrameThreads / 32) * KB) {
+            float4 p[KB];
+            u32 row[KB];
+#pragma unroll
+            for (u32 j = 0; j < KB; ++j) {
+              row[j] = e0 + j < nlive ? (u32)liverow[e0 + j] : 0xFFFFFFFFu;
+              const u32 i = (cb + row[j]) * 32u + lane;
+              p[j] = (row[j] != 0xFFFFFFFFu && i < npts) ? load_point<MODE>(a.in, first + i, a.layout)
+                                                          : make_float4(0.f, 0.f, -__int_as_float(0x7f800000), 0.f);
+            }
+#pragma unroll
+            for (u32 j = 0; j < KB; ++j) {
+              if (row[j] == 0xFFFFFFFFu) break;
+              const u32 i = (cb + row[j]) * 32u + lane;
+              const u32 bal = __ballot_sync(kFull, keep_point(p[j], i < npts, a.crop, a.gk, s.thr, thr_min, thr_max, gkept));
+              if (lane == 0) mword[row[j]] = bal;
+            }
+          }
+          __syncthreads();
+          CP_PHASE("pass 2");
+          if (tid == 0 && nlive) atomicAdd(a.rows_loaded, nlive);
+#pragma unroll
+          for (u32 q = 0; q < RPT; ++q) w[q] = mword[r0 + q];
         }
+        // (c) ordered survivor indices of the chunk (k0 is free until the sort)
+        u32 cnt = 0;
+#pragma unroll
+        for (u32 q = 0; q < RPT; ++q) cnt += __popc(w[q]);
         u32 total;
         u32 pos = C + block_excl_scan<T>(cnt, s.wsum, total);
         if (cnt && C + total <= (u32)CMAX) {
-          // phase 1: only the frame-local point indices, in order (k0 is free until the sort)
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            u32 bits = w[k];
+          for (u32 q = 0; q < RPT; ++q) {
+            u32 bits = w[q];
             while (bits) {
               const u32 b = (u32)__ffs(bits) - 1u;
               bits &= bits - 1;
-              s.k0[pos++] = (wb + k) * 32 + b;
+              s.k0[pos++] = (cb + r0 + q) * 32u + b;
             }
           }
         }
         C += total;
+        __syncthreads();   // mword / liverow are rewritten by the next chunk
+      }
+      CP_PHASE("expand");
+      if (do_ground) {
+        gkept = __reduce_add_sync(kFull, gkept);
+        if (lane == 0 && gkept) atomicAdd(&s.gkept, gkept);
       }
       __syncthreads();
-      // phase 2: all threads fetch points in parallel (independent loads, no serial chains)
+      if (do_ground && tid == 0) a.gcount[f] = s.gkept;
+      // all threads fetch the survivors in parallel (independent loads, no serial chains; L2 hits after (b))
       if (C <= (u32)CMAX) {
 #pragma unroll 4
         for (u32 i = tid; i < C; i += kFrameThreads) {
@@ -237,7 +344,7 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
           mnz = min(mnz, kz); mxz = max(mxz, kz);
         }
       }
-      (void)npts;
+      (void)ntiles;
       mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny);
       mnz = __reduce_min_sync(kFull, mnz); mxx = __reduce_max_sync(kFull, mxx);
       mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
@@ -260,7 +367,7 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
     }
     __syncthreads();
 
-    CP_PHASE("gather");
+    CP_PHASE("fetch+bbox");
     // ---- S0b: VoxelGrid setup from the survivors' bounding box (thread 0)
     if (tid == 0) {
       VoxelFrame v;
@@ -430,6 +537,7 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
       const unsigned short* vs = (passes4 & 1) ? s.v1 : s.v0;
       // NOTE: the voxel arrays alias the sort scratch; the sort is complete (barrier above)
       float mxv = 0.f, myv = 0.f, mzv = 0.f;
+      const u32 gcount_f = a.pad_survives ? (fused ? s.gkept : a.gcount[f]) : 0u;
       for (u32 v = tid; v < V; v += kFrameThreads) {
         const u32 b = s.vstart[v], e = s.vstart[v + 1];
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
@@ -440,7 +548,7 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
           sy = __fadd_rn(sy, s.py[i]);
           sz = __fadd_rn(sz, s.pz[i]);
           si = __fadd_rn(si, s.pw[i]);
-          if (i == pad_idx) cnt += (npts - a.gcount[f]) - 1u;
+          if (i == pad_idx) cnt += (npts - gcount_f) - 1u;
         }
         const float c = (float)cnt;
         mxv = __fdiv_rn(sx, c); myv = __fdiv_rn(sy, c); mzv = __fdiv_rn(sz, c);
@@ -622,7 +730,7 @@ __global__ void __launch_bounds__(T) frame_backend_kernel(FrameArgs a) {
       a.ncomp_f[f] = s.n_comp;
       u32* fc = a.fc + (u64)f * 8;   // cp_frame_counters
       fc[0] = npts;
-      fc[1] = a.counted_ground ? a.gcount[f] : 0xFFFFFFFFu;
+      fc[1] = a.counted_ground ? (fused ? s.gkept : a.gcount[f]) : npts;   // G (= N without ground removal)
       fc[2] = C;
       fc[3] = V;
       fc[4] = s.n_comp;

@@ -49,6 +49,7 @@ struct RunParams {
   VoxelK vk;
   ClusterK ck;
   GroundK gk;
+  CropK crop;
   u32 csort_bits, osort_bits;
 };
 
@@ -57,7 +58,7 @@ struct cp_handle {
   int sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage[2] = {nullptr, nullptr};
-  cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};  // around the two streaming kernels
+  cudaEvent_t ev_k[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // around pass 1, pass 2, per-frame kernel
   bool stage_timing = false;
   std::string err = "";
   u32 launches = 0;
@@ -99,6 +100,12 @@ struct cp_handle {
   u32* d_nvox_f = nullptr;
   ClusterRec* d_slots = nullptr;  // [max_frames][2048] per-frame result slots of the fast back half
   bool gathered = false;  // the global scan + gather of the current run has been enqueued
+  bool masked = false;    // keep_mask_kernel of the current run has been enqueued (global keep mask + tile counts)
+  // per-frame kernel evaluates pass 2 itself (CONESGPU_FUSED_MASK=0: separate keep_mask_kernel; 2: fused even for a
+  // few frames without ground removal, where the default prefers the streaming kernel)
+  bool fuse_mask = true, fuse_mask_always = false;
+  bool run_fused_mask = false;
+  bool ran_frame_kernel = false;
 
   u64 cap_c = 0, cap_v = 0;
   u32 tiles_cap = 0, sort_tiles_cap = 0, hash_cap = 0;
@@ -144,6 +151,7 @@ struct cp_handle {
   bool tail_priority = false;  // CONESGPU_PRIO=1: greatest-priority stream, pass 1 demoted
   int prio_low = 0;
   int k1_ctas_per_sm = 0;  // CONESGPU_K1_CTAS: separate grid cap for pass 1 (0 = stream_ctas_per_sm)
+  u32 run_sgrid = 0;  // grid of the streaming kernels of the current run
   int stream_ctas_per_sm = 8;  // grid cap of the streaming kernels (CONESGPU_STREAM_CTAS: leave room for a second handle)
   u64 *d_desc_a = nullptr, *d_desc_b = nullptr, *d_desc_c = nullptr, *d_desc_d = nullptr;
   u32 *d_tap_keys = nullptr, *d_tap_order = nullptr;
@@ -514,6 +522,7 @@ void launch_keep_mask(cp_handle* h, const Geom& g, const CropK& c, const GroundK
   }
   if (h->stage_timing) cudaEventRecord(h->ev_k[3], h->stream);
   h->launches++;
+  h->masked = true;
 }
 
 // part 2: tile scan -> ordered gather (+bbox) into the global survivor arrays
@@ -711,7 +720,7 @@ __global__ void counters_kernel(u32 n_frames, const u32* frame_n, u32 uniform_n,
   if (f >= n_frames) return;
   u32* o = fc + (u64)f * 8;
   o[0] = uniform_n ? uniform_n : frame_n[f];
-  o[1] = counted_ground ? gcount[f] : 0xFFFFFFFFu;
+  o[1] = counted_ground ? gcount[f] : o[0];   // G (= N without ground removal)
   o[2] = c_off[f + 1] - c_off[f];
   o[3] = v_off[f + 1] - v_off[f];
   o[4] = ncomp_f[f];
@@ -872,7 +881,10 @@ void launch_frame_kernel(cp_handle* h, const FrameArgs& fa) {
   }
   const int per_sm = per_sm_dev[dev];
   const u32 grid = std::min<u32>(fa.n_frames, (u32)h->sms * (u32)per_sm);
+  if (h->stage_timing && !h->capturing) cudaEventRecord(h->ev_k[4], h->stream);
   frame_backend_kernel<CMAX, VMAX, MODE, T><<<grid, T, smem, h->stream>>>(fa);
+  if (h->stage_timing && !h->capturing) cudaEventRecord(h->ev_k[5], h->stream);
+  h->ran_frame_kernel = true;
   h->launches++;
 }
 
@@ -884,7 +896,12 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   fa.in = h->in_ptr;
   fa.layout = h->layout;
   fa.geom = device_geom(h);
-  fa.mask = h->d_mask;
+  fa.mask = h->run_fused_mask ? nullptr : h->d_mask;
+  fa.rowmax = h->rowmax_valid ? h->d_rowmax : nullptr;
+  fa.low_key = h->d_low_key;
+  fa.crop = rp.crop;
+  fa.gk = rp.gk;
+  fa.rows_loaded = &h->d_ctl->rows_loaded;
   fa.c_off = h->taps ? h->d_c_off : nullptr;
   fa.gcount = h->d_gcount;
   fa.pad_survives = rp.gk.pad_survives;
@@ -912,7 +929,8 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   fa.tap_keys = h->taps ? h->d_tap_keys : nullptr;
   fa.tap_order = h->taps ? h->d_tap_order : nullptr;
   fa.tap_labels = h->taps ? h->d_tap_labels : nullptr;
-  // the crop taps (survivor arrays, offsets) come from the global gather
+  // the crop taps (survivor arrays, offsets) come from the global keep mask + gather
+  if (h->taps && !h->masked) launch_keep_mask(h, fa.geom, rp.crop, rp.gk, h->run_sgrid);
   if (h->taps && !h->gathered) launch_scan_gather<false>(h, fa.geom, rp.gk, (u32)h->cap_c, nullptr);
   switch (h->layout.mode) {
     case 0: launch_frame_kernel<CMAX, VMAX, 0, T>(h, fa); break;
@@ -935,15 +953,20 @@ constexpr u32 kGatherFlagWords = 64;
 // The run number lives on the device (d_seq) so that a CUDA-graph replay publishes under a fresh
 // number without any kernel parameter changing: every CTA reads it on entry, the last one to finish
 // advances it.  `advance` = 0 re-publishes under the current number (back-half retry by cp_sync).
+constexpr u32 kGatherOverflowBit = 0x80000000u;  // flag bit: the rank had more cones than its slot holds
+
 __global__ void __launch_bounds__(256) gather_publish_kernel(const u32* __restrict__ src, u32 words, u32* base,
-                                                             u32 world, u32 rank, u32 slot_words, u32* d_seq,
-                                                             u32 advance, u32* done, const Ctl* __restrict__ ctl) {
+                                                             u32 world, u32 rank, u32 slot_words, u32 off_words,
+                                                             u32* d_seq, u32 advance, u32* done, Ctl* ctl) {
   const u32 seq = *((volatile u32*)d_seq) + advance;
   const u32 parity = seq & 1u;
   u32* dst = base + kGatherFlagWords + ((size_t)parity * world + rank) * slot_words;
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   uint4* d4 = reinterpret_cast<uint4*>(dst);
-  const u32 n4 = words / 4;
+  // only the live part travels: the offsets and the K records of this run
+  const u64 live = (u64)off_words + 4ull * ctl->n_clusters;
+  const bool overflow = live > (u64)words;
+  const u32 n4 = (u32)((overflow ? (u64)words : live) / 4);
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) d4[i] = s4[i];
   __threadfence_system();
   __syncthreads();
@@ -952,9 +975,13 @@ __global__ void __launch_bounds__(256) gather_publish_kernel(const u32* __restri
     if (t == gridDim.x - 1) {
       *done = 0;
       *d_seq = seq;
+      // never silently truncated: the publishing rank's cp_sync fails with CP_E_CAPACITY and the gathering
+      // rank's cp_gather_wait sees the overflow bit in the flag
+      if (overflow) atomicOr(&ctl->error, kErrGather);
       __threadfence_system();
       // a run whose shared-memory back half overflowed is re-run (and re-published) by cp_sync
-      if (ctl->fast_overflow == 0) *((volatile u32*)(base + parity * world + rank)) = seq;
+      if (ctl->fast_overflow == 0)
+        *((volatile u32*)(base + parity * world + rank)) = (seq & ~kGatherOverflowBit) | (overflow ? kGatherOverflowBit : 0u);
     }
   }
 }
@@ -964,7 +991,7 @@ void enqueue_gather_publish(cp_handle* h, bool retry) {
   const u32 words = (u32)std::min<size_t>(g.slot_words, h->off_words + 4 * (size_t)h->cap_v) / 4 * 4;
   const u32 grid = std::max<u32>(1, std::min<u32>(64, words / 4 / 256));
   gather_publish_kernel<<<grid, 256, 0, h->stream>>>(h->d_k_off, words, g.base, g.world, g.rank, g.slot_words,
-                                                     g.d_seq, retry ? 0u : 1u, g.d_done, h->d_ctl);
+                                                     (u32)h->off_words, g.d_seq, retry ? 0u : 1u, g.d_done, h->d_ctl);
   h->launches++;
 }
 
@@ -982,6 +1009,7 @@ cp_status enqueue_back(cp_handle* h, bool retry) {
   else if (h->back_mode == 1) enqueue_back_fast<2048, 1024, 512>(h, rp);
   else if (h->back_mode == 2) enqueue_back_fast<4096, 2048, 512>(h, rp);
   else {
+    if (!h->masked) launch_keep_mask(h, device_geom(h), rp.crop, rp.gk, h->run_sgrid);
     if (!h->gathered) launch_scan_gather<false>(h, device_geom(h), rp.gk, (u32)h->cap_c, nullptr);
     enqueue_back_general(h, rp);
   }
@@ -1057,8 +1085,8 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   GroundK gk;
   gk.do_ground = ground ? 1 : 0;
   gk.pad_survives = (ground && zero_point_survives(d)) ? 1 : 0;
-  gk.want_count = gk.pad_survives;
-  h->counted_ground = gk.want_count != 0;
+  gk.want_count = gk.do_ground;   // ground survivors are always counted (n_ground_kept); skipped rows hold none
+  h->counted_ground = gk.do_ground != 0;
   VoxelK vk;
   for (int a = 0; a < 3; ++a) vk.inv[a] = 1.0f / leaf[a];
   vk.frame_bits = ceil_log2_host(h->hg.n_frames);
@@ -1067,14 +1095,19 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   h->launches = 0;
   if (!h->capturing) cudaEventRecord(h->ev0, h->stream);
   launch_init(h, ground ? ground->default_lowest_point : 0.0f);
+  h->masked = false;
+  h->run_fused_mask = false;
+  h->ran_frame_kernel = false;
   const u32 sgrid = grid_for((u64)g.n_tiles * kStreamThreads, kStreamThreads, h->sms, h->stream_ctas_per_sm);
+  h->run_sgrid = sgrid;
   h->ran_cluster = cluster_front_eligible(h, g, ground != nullptr) &&
                    launch_front_cluster(h, g, crop, gk, ground->default_lowest_point);
   h->ran_fused = !h->ran_cluster && ground && g.uniform_n && h->use_fused;
   if (h->ran_cluster) {
-    // front end done in one launch
+    h->masked = true;  // front end done in one launch
   } else if (h->ran_fused) {
     launch_front_fused(h, g, crop, gk);
+    h->masked = true;
   } else {
     h->rowmax_valid = false;
     if (ground) {
@@ -1084,7 +1117,11 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
       h->launches++;
       h->rowmax_valid = h->use_rowskip;
     }
-    launch_keep_mask(h, g, crop, gk, sgrid);
+    // pass 2 (ground verdicts + crop) normally runs inside the per-frame kernel; the separate streaming kernel
+    // serves the general back half and — a few frames without ground removal, where every row is live and one
+    // CTA per frame would be too few — small unskippable batches
+    h->run_fused_mask = h->fuse_mask && h->back_mode < 3 && (ground != nullptr || g.n_frames >= (u32)h->sms || h->fuse_mask_always);
+    if (!h->run_fused_mask) launch_keep_mask(h, g, crop, gk, sgrid);
   }
   h->gathered = false;
   h->ran_ground = ground != nullptr;
@@ -1092,6 +1129,7 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   h->rp.vk = vk;
   h->rp.ck = ck;
   h->rp.gk = gk;
+  h->rp.crop = crop;
   h->rp.csort_bits = csort_bits;
   h->rp.osort_bits = osort_bits;
   if (h->gather.open) h->gather.seq++;
@@ -1206,6 +1244,7 @@ cp_status device_errors(cp_handle* h) {
   if (e & kErrSurvivors) h->err = "more crop survivors than cp_config.max_survivors";
   else if (e & kErrVoxels) h->err = "more voxels / clusters than cp_config.max_voxels";
   else if (e & kErrHash) h->err = "neighbour-grid hash table too small for this batch";
+  else if (e & kErrGather) h->err = "this rank found more cones than its slot of the gather buffer holds (slot_words)";
   else h->err = "internal capacity error";
   return CP_E_CAPACITY;
 }
@@ -1414,7 +1453,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
       cudaEventCreateWithFlags(&h->ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&h->ev_k[0]) != cudaSuccess || cudaEventCreate(&h->ev_k[1]) != cudaSuccess ||
-      cudaEventCreate(&h->ev_k[2]) != cudaSuccess || cudaEventCreate(&h->ev_k[3]) != cudaSuccess) {
+      cudaEventCreate(&h->ev_k[2]) != cudaSuccess || cudaEventCreate(&h->ev_k[3]) != cudaSuccess ||
+      cudaEventCreate(&h->ev_k[4]) != cudaSuccess || cudaEventCreate(&h->ev_k[5]) != cudaSuccess) {
     h->err = "stream/event creation failed";
     return fail(CP_E_CUDA);
   }
@@ -1432,6 +1472,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
     const char* st_env = getenv("CONESGPU_STAGE_THREADS");
     if (st_env && atoi(st_env) >= 1 && atoi(st_env) <= 16) h->stage_threads = atoi(st_env);
   }
+  const char* fm_env = getenv("CONESGPU_FUSED_MASK");  // "0": pass 2 as a separate streaming kernel
+  if (fm_env) h->fuse_mask = fm_env[0] != '0', h->fuse_mask_always = fm_env[0] == '2';
   const char* rs_env = getenv("CONESGPU_ROWSKIP");
   if (rs_env) h->use_rowskip = rs_env[0] != '0';
   const char* cl_env = getenv("CONESGPU_CLUSTER_FRONT");  // "1": single-pass 16-CTA-cluster front end
@@ -1530,7 +1572,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
   A(palloc(h, &h->h_stage[0], kStageChunk));
   A(palloc(h, &h->h_stage[1], kStageChunk));
   A(palloc(h, &h->h_ctl, 1));
-  A(palloc(h, &h->h_frame_u32, (size_t)(F + 1) * 8));
+  // per-frame readback scratch; cp_ground_remove also parks one frame's kNSect sector minima in it
+  A(palloc(h, &h->h_frame_u32, std::max<size_t>((size_t)(F + 1) * 8, (size_t)kSectStride)));
 #undef A
   memset(h->h_ctl, 0, sizeof(Ctl));
   *out = h;
@@ -1556,10 +1599,30 @@ void cp_destroy(cp_handle* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 2; ++i)
     if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 6; ++i)
     if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+cp_status cp_pinned_alloc(int32_t device, size_t bytes, int32_t write_combined, void** out) {
+  if (!out || bytes == 0) return CP_E_PARAM;
+  *out = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    cudaGetLastError();
+    return CP_E_CUDA;
+  }
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  const cudaError_t e = cudaHostAlloc(out, bytes, flags);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return e == cudaErrorMemoryAllocation ? CP_E_NOMEM : CP_E_CUDA;
+  }
+  return CP_OK;
+}
+void cp_pinned_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 cp_status cp_batch_set_device_input(cp_handle* h, const void* d_points, uint32_t n_frames,
@@ -1672,6 +1735,10 @@ struct RunKey {
   u32 n_frames, uniform_n, n_tiles, layout_mode, layout_step;
   i32 ox, oy, oz, oi;
   int back_mode, has_ground;
+  // the result publish over peer memory is part of the enqueued sequence: a graph captured before the gather
+  // was wired has no publish node, so the gather state is part of the key
+  u32 gather_open, gather_rank, gather_slot_words;
+  const void* gather_base;
   cp_detect_params d;
   cp_ground_params g;
 };
@@ -1688,6 +1755,10 @@ static RunKey make_key(const cp_handle* h, const cp_detect_params* d, const cp_g
   k.ox = h->layout.ox; k.oy = h->layout.oy; k.oz = h->layout.oz; k.oi = h->layout.oi;
   k.back_mode = h->back_mode;
   k.has_ground = ground ? 1 : 0;
+  k.gather_open = h->gather.open ? 1u : 0u;
+  k.gather_rank = h->gather.rank;
+  k.gather_slot_words = h->gather.slot_words;
+  k.gather_base = h->gather.base;
   k.d = *d;
   if (ground) k.g = *ground;
   return k;
@@ -1875,7 +1946,7 @@ cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_groun
   memset(&crop, 0, sizeof(crop));
   GroundK gk;
   gk.do_ground = 1;
-  gk.want_count = 0;
+  gk.want_count = 1;
   gk.pad_survives = 0;
   launch_keep_mask(h, geo, crop, gk, sgrid);
   launch_scan_gather<true>(h, geo, gk, n, h->d_out32);
@@ -1883,6 +1954,7 @@ cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_groun
   h->launches += 1;
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_xyzi32, h->d_out32, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+  static_assert(kNSect <= kSectStride, "h_frame_u32 holds at least kSectStride words");
   if (low17) CK(cudaMemcpyAsync(h->h_frame_u32, h->d_low_key, sizeof(u32) * kNSect, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -1992,8 +2064,19 @@ cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms) try {
       h->err = "the last run used a single-kernel front end";
       return CP_E_STATE;
     }
+    if (h->run_fused_mask && !h->masked) {
+      h->err = "pass 2 ran inside the per-frame kernel (CP_STAGE_FRAME_BACKEND)";
+      return CP_E_STATE;
+    }
     CK(cudaEventSynchronize(h->ev_k[3]));
     CK(cudaEventElapsedTime(ms, h->ev_k[2], h->ev_k[3]));
+  } else if (stage == CP_STAGE_FRAME_BACKEND) {
+    if (!h->ran_frame_kernel) {
+      h->err = "the last run used the general back half";
+      return CP_E_STATE;
+    }
+    CK(cudaEventSynchronize(h->ev_k[5]));
+    CK(cudaEventElapsedTime(ms, h->ev_k[4], h->ev_k[5]));
   } else {
     h->err = "unknown stage";
     return CP_E_PARAM;
@@ -2018,6 +2101,23 @@ cp_status cp_device_results(cp_handle* h, const void** d_clusters, const uint32_
   return abi_exception(h);
 }
 
+// the gather slot of a rank is laid out like the handle's own result block: round_up(max_frames + 1, 4) offset
+// words, then the records.  A slot that cannot even hold the offsets is a caller error.
+static cp_status gather_check(cp_handle* h, uint32_t slot_words) {
+  if ((size_t)slot_words < h->off_words + 4) {
+    h->err = "slot_words is smaller than round_up(max_frames + 1, 4) + 4: the slot cannot hold the offsets of this handle";
+    return CP_E_PARAM;
+  }
+  // a graph captured before the gather was wired has no publish node
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  h->graph_key_valid = false;
+  h->key_valid = false;
+  return CP_OK;
+}
+
 cp_status cp_gather_create(cp_handle* h, uint32_t world, uint32_t slot_words, uint8_t handle_out[64]) try {
   if (!h || !handle_out || world == 0 || slot_words == 0 || slot_words % 4) return CP_E_PARAM;
   CK(cudaSetDevice(h->cfg.device));
@@ -2027,6 +2127,7 @@ cp_status cp_gather_create(cp_handle* h, uint32_t world, uint32_t slot_words, ui
     h->err = "gather already configured on this handle";
     return CP_E_STATE;
   }
+  if (cp_status gs = gather_check(h, slot_words)) return gs;
   const size_t words = kGatherFlagWords + 2ull * world * slot_words;
   void* p = nullptr;
   CK(cudaMalloc(&p, words * sizeof(u32)));
@@ -2063,6 +2164,7 @@ cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, 
     h->err = "gather already configured on this handle";
     return CP_E_STATE;
   }
+  if (cp_status gs = gather_check(h, slot_words)) return gs;
   cudaIpcMemHandle_t ih;
   memcpy(&ih, handle, 64);
   void* p = nullptr;
@@ -2102,8 +2204,16 @@ cp_status cp_gather_wait(cp_handle* h, uint32_t seq, uint32_t timeout_ms) try {
   for (u32 waited = 0;; ++waited) {
     CK(cudaMemcpy(g.h_flags, g.base, kGatherFlagWords * sizeof(u32), cudaMemcpyDeviceToHost));
     bool all = true;
-    for (u32 r = 0; r < g.world; ++r) all = all && (g.h_flags[parity * g.world + r] == seq);
-    if (all) return CP_OK;
+    for (u32 r = 0; r < g.world; ++r)
+      all = all && ((g.h_flags[parity * g.world + r] & ~kGatherOverflowBit) == (seq & ~kGatherOverflowBit));
+    if (all) {
+      for (u32 r = 0; r < g.world; ++r)
+        if (g.h_flags[parity * g.world + r] & kGatherOverflowBit) {
+          h->err = "rank " + std::to_string(r) + " published more cones than its gather slot holds";
+          return CP_E_CAPACITY;
+        }
+      return CP_OK;
+    }
     if (waited >= timeout_ms * 10) {
       h->err = "timed out waiting for the ranks to publish their cone lists";
       return CP_E_STATE;

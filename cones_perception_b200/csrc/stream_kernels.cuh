@@ -55,7 +55,8 @@ struct CropK {
 
 struct GroundK {
   int do_ground;
-  int want_count;   // also count ground survivors per frame (n_ground_kept)
+  int want_count;   // = do_ground: ground survivors are counted per frame (n_ground_kept); only the two
+                    // experimental front ends still read it
   int pad_survives; // the zero points the ground node pads with survive the crop
 };
 
@@ -480,30 +481,34 @@ __device__ __forceinline__ void keep_mask_finish(const Geom& g, const GroundK& g
   __syncthreads();
 }
 
-// one row (32 consecutive points, one per lane): keep verdict of this lane's point
+// one row (32 consecutive points, one per lane): keep verdict of this lane's point, ground filter first
+// (src/ground_removal.cpp:70-77), then the crop on what it keeps (src/cone_detection.cpp:189-204).
+// gkept counts the ground node's survivors (cp_frame_counters::n_ground_kept).  thr_min / thr_max are the
+// lowest / highest threshold of any sector: below thr_min a point is ground everywhere, at or above thr_max it
+// is kept everywhere, and only the points in between need their sector (thr_min = thr_max = -inf: no ground
+// removal).
 __device__ __forceinline__ bool keep_point(const float4& q, bool in_range, const CropK& c, const GroundK& gk,
-                                           const float* thr, float thr_min, u32& gkept) {
+                                           const float* thr, float thr_min, float thr_max, u32& gkept) {
   const float x = q.x, y = q.y, z = q.z;
   bool keep = false;
-  // ground prefilter: below the lowest threshold of any sector => ground everywhere
-  // (without the per-frame count, points failing the crop need no ground verdict either)
   if (in_range && !(z < thr_min) && finite3(x, y, z)) {
-    keep = !c.do_crop || crop_keep(c, x, y, z);
-    if (keep || gk.want_count) {
-      bool ok;
-      const float a = atan2_approx(y, x, ok);
+    bool ok = false, have_a = false, gkeep = true;
+    float a = 0.0f;
+    if (gk.do_ground && z < thr_max) {
+      a = atan2_approx(y, x, ok);
+      have_a = true;
+      gkeep = !(z < thr[sector_of(x, y, a, ok)]);
+    }
+    if (gkeep) {
+      gkept++;
+      keep = !c.do_crop || crop_keep(c, x, y, z);
       if (keep && c.do_crop) {
+        if (!have_a) a = atan2_approx(y, x, ok);
         const float aa = fabsf(a);
         if (!ok | (aa > c.f_lo_guard)) {
           if (ok & (aa >= c.f_hi_guard)) keep = false;
           else keep = fabsf(atan2_exact(y, x)) < c.f_hi;  // src/cone_detection.cpp:200-201
         }
-      }
-      if (gk.do_ground && (keep || gk.want_count)) {
-        const int s = sector_of(x, y, a, ok);
-        const bool gkeep = !(z < thr[s]);
-        if (gkeep) gkept++;
-        keep = keep && gkeep;
       }
     }
   }
@@ -512,17 +517,19 @@ __device__ __forceinline__ bool keep_point(const float4& q, bool in_range, const
 
 // per-frame ground thresholds, once per frame instead of once per tile:
 // :75  p.z < low + 0.1 in double  <=>  z < roundup_to_float((double)low + 0.1).
-// thr_f[f*32 + s] for the 17 sectors, thr_f[f*32 + 31] = their minimum.
+// thr_f[f*32 + s] for the 17 sectors, thr_f[f*32 + 31] = their minimum, thr_f[f*32 + 30] = their maximum.
 __global__ void ground_thresholds_kernel(u32 n_frames, const u32* __restrict__ low_key, float* __restrict__ thr_f) {
   const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= n_frames) return;
-  float mn = __int_as_float(0x7f800000);
+  float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
   for (int s = 0; s < kNSect; ++s) {
     const float t = __double2float_ru((double)ord2f(low_key[f * kSectStride + s]) + 0.1);
     thr_f[f * kSectStride + s] = t;
     mn = fminf(mn, t);
+    mx = fmaxf(mx, t);
   }
   thr_f[f * kSectStride + 31] = mn;
+  thr_f[f * kSectStride + 30] = mx;
 }
 
 // Pass 2 as a warp-independent streaming map.  A group is 32 rows = 1024 consecutive points
@@ -541,7 +548,9 @@ keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, Grou
   const u32 nwarps = gridDim.x * kStreamWarps;
   const u32 gw = blockIdx.x * kStreamWarps + (threadIdx.x >> 5);
   const u32 ngroups = g.n_tiles * 2u;                          // group G = rows [G*32, G*32+32) of the mask
-  const bool skipping = gk.do_ground && rowmax != nullptr && !gk.want_count;
+  // a skipped row lies entirely below every threshold: none of its points survives the ground filter, so it
+  // contributes nothing to the per-frame ground count either
+  const bool skipping = gk.do_ground && rowmax != nullptr;
   u32 nrows = 0;
   // scan order clusters the rows that cannot be skipped (e.g. the beams above the horizon); a
   // contiguous split would leave most warps idle while a few do all the work
@@ -563,6 +572,7 @@ keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, Grou
     tile_lookup(g, tile, frame, local0, count, first);
     const float* thr = thr_f + (size_t)frame * kSectStride;
     const float thr_min = gk.do_ground ? __ldg(thr + 31) : -__int_as_float(0x7f800000);
+    const float thr_max = gk.do_ground ? __ldg(thr + 30) : -__int_as_float(0x7f800000);
     const u32 half0 = (grp & 1u) * (kStreamTile / 2);          // tile-local index of the group's first point
     if (gk.pad_survives && (grp & 1u) && lane == 0 && sub == 0 &&
         (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]))
@@ -586,7 +596,7 @@ keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, Grou
 #pragma unroll
         for (int r = 0; r < kStreamRows; ++r) {
           const u32 i = half0 + (b * kStreamRows + r) * 32 + lane;
-          const u32 bal = __ballot_sync(kFull, keep_point(p[r], i < count, c, gk, thr, thr_min, gkept));
+          const u32 bal = __ballot_sync(kFull, keep_point(p[r], i < count, c, gk, thr, thr_min, thr_max, gkept));
           gcount += __popc(bal);
           if ((u32)lane == b * kStreamRows + r) myword = bal;
         }
@@ -609,7 +619,7 @@ keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, Grou
       for (int j = 0; j < kBatch; ++j) {
         if (rowid[j] == 0xFFFFFFFFu) break;
         const u32 i = half0 + rowid[j] * 32 + lane;
-        const bool keep = keep_point(p[j], i < count, c, gk, thr, thr_min, gkept);
+        const bool keep = keep_point(p[j], i < count, c, gk, thr, thr_min, thr_max, gkept);
         const u32 bal = __ballot_sync(kFull, keep);
         gcount += __popc(bal);
         if ((u32)lane == rowid[j]) myword = bal;
@@ -619,7 +629,7 @@ keep_mask_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, Grou
       if ((live >> lane) & 1u) o.mask[(u64)grp * 32 + lane] = myword;
       if (lane == 0) atomicAdd(&o.tile_count[tile], gcount);
     }
-    if (gk.want_count) {
+    if (gk.do_ground) {
       const u32 gsum = __reduce_add_sync(kFull, gkept);
       if (lane == 0 && gsum) atomicAdd(&o.gcount[frame], gsum);
     }

@@ -107,6 +107,15 @@ const char* cp_create_error(void);            /* detail of the last failed cp_cr
 cp_status cp_create(cp_handle** out, const cp_config* cfg);
 void cp_destroy(cp_handle* h);
 
+/* Page-locked host memory for message buffers (north_star: "PointCloud2 staged to device through pinned
+ * cudaMemcpyAsync"): a cloud that already lives in such a buffer is DMA'd straight from it, with no
+ * pass through the library's staging ring.  write_combined != 0 asks for cudaHostAllocWriteCombined
+ * (fast for the CPU to fill sequentially and for the GPU to read, very slow for the CPU to read back).
+ * The pages are placed by the calling thread's NUMA policy: bind the thread next to the GPU first
+ * (cones_perception_b200/placement.py).  No handle is needed; device selects the context. */
+cp_status cp_pinned_alloc(int32_t device, size_t bytes, int32_t write_combined, void** out);
+void cp_pinned_free(void* p);
+
 /* --- node-equivalent single-frame calls (host buffers in, host buffers out) -------- */
 
 /* src/ground_removal.cpp:54-79.  out_xyzi32 receives width*height points in the PCL
@@ -134,8 +143,14 @@ cp_status cp_batch_set_device_input(cp_handle* h, const void* d_points, uint32_t
                                     int32_t off_x, int32_t off_y, int32_t off_z,
                                     int32_t off_intensity);
 
-/* Stage a batch from host memory: pinned staging + chunked cudaMemcpyAsync overlapped
- * with nothing yet (the copy is enqueued on the handle's stream). */
+/* Stage a batch from host memory (cudaMemcpyAsync on the handle's stream).
+ * Lifetime of the source buffers:
+ *   - pageable memory (a ROS message's std::vector): fully consumed when the call returns — it
+ *     is packed through the library's pinned ring;
+ *   - page-locked memory (cudaHostAlloc / cudaHostRegister), contiguous rows: the DMA reads the
+ *     caller's buffer directly and is still in flight when the call returns.  The buffer must
+ *     stay valid and unmodified until cp_sync / cp_batch_results (or cp_detect*) of this batch
+ *     has returned. */
 cp_status cp_batch_set_host_input(cp_handle* h, const cp_cloud_view* frames, uint32_t n_frames);
 
 /* Enqueue the whole pipeline for the current batch on the handle's stream (async). */
@@ -161,9 +176,11 @@ cp_status cp_last_run_ms(cp_handle* h, float* ms);
  * around each launch).  Off by default; bench.py switches it on for the roofline pass. */
 typedef enum cp_stage {
   CP_STAGE_SECTOR_MIN = 0,        /* ground_sector_min_kernel (two-kernel front end)   */
-  CP_STAGE_MASK_CROP_COMPACT = 1, /* keep_mask_kernel (two-kernel front end)           */
+  CP_STAGE_MASK_CROP_COMPACT = 1, /* keep_mask_kernel (only when pass 2 runs as its own kernel) */
   CP_STAGE_FRONT_FUSED = 2,       /* front_fused_kernel: both passes, pass 2 from L2   */
-  CP_STAGE_FRONT_CLUSTER = 3      /* front_cluster_kernel: one HBM pass, 16-CTA clusters */
+  CP_STAGE_FRONT_CLUSTER = 3,     /* front_cluster_kernel: one HBM pass, 16-CTA clusters */
+  CP_STAGE_FRAME_BACKEND = 4      /* frame_backend_kernel: pass 2 (keep bits) + VoxelGrid + clustering +
+                                     centroids, one CTA per frame                         */
 } cp_stage;
 cp_status cp_set_stage_timing(cp_handle* h, int on);
 cp_status cp_stage_ms(cp_handle* h, cp_stage stage, float* ms);
@@ -190,7 +207,10 @@ cp_status cp_device_results(cp_handle* h, const void** d_clusters, const uint32_
  *   others:  cp_gather_open(h, handle, rank, world, slot_words)
  *   then cp_batch_run as usual on every rank; run number = cp_gather_seq(h)
  *   rank 0:  cp_gather_wait(h, seq, timeout_ms); cp_gather_read(h, seq, out, cap)
- * slot_words (multiple of 4) >= round_up(max_frames + 1, 4) + 4 * (cone capacity per rank). */
+ * slot_words (multiple of 4) >= round_up(max_frames + 1, 4) + 4 * (cone capacity per rank); every
+ * handle of the gather must be created with the same cp_config.max_frames (a slot is laid out like
+ * the handle's own result block).  A rank that finds more cones than its slot holds is never
+ * truncated silently: its own cp_sync and the gathering rank's cp_gather_wait return CP_E_CAPACITY. */
 cp_status cp_gather_create(cp_handle* h, uint32_t world, uint32_t slot_words, uint8_t handle_out[64]);
 cp_status cp_gather_open(cp_handle* h, const uint8_t handle[64], uint32_t rank, uint32_t world,
                          uint32_t slot_words);

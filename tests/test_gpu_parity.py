@@ -359,6 +359,112 @@ def test_row_skipping_is_exact_and_effective():
         assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
 
 
+@pytest.mark.parametrize("ground", [True, False])
+def test_pass2_inside_the_frame_kernel_equals_the_streaming_kernel(ground):
+    """Pass 2 (ground verdicts + crop) runs inside the per-frame kernel by default (CONESGPU_FUSED_MASK unset; "2"
+    forces it for small batches without ground removal) or as its own streaming kernel ("0").  Same cones, same
+    counters (n_ground_kept included), same rows read — on a uniform batch, a ragged one with an empty frame and
+    a one-tile frame, and the threshold-boundary cloud — and all equal to the oracle."""
+    cfg = scans.config(3)
+    g = cfg.ground if ground else None
+    frames = list(scans.generate(cfg, 6, base_seed=900))
+    rng = np.random.default_rng(5)
+    ragged = [f[: int(n)] for f, n in zip(frames, rng.integers(1000, cfg.points_per_frame, len(frames)))]
+    ragged[1] = ragged[1][:0]
+    ragged[3] = ragged[3][:2048]
+    ragged[4] = ragged[4][:33]
+    batches = {"uniform": frames, "ragged": ragged, "boundary": [boundary_cloud(cfg.detect, seed=4)]}
+    for name, fr in batches.items():
+        msgs = [PointCloud2.from_xyzi(f) for f in fr]
+        out = {}
+        for fm in ("2", "0"):
+            with api.ConesGpu(max_points=sum(len(f) for f in fr) + 1, max_frames=len(fr),
+                              env={"CONESGPU_FUSED_MASK": fm}) as h:
+                for _ in range(3):            # direct, graph capture, graph replay
+                    ctr, off, cl = h.detect_batch(msgs, cfg.detect, g)
+                out[fm] = (ctr.copy(), off.copy(), cl.copy(), h.last_rows_loaded(), h.last_launch_count())
+        for a, b in zip(out["2"][:3], out["0"][:3]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), name
+        if name == "uniform":     # (a partly filled last tile: the streaming kernel also counts its padding rows)
+            assert out["2"][3] == out["0"][3], (name, "rows read differ")
+            assert out["2"][4] < out["0"][4], (name, "the fused path must need fewer launches")
+        for f, a in enumerate(fr):
+            exp, octr, _ = O.detect(O.view_of_xyzi(a), cfg.detect, g, O.CANONICAL)
+            got = out["2"][2][out["2"][1][f]:out["2"][1][f + 1]]
+            assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (name, f)
+            assert int(out["2"][0]["n_ground_kept"][f]) == octr.n_ground_kept, (name, f)
+            assert int(out["2"][0]["n_cropped"][f]) == octr.n_cropped, (name, f)
+
+
+def test_frames_larger_than_one_mask_chunk():
+    """The per-frame kernel walks a frame in chunks of 4 x CMAX rows (4096 rows = 131 072 points with the smallest
+    budget): a 300 000-point frame crosses two chunk boundaries and must still come out like the oracle."""
+    cfg = scans.config(3)
+    parts = scans.generate(cfg, 3, base_seed=910)
+    rng = np.random.default_rng(910)
+    far = np.zeros((170_000, 4), np.float32)           # returns beyond distance_treshold_max, at and above the ground
+    ang, rad = rng.uniform(-np.pi, np.pi, len(far)), rng.uniform(30, 60, len(far))
+    far[:, 0], far[:, 1] = rad * np.cos(ang), rad * np.sin(ang)
+    far[:, 2] = np.where(rng.random(len(far)) < 0.8, -0.6 + rng.normal(0, 0.004, len(far)), rng.uniform(-0.4, 2.0, len(far)))
+    clouds = {"few survivors": np.ascontiguousarray(np.concatenate([parts[0][:70_001], far, parts[0][70_001:]])),
+              "three scans in one (overflows the small budgets)": np.ascontiguousarray(np.concatenate(list(parts))[:300_000])}
+    for name, big in clouds.items():
+        exp, octr, _ = O.detect(O.view_of_xyzi(big), cfg.detect, cfg.ground, O.CANONICAL)
+        for mode in (0, 2):
+            with api.ConesGpu(max_points=len(big), max_frames=1, back_mode=mode) as h:
+                cl, ctr = h.detect(PointCloud2.from_xyzi(big), cfg.detect, cfg.ground, cap=1 << 16)
+            assert np.array_equal(cl.view(np.uint32), exp.view(np.uint32)), (name, mode)
+            assert int(ctr["n_ground_kept"]) == octr.n_ground_kept and int(ctr["n_cropped"]) == octr.n_cropped
+
+
+def test_gather_wired_after_a_graph_was_captured():
+    """A handle that has already replayed a run from a CUDA graph gets its peer gather wired afterwards
+    (warm-up, then setup): the graph must be dropped, or the publish kernel would never run again."""
+    from cones_perception_b200.sharding import pack_words, unpack_gathered
+    import torch
+    cfg = scans.config(3)
+    a = scans.generate(cfg, 3, base_seed=920)
+    F, N = a.shape[0], a.shape[1]
+    dev = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    with api.ConesGpu(max_points=F * N, max_frames=F) as h:
+        h.set_device_input(dev.data_ptr(), np.full(F, N, np.uint32), keep=dev)
+        for _ in range(3):                      # direct, capture, replay
+            h.run(cfg.detect, cfg.ground)
+            ctr, off, cl = h.results()
+        words = pack_words(F, 4 * 64)
+        h.gather_create(1, words)
+        for rep in range(3):
+            h.run(cfg.detect, cfg.ground)
+            h.sync()
+            seq = h.gather_seq()
+            assert seq == rep + 1
+            h.gather_wait(seq, timeout_ms=2000)
+            got = unpack_gathered(h.gather_read(seq, 1, words), F)
+            assert np.array_equal(np.concatenate(got).view(np.uint32), cl.view(np.uint32))
+
+
+def test_gather_slot_overflow_is_reported():
+    """More cones than the gather slot holds: never truncated silently — the publishing rank's cp_sync and the
+    gathering rank's cp_gather_wait both fail with CP_E_CAPACITY."""
+    from cones_perception_b200.sharding import pack_words
+    cfg = scans.config(3)
+    frames = list(scans.generate(cfg, 4, base_seed=60))
+    F = len(frames)
+    with api.ConesGpu(max_points=F * cfg.points_per_frame, max_frames=F) as h:
+        with pytest.raises(api.ConesGpuError):
+            h.gather_create(1, 4)               # cannot even hold the offsets
+        words = pack_words(F, 8)                # room for 8 cones; the batch has ~100
+        h.gather_create(1, words)
+        h.set_host_input([PointCloud2.from_xyzi(f) for f in frames])
+        h.run(cfg.detect, cfg.ground)
+        with pytest.raises(api.ConesGpuError) as e:
+            h.sync()
+        assert e.value.status == api.CP_E_CAPACITY
+        with pytest.raises(api.ConesGpuError) as e:
+            h.gather_wait(h.gather_seq(), timeout_ms=2000)
+        assert e.value.status == api.CP_E_CAPACITY
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_every_back_half_variant_gives_the_same_cones(mode):
     """All four back-half variants (three shared-memory budgets + the general path), forced one by one,

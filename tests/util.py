@@ -62,6 +62,9 @@ def assert_frame_parity(gpu: "api.ConesGpu", f: int, ora: dict, offs: dict, taps
     assert np.array_equal(got_real, exp_real), f"frame {f}: crop keep-mask differs"
     assert (got_idx < 0).sum() == (1 if n_fill else 0)
     assert ctr["n_cropped"][f] == len(got_idx)
+    # G: survivors of the ground node (= N without ground removal), counted although all-ground rows are skipped
+    exp_g = int(ora["ground_keep"].sum()) if "ground_keep" in ora else ora["n"]
+    assert int(ctr["n_ground_kept"][f]) == exp_g, f"frame {f}: n_ground_kept {ctr['n_ground_kept'][f]} vs {exp_g}"
     if n_fill == 0:
         assert np.array_equal(taps["voxel_keys"][c0:c1], ora["keys"]), f"frame {f}: voxel keys differ"
         assert np.array_equal(taps["voxel_order"][c0:c1] - c0, ora["order"]), f"frame {f}: voxel order differs"
