@@ -121,8 +121,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU path (oracle)
-def cpu_frames_per_sec(frames: np.ndarray, cfg, threads: int, mode_faithful: bool = True):
-    """Times the CPU restatement (PCL cost profile) on `frames`; returns (seconds, per-stage ms)."""
+def cpu_frames_per_sec(frames: np.ndarray, cfg, threads: int, mode_faithful: bool = True, keep: list | None = None):
+    """Times the CPU restatement (PCL cost profile) on `frames`; returns (seconds, per-stage ms).
+    keep: a list of len(frames) that receives every frame's (clusters, counters) for the parity check."""
     from oracle import oracle as O
 
     mode = O.PCL_FAITHFUL if mode_faithful else O.CANONICAL
@@ -133,7 +134,9 @@ def cpu_frames_per_sec(frames: np.ndarray, cfg, threads: int, mode_faithful: boo
     def work(idx):
         loc = dict.fromkeys(stage, 0.0)
         for i in idx:
-            _, _, tm = O.detect(O.view_of_xyzi(frames[i]), cfg.detect, cfg.ground, mode)
+            cl, oc, tm = O.detect(O.view_of_xyzi(frames[i]), cfg.detect, cfg.ground, mode)
+            if keep is not None:
+                keep[i] = (cl, (oc.n_ground_kept, oc.n_cropped, oc.n_voxels, oc.n_components, oc.n_clusters))
             for k in loc:
                 loc[k] += getattr(tm, k)
         with lock:
@@ -150,6 +153,30 @@ def cpu_frames_per_sec(frames: np.ndarray, cfg, threads: int, mode_faithful: boo
         [t.join() for t in th]
     dt = time.perf_counter() - t0
     return dt, {k: 1e3 * v / n for k, v in stage.items()}
+
+
+def compare_with_oracle(kept, ctr, k_off, clusters, tol=1e-5):
+    """GPU results of a batch against the oracle's (pcl_faithful mode: PCL's own cluster order and summation
+    order) for the first len(kept) frames: counters identical, the multiset of (size, min voxel index) per frame
+    identical, centroids within `tol` metres (north_star's 1e-5 m).  Raises on any difference."""
+    worst = 0.0
+    n_cl = 0
+    for f, (ocl, oc) in enumerate(kept):
+        got = clusters[k_off[f]:k_off[f + 1]]
+        names = ("n_ground_kept", "n_cropped", "n_voxels", "n_components", "n_clusters")
+        mine = tuple(int(ctr[n][f]) for n in names)
+        assert mine == tuple(int(v) for v in oc), f"frame {f}: counters {dict(zip(names, mine))} vs oracle {oc}"
+        a = np.sort(got, order=("size", "min_index"))
+        b = np.sort(ocl, order=("size", "min_index"))
+        assert len(a) == len(b) and np.array_equal(a["size"], b["size"]) and \
+            np.array_equal(a["min_index"], b["min_index"]), f"frame {f}: cluster membership differs from the oracle"
+        if len(a):
+            worst = max(worst, float(np.max(np.abs(a["x"] - b["x"]))), float(np.max(np.abs(a["y"] - b["y"]))))
+        n_cl += len(a)
+    assert worst <= tol, f"centroids differ from the oracle by {worst} m"
+    return {"frames_checked": len(kept), "clusters_checked": n_cl, "max_centroid_diff_m": worst, "tolerance_m": tol,
+            "oracle_mode": "pcl_faithful", "what": "counters (G, C, V, components, K) and (size, min index) sets "
+            "identical; centroids within tolerance"}
 
 
 def run_reference(args):
@@ -185,34 +212,6 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ ours
-def bind_to_gpu_numa(gpu_index: int) -> str:
-    """Best effort: run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node
-    the GPU hangs off, so 8 ranks streaming from host memory do not all cross the socket link."""
-    try:
-        import pynvml as nv
-        nv.nvmlInit()
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        idx = int(vis.split(",")[gpu_index]) if vis else gpu_index
-        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        nv.nvmlShutdown()
-        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
-        node = int(open(dev + "/numa_node").read())
-        if node < 0:
-            return "numa: unknown"
-        cpus = []
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.extend(range(int(a), int(b or a) + 1))
-        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return f"numa node {node}, {len(allowed)} cpus"
-        return f"numa node {node}: no allowed cpus"
-    except Exception as e:  # containers often hide the topology
-        return f"numa: not bound ({type(e).__name__})"
-
-
 class _DevArray:
     """Zero-copy torch view of a raw device pointer (result buffers of the library)."""
 
@@ -240,9 +239,36 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libconesgpu has no CPU fallback")
     torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa(local) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_obj(v):
+        if world == 1:
+            return [v]
+        out = [None] * world
+        dist.all_gather_object(out, v)
+        return out
+
+    # ---- host placement, then the box's raw host->device ceiling (both BEFORE the pinned batch is allocated).
+    # Ranks look for their CPU group one after the other (the placement probes must not disturb each other);
+    # the ceiling is then measured with every rank copying at the same time.
+    from cones_perception_b200 import placement
+    bind = {"how": "single rank: not bound"}
+    if world > 1 and os.environ.get("BENCH_BIND", "1") != "0":
+        for r in range(world):
+            if r == rank:
+                try:
+                    bind = placement.bind_rank(local)
+                except Exception as e:            # never let placement stop the measurement
+                    bind = {"how": f"failed ({type(e).__name__}: {e})"}
+            barrier()
+    probe = placement.h2d_probe(local, 1 << 30, 6, barrier)
+    probes = gather_obj({"GBps": probe["GBps"], "bind": bind, "pages_by_node": probe["pages_by_node"]})
 
     cfg = scans.config(3)
     F, N = args.frames_per_gpu, cfg.points_per_frame
@@ -330,11 +356,6 @@ def run_ours(args):
         for e in exts[1:]:
             ext.wait_stream(e)                      # lane 0's stream waits for the other lane
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3) * len(lanes)):
         step_device()
     drain()
@@ -367,14 +388,55 @@ def run_ours(args):
         seq = last.gather_seq()
         last.gather_wait(seq)
         gathered[0] = torch.from_numpy(last.gather_read(seq, world, words))
-    if world > 1 and rank == 0 and gathered[0] is not None:
-        # the gathered list must hold every rank's frames; rank 0's block must equal its own results
-        from cones_perception_b200.sharding import unpack_gathered
-        per_frame = unpack_gathered(gathered[0].cpu().numpy(), F)
-        assert len(per_frame) == world * F
-        mine = np.concatenate(per_frame[:F]) if int(ctr["n_clusters"].sum()) else np.zeros(0, api.CLUSTER_DTYPE)
-        assert np.array_equal(mine.view(np.uint32), clusters.view(np.uint32)), "gathered cone list is wrong"
-        assert all(sum(len(c) for c in per_frame[r * F:(r + 1) * F]) > 0 for r in range(world))
+    # ---- result path check, EVERY rank's block: each rank hashes the results it read itself (cp_batch_results),
+    # the hashes travel over NCCL, and rank 0 compares them with what every peer published into its memory.
+    # A second run with a different min_cluster_size changes the cone lists, so a stale double-buffer slot or a
+    # misrouted rank cannot pass by showing an older, identical-looking block.
+    import hashlib
+    from dataclasses import replace
+    from cones_perception_b200.sharding import offset_words
+
+    def block_hash(off, recs):
+        k = int(off[-1])
+        return hashlib.sha256(np.ascontiguousarray(off, np.uint32).tobytes() +
+                              np.ascontiguousarray(recs[:k]).view(np.uint32).tobytes()).hexdigest()
+
+    def check_gather(g_np, hashes, what):
+        gw = np.ascontiguousarray(g_np).view(np.uint32).reshape(world, -1)
+        for r in range(world):
+            off = gw[r, :F + 1]
+            recs = gw[r, offset_words(F):].reshape(-1, 4)
+            assert block_hash(off, recs) == hashes[r], f"{what}: rank {r}'s published cone list differs from its own"
+
+    gather_check = None
+    if world > 1:
+        my_hash = block_hash(k_off, clusters)
+        hashes = gather_obj(my_hash)
+        if rank == 0 and gathered[0] is not None:
+            check_gather(gathered[0].cpu().numpy(), hashes, "timed run")
+        # second run, different parameters -> different lists, fresh sequence number
+        d_alt = replace(d, min_cluster_size=d.min_cluster_size + 1)
+        h_alt = lanes[args.steps % len(lanes)]
+        barrier()
+        h_alt.run(d_alt, g)
+        h_alt.sync()
+        _, off_alt, cl_alt = h_alt.results()
+        alt_hashes = gather_obj(block_hash(off_alt, cl_alt))
+        if gather_mode == "peer" and rank == 0:
+            seq = h_alt.gather_seq()
+            h_alt.gather_wait(seq)
+            check_gather(h_alt.gather_read(seq, world, words), alt_hashes, "changed-parameter run")
+        elif gather_mode == "nccl":
+            stage[0].copy_(torch.as_tensor(_DevArray(h_alt.device_results()[1], (words,)), device="cuda"))
+            got = gather_cone_lists(stage[0])
+            if rank == 0:
+                check_gather(got.cpu().numpy(), alt_hashes, "changed-parameter run")
+        gather_check = {"ranks_checked": world, "runs_checked": 2 if gathered[0] is not None or rank else 1,
+                        "changed_run_differs": bool(alt_hashes[0] != hashes[0]),
+                        "how": "sha256 of every rank's own cp_batch_results vs the block it published on rank 0"}
+        barrier()
+        h_alt.run(d, g)           # leave the handle (and its replay graph) on the benchmark parameters
+        h_alt.sync()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -384,6 +446,7 @@ def run_ours(args):
     # ---- per-kernel roofline pass (events around each streaming kernel, same workload)
     gpu.set_stage_timing(True)
     k1, k2, kf, kc = [], [], [], []
+    k2_name = ["keep_mask_kernel"]
     for _ in range(min(args.steps, 10)):
         gpu.run(d, g)
         gpu.sync()
@@ -398,6 +461,7 @@ def run_ours(args):
                     k2.append(gpu.stage_ms(1))
                 except api.ConesGpuError:
                     k2.append(gpu.stage_ms(4))      # pass 2 runs inside the per-frame kernel
+                    k2_name[0] = "frame_backend_kernel"
     gpu.set_stage_timing(False)
     C_tot, V_tot, K_tot = int(ctr["n_cropped"].sum()), int(ctr["n_voxels"].sum()), int(ctr["n_clusters"].sum())
     mask_bytes = F * N // 8
@@ -428,11 +492,16 @@ def run_ours(args):
         bytes_k1 = 16 * F * N + 4 * rows_total
         bytes_k2 = 512 * rows_read + 4 * rows_total + mask_bytes
         kernels["ground_sector_min_kernel"] = {"ms": k1_ms, "GBps": bytes_k1 / (k1_ms * 1e-3) / 1e9}
-        kernels["keep_mask_kernel"] = {"ms": k2_ms, "GBps": bytes_k2 / (k2_ms * 1e-3) / 1e9,
-                                       "rows_read_fraction": rows_read / rows_total,
-                                       "unskipped_equivalent_GBps": (16 * F * N + mask_bytes) / (k2_ms * 1e-3) / 1e9}
-        dom = ("ground_sector_min_kernel", k1_ms, bytes_k1) if k1_ms >= k2_ms else \
-            ("keep_mask_kernel", k2_ms, bytes_k2)
+        if k2_name[0] == "frame_backend_kernel":
+            # pass 2 lives in the per-frame kernel: row maxima + live rows in, survivors stay in shared memory
+            # (no keep mask is written), cone records out
+            bytes_k2 = 512 * rows_read + 4 * rows_total + 16 * int(ctr["n_clusters"].sum())
+        kernels[k2_name[0]] = {"ms": k2_ms, "GBps": bytes_k2 / (k2_ms * 1e-3) / 1e9,
+                               "rows_read_fraction": rows_read / rows_total,
+                               "what": "pass 2 (ground verdicts + crop) of the live rows" +
+                                       (", VoxelGrid, clustering, centroids: one CTA per frame"
+                                        if k2_name[0] == "frame_backend_kernel" else "")}
+        dom = ("ground_sector_min_kernel", k1_ms, bytes_k1) if k1_ms >= k2_ms else (k2_name[0], k2_ms, bytes_k2)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
@@ -455,13 +524,23 @@ def run_ours(args):
                              "reads (16 B/point + 4 B written per 32 points), and a read-only stream runs slightly above "
                              "the copy figure, so frac can exceed 1; ncu DRAM bytes (traffic) equal the algorithmic bytes",
                 "algorithmic_bytes_per_launch": dom[2], "kernel_ms": dom[1],
-                "kernels": kernels,
-                "pipeline_algorithmic_bytes_per_step": b_alg_step,
-                "pipeline_GBps": b_alg_step / (ms_total * 1e-3 / args.steps) / 1e9,
-                "pipeline_frac": b_alg_step / (ms_total * 1e-3 / args.steps) / 1e9 / peak,
-                "pipeline_note": "SURVEY 8(d) algorithmic bytes (two full passes over the scan) / step time; it can "
-                                 "exceed 1 because pass 2 provably skips rows that are entirely ground "
-                                 "(see kernels.keep_mask_kernel.rows_read_fraction) instead of reading them"}
+                "kernels": kernels}
+    # whole-step fractions of the measured peak.  bytes moved = what the step's kernels actually read and write
+    # (library counters: every point once in pass 1, the row maxima out and in, only the rows pass 2 could not
+    # skip, the cone records); single read = the strict bound of one pass over the scan plus the results.
+    # SURVEY 8(d)'s B_alg charges two full passes (32 B/point); it is listed for reference only, a step that
+    # skips provably-ground rows moves less than that.
+    step_s = ms_total * 1e-3 / args.steps
+    rows_total = F * N // 32
+    rows_read_step = gpu.last_rows_loaded()
+    moved = 16 * F * N + 8 * rows_total + 512 * rows_read_step + 16 * K_tot
+    single = 16 * F * N + 16 * K_tot
+    roofline.update({
+        "step_bytes_moved": moved, "step_frac_bytes_moved": moved / step_s / 1e9 / peak,
+        "step_bytes_single_read": single, "step_frac_single_read": single / step_s / 1e9 / peak,
+        "survey_b_alg_bytes_per_step": b_alg_step,
+        "step_note": "fractions of the measured HBM peak over the whole step (all kernels, both lanes); "
+                     "profiles/traffic.json holds the ncu DRAM sum of the same step"})
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + pipeline + D2H
     msgs = [PointCloud2.from_xyzi(hnp[f]) for f in range(F)]
@@ -480,8 +559,10 @@ def run_ours(args):
         if st != 0:
             raise RuntimeError(lib.cp_last_error(h._h).decode())
 
+    cur_views = [views]
+
     def submit_e2e(h):          # H2D of the batch (pinned -> device) + the whole pipeline, asynchronous
-        ck(h, lib.cp_batch_set_host_input(h._h, views, F))
+        ck(h, lib.cp_batch_set_host_input(h._h, cur_views[0], F))
         ck(h, lib.cp_batch_run(h._h, C.byref(cd), C.byref(cg)))
 
     def collect_e2e(h):         # D2H of counters, offsets and the cone list of the handle's batch
@@ -501,23 +582,207 @@ def run_ours(args):
             collect_e2e(pending.pop(0))
 
     e2e_steps = max(4, min(args.steps, 10))
-    run_e2e(2 * len(lanes))
-    barrier()
-    t0 = time.perf_counter()
-    run_e2e(e2e_steps)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+
+    def time_e2e(v):
+        cur_views[0] = v
+        run_e2e(2 * len(lanes))
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(e2e_steps)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert total.value == K_tot and np.array_equal(o_cl[:K_tot].view(np.uint32), clusters.view(np.uint32)), \
+            "host-input and device-input runs disagree"
+        return world * F * N * e2e_steps / float(dt.item())
+
+    e2e_pinned = time_e2e(views)
     clocks = sampler.stop() if rank == 0 else None   # sampled across both timed regions (resident + e2e)
+    # the same batch in write-combined page-locked memory (cp_pinned_alloc(.., write_combined = 1)): the DMA reads
+    # it without snooping CPU caches.  Same public call; reported beside the default, the better one is `value`.
+    e2e_wc = None
+    if os.environ.get("BENCH_WC", "1") != "0":
+        try:
+            wc = api.PinnedBuffer(F * N * 16, device=local, write_combined=True)
+            wnp = wc.array.view(np.float32).reshape(F, N, 4)
+            np.copyto(wnp, hnp)
+            wmsgs = [PointCloud2.from_xyzi(wnp[f]) for f in range(F)]
+            wviews = (CCloudView * F)(*[make_view(m, True) for m in wmsgs])
+            e2e_wc = time_e2e(wviews)
+            cur_views[0] = views
+            del wviews, wmsgs, wnp
+            wc.close()
+        except Exception as e:
+            print(f"[bench] write-combined variant skipped: {e}", file=sys.stderr)
+            e2e_wc = None
+    flags = torch.tensor([1.0 if e2e_wc is not None else 0.0], device="cuda")
     if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_val = world * F * N * e2e_steps / float(e2e_s.item())
-    assert total.value == K_tot and np.array_equal(o_cl[:K_tot].view(np.uint32), clusters.view(np.uint32)), \
-        "host-input and device-input runs disagree"
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if float(flags.item()) == 0.0:
+        e2e_wc = None
+    e2e_val = max(e2e_pinned, e2e_wc or 0.0)
     d2h = int(o_ctr.nbytes + o_off.nbytes + K_tot * 16 + 64)
+    probe_rates = [p_["GBps"] for p_ in probes]
+    probe_total = float(sum(probe_rates))
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(F * N * 16), "d2h_bytes_per_step": d2h,
            "frames_per_sec": e2e_val / N, "steps": e2e_steps,
+           "source_memory": "write_combined" if (e2e_wc or 0.0) > e2e_pinned else "pinned",
+           "variants": {"pinned": e2e_pinned, "write_combined": e2e_wc},
+           "h2d_GBps": e2e_val * 16 / 1e9,
+           "h2d_probe_GBps": {"per_rank": probe_rates, "aggregate": probe_total,
+                              "how": "every rank at the same time: 6 x 1 GiB pinned cudaMemcpyAsync, CUDA events "
+                                     "(cones_perception_b200/placement.py h2d_probe), after rank placement"},
+           "frac_of_probe": e2e_val * 16 / 1e9 / probe_total if probe_total > 0 else None,
+           "placement": [p_["bind"] for p_ in probes],
            "timer": "host wall clock around cp_batch_set_host_input + cp_batch_run + cp_batch_results per step "
-                    f"(pinned host clouds), {len(lanes)} batch(es) in flight"}
+                    f"(page-locked host clouds), {len(lanes)} batch(es) in flight"}
+
+    # ---- sub-records: the same step under other conditions (all inside the default command)
+    subs = {}
+    dev_t = torch.device("cuda", local)
+    rows_total = F * N // 32
+
+    def new_handle(frames, env=None):
+        h = api.ConesGpu(max_points=frames * N, max_frames=frames, device=local,
+                         max_survivors=max(frames * N // 8, 1 << 20), max_voxels=max(frames * N // 16, 1 << 19),
+                         env=env)
+        return h
+
+    def timed_run(handles, n_steps, dp=d, gp=g):
+        """Device-resident ms/step over n_steps, handles alternating; CUDA events; max over ranks."""
+        sts = [torch.cuda.ExternalStream(h.stream(), device=dev_t) for h in handles]
+        for i in range(3 * len(handles)):
+            handles[i % len(handles)].run(dp, gp)
+        for h in handles:
+            h.sync()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(sts[0])
+        for s_ in sts[1:]:
+            s_.wait_event(a)
+        for i in range(n_steps):
+            handles[i % len(handles)].run(dp, gp)
+        for s_ in sts[1:]:
+            sts[0].wait_stream(s_)
+        b.record(sts[0])
+        barrier()
+        for h in handles:
+            h.sync()
+        t = torch.tensor([a.elapsed_time(b)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n_steps
+
+    if args.sub_records:
+        sub_steps = max(4, min(args.steps, 20))
+        # (1) the exact row skip switched off: pass 2 reads every row
+        hs = [new_handle(F, env={"CONESGPU_ROWSKIP": "0"}) for _ in lanes]
+        for h in hs:
+            h.set_device_input(dev.data_ptr(), frame_points, keep=dev)
+        ms_ = timed_run(hs, sub_steps)
+        _, off_, cl_ = hs[0].results()
+        assert np.array_equal(cl_.view(np.uint32), clusters.view(np.uint32)), "row skip changes the result"
+        subs["rowskip_off"] = {"ms_per_step": ms_, "value": world * F * N / (ms_ * 1e-3), "unit": UNIT,
+                               "rows_read_fraction": hs[0].last_rows_loaded() / rows_total,
+                               "what": "same step with CONESGPU_ROWSKIP=0 (pass 2 reads the whole scan again)"}
+        for h in hs:
+            h.close()
+        # (2) the same scans in firing order (azimuth-major: a 32-point row mixes 32 beams), as an unorganised
+        # Velodyne driver publishes them; results checked against the oracle on the permuted clouds
+        dev_az = dev.view(F, cfg.beams, cfg.az * cfg.sweeps, 4).transpose(1, 2).contiguous()
+        for h in lanes:
+            h.set_device_input(dev_az.data_ptr(), frame_points, keep=dev_az)
+        ms_ = timed_run(lanes, sub_steps)
+        ctr_a, off_a, cl_a = lanes[0].results()
+        az = {"ms_per_step": ms_, "value": world * F * N / (ms_ * 1e-3), "unit": UNIT,
+              "rows_read_fraction": lanes[0].last_rows_loaded() / rows_total,
+              "clusters_per_step": int(off_a[-1]),
+              "what": "same scans permuted from ring-major to firing order (azimuth-major)"}
+        if rank == 0 and args.cpu_sample_frames > 0:
+            from oracle import oracle as O
+            nchk = min(8, F)
+            az_host = dev_az[:nchk].cpu().numpy()
+            kept = []
+            for f in range(nchk):
+                ocl, oc, _ = O.detect(O.view_of_xyzi(az_host[f]), d, g, O.CANONICAL)
+                kept.append((ocl, (oc.n_ground_kept, oc.n_cropped, oc.n_voxels, oc.n_components, oc.n_clusters)))
+                got = cl_a[off_a[f]:off_a[f + 1]]
+                assert np.array_equal(got.view(np.uint32), ocl.view(np.uint32)), f"azimuth-major frame {f} differs"
+            compare_with_oracle(kept, ctr_a, off_a, cl_a)
+            az["oracle_checked_frames"] = nchk
+        subs["azimuth_major"] = az
+        for h in lanes:
+            h.set_device_input(dev.data_ptr(), frame_points, keep=dev)
+        del dev_az
+        # (3) BASELINE.json config 3 as worded: ONE batch of 4096 scans, sharded over the GPUs (strong scaling)
+        G_FR = args.strong_frames
+        Fs = G_FR // world
+        if Fs == F:
+            subs["strong_4096"] = {"frames_per_gpu": Fs, "global_frames": G_FR, "ms_per_step": ms_total / args.steps,
+                                   "value": value, "unit": UNIT, "scaling": "strong",
+                                   "what": "identical to the headline at this N (4096 / N = frames per GPU)"}
+        elif Fs > 0:
+            dev_s = torch.empty((Fs, N, 4), dtype=torch.float32, device=dev_t)
+            for c0 in range(0, Fs, F):
+                nc = min(F, Fs - c0)
+                scans.generate(cfg, nc, base_seed=rank * Fs + c0, out=hnp[:nc])
+                dev_s[c0:c0 + nc].copy_(host[:nc])
+            scans.generate(cfg, F, base_seed=rank * F, out=hnp)        # the pinned batch back to the headline's frames
+            fp_s = np.full(Fs, N, dtype=np.uint32)
+            hs = [new_handle(Fs) for _ in lanes]
+            for h in hs:
+                h.set_device_input(dev_s.data_ptr(), fp_s, keep=dev_s)
+            ms_ = timed_run(hs, sub_steps)
+            ctr_s, off_s, cl_s = hs[0].results()
+            if rank == 0:      # rank 0's shard starts with the headline's frames (same seeds): same cones
+                nf = min(F, Fs)
+                assert np.array_equal(cl_s[:off_s[nf]].view(np.uint32), clusters[:k_off[nf]].view(np.uint32)), \
+                    "the 4096-frame batch disagrees with the headline batch on their common frames"
+            subs["strong_4096"] = {"frames_per_gpu": Fs, "global_frames": Fs * world, "ms_per_step": ms_,
+                                   "value": world * Fs * N / (ms_ * 1e-3), "unit": UNIT,
+                                   "frames_per_sec": world * Fs / (ms_ * 1e-3), "scaling": "strong",
+                                   "clusters_per_step_rank0": int(off_s[-1]),
+                                   "input_GB_per_gpu": Fs * N * 16 / 1e9,
+                                   "what": f"one batch of {Fs * world} scans, {Fs} per GPU, device-resident, "
+                                           f"{len(hs)} batches in flight"}
+            for h in hs:
+                h.close()
+            del dev_s
+        # (4) BASELINE.json configs 4 and 5 (N = 1 only): dense 2.6 M-point frames / adversarial clustering
+        if world == 1:
+            for idx in (4, 5):
+                cfgx = scans.config(idx)
+                rec = {}
+                for Fx in (1, 8):
+                    fr = scans.generate_config5(Fx, 0) if idx == 5 else scans.generate(cfgx, Fx, 0)
+                    Nx = fr.shape[1]
+                    dx = torch.from_numpy(np.ascontiguousarray(fr)).to(dev_t)
+                    with api.ConesGpu(max_points=Fx * Nx, max_frames=Fx, device=local) as hx:
+                        hx.set_device_input(dx.data_ptr(), np.full(Fx, Nx, np.uint32), keep=dx)
+                        for _ in range(4):
+                            hx.run(cfgx.detect, cfgx.ground)
+                            hx.sync()
+                        cx, ox, _ = hx.results()
+                        lat_ = []
+                        for _ in range(20):
+                            t_ = time.perf_counter()
+                            hx.run(cfgx.detect, cfgx.ground)
+                            hx.sync()
+                            lat_.append(1e3 * (time.perf_counter() - t_))
+                        msx = float(np.percentile(lat_, 50))
+                        Px = (int(cx["key_bits"].max()) + 7) // 8
+                        Cx, Vx, Kx = int(cx["n_cropped"].sum()), int(cx["n_voxels"].sum()), int(cx["n_clusters"].sum())
+                        b_alg = (32 if cfgx.ground is not None else 16) * Fx * Nx + (72 + 16 * Px) * Cx + 104 * Vx + 16 * Kx
+                        rec["single" if Fx == 1 else "batch8"] = {
+                            "ms_per_frame": msx / Fx, "points_per_frame": Nx, "C": Cx // Fx, "V": Vx // Fx, "K": Kx // Fx,
+                            "launches": hx.last_launch_count(), "b_alg_bytes_per_frame": b_alg // Fx,
+                            "GBps": b_alg / (msx * 1e-3) / 1e9, "frac_of_peak": b_alg / (msx * 1e-3) / 1e9 / peak}
+                    del dx
+                rec["what"] = ("dense 128-beam x 10-sweep cloud, fsai params" if idx == 4 else
+                               "adversarial clustering (fences, 10.6k-voxel chain, solid blobs), simulation params") + \
+                              "; p50 of 20 runs through cp_batch_run + cp_sync, device-resident"
+                subs[f"cfg{idx}"] = rec
 
     line = None
     if rank == 0:
@@ -572,16 +837,19 @@ def run_ours(args):
         if world == 1 and args.cpu_sample_frames > 0:
             ns = min(args.cpu_sample_frames, F)
             dt, stages, passes = 0.0, None, 0
+            kept = [None] * ns
             while dt < args.cpu_sample_seconds and passes < 8:      # about 10 s of single-core work
-                d1, stages = cpu_frames_per_sec(hnp[:ns], cfg, threads=1)
+                d1, stages = cpu_frames_per_sec(hnp[:ns], cfg, threads=1, keep=kept if passes == 0 else None)
                 dt += d1
                 passes += 1
+            # parity of the TIMED batch: the oracle's clusters for these frames against the GPU step's results
+            parity = compare_with_oracle(kept, ctr, k_off, clusters)
             cpu = {"value": passes * ns * N / dt, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"first {ns} frames of the step's batch x {passes} passes, oracle pcl_faithful mode "
                              f"(PCL cost profile), g++ -O2, single thread like the reference's ros::spin nodes",
                    "frames_per_sec": passes * ns / dt, "ms_per_frame": 1e3 * dt / (passes * ns),
                    "stage_ms_per_frame": stages,
-                   "host_cores_available": os.cpu_count()}
+                   "host_cores_available": os.cpu_count(), "parity_of_timed_batch": parity}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -591,15 +859,16 @@ def run_ours(args):
             "p50_frame_latency_pageable_ms": float(np.percentile(lat_page, 50)),
             "p50_frame_latency_device_resident_ms": float(np.percentile(lat_dev, 50)),
             "config": {"workload": "cfg3: batch of 64-beam 131072-pt scans (simulation params, ground removal on), "
-                                   f"{F} frames per GPU, frame-sharded, cone lists gathered over NCCL when N>1",
+                                   f"{F} frames per GPU, frame-sharded; when N>1 every rank publishes its cone list into rank 0's "
+                                   "memory (CUDA-IPC peer stores over NVLink), NCCL for setup / barriers only",
                        "frames_per_gpu": F, "points_per_frame": N, "global_frames": world * F,
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                       "result_gather": gather_mode, "host_binding_rank0": numa,
+                       "result_gather": gather_mode, "result_gather_check": gather_check,
                        "batches_in_flight": len(lanes),
                        "cache": f"inputs larger than L2 ({F * N * 16 / 1e6:.0f} MB per rank vs 126 MB), no flush needed",
                        "latency_workload": "cfg2 single frame, host cloud in -> cone list out"},
             "per_step_counts": {"points": F * N, "cropped": C_tot, "voxels": V_tot, "clusters": K_tot},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sub_records": subs,
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
         }
@@ -625,6 +894,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=2, help="batches in flight (handles/streams alternating per step)")
     ap.add_argument("--cpu-sample-frames", type=int, default=512, help="frames timed on one core for cpu_baseline")
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0, help="minimum CPU time spent on cpu_baseline")
+    ap.add_argument("--no-sub-records", dest="sub_records", action="store_false",
+                    help="skip rowskip_off / azimuth_major / strong_4096 / cfg4 / cfg5")
+    ap.add_argument("--strong-frames", type=int, default=4096, help="global batch of the strong-scaling sub-record")
     ap.add_argument("--cpu-step-frames", type=int, default=128, help="frames per step of --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -192,7 +192,42 @@ def synthetic(idx, seed):
     print(f"cfg{idx} seed {seed}: K={len(cl)} V={ctr.n_voxels} C={ctr.n_cropped} sha={digest[:12]}")
 
 
+PCL_PIN_CASES = ((1, 0), (2, 0), (3, 5), (4, 0), (5, 0))      # (config, seed): one frame of each BASELINE.json config
+
+
+def pcl_pin_input(idx, seed):
+    """The cloud the reference hands to pcl::VoxelGrid for one frame of config idx: the crop survivors
+    (ground removal + zero padding + filter_points_position), x, y, z, intensity as float32 [C,4]."""
+    from tests.util import oracle_stages
+    cfg = scans.config(idx)
+    frame = scans.generate_config5(1, seed)[0] if idx == 5 else scans.generate(cfg, 1, seed)[0]
+    st = oracle_stages(frame, cfg.detect, cfg.ground)
+    c = st["cropped"]
+    pts = np.ascontiguousarray(np.stack([c["x"], c["y"], c["z"], c["intensity"]], 1), np.float32)
+    return cfg, pts
+
+
+def pcl_inputs(out_dir):
+    """Inputs of tools/pcl_pin (run where the real PCL exists): <out_dir>/<name>.bin + manifest.json."""
+    import json
+    os.makedirs(out_dir, exist_ok=True)
+    manifest = []
+    for idx, seed in PCL_PIN_CASES:
+        cfg, pts = pcl_pin_input(idx, seed)
+        name = f"cfg{idx}_seed{seed}"
+        pts.tofile(os.path.join(out_dir, name + ".bin"))
+        d = cfg.detect
+        manifest.append({"name": name, "points": int(len(pts)), "sha256": hashlib.sha256(pts.tobytes()).hexdigest(),
+                         "leaf": [d.voxel_filter_leaf_size_x, d.voxel_filter_leaf_size_y, d.voxel_filter_leaf_size_z],
+                         "min_cluster_size": d.min_cluster_size, "max_cluster_size": d.max_cluster_size})
+        print(f"pcl input {name}: {len(pts)} survivors")
+    json.dump(manifest, open(os.path.join(out_dir, "manifest.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "pcl_inputs":
+        pcl_inputs(sys.argv[2])
+        sys.exit(0)
     cone_crops()
     cone_images()
     reference_nodes()

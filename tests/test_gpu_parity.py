@@ -387,7 +387,10 @@ def test_pass2_inside_the_frame_kernel_equals_the_streaming_kernel(ground):
             assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), name
         if name == "uniform":     # (a partly filled last tile: the streaming kernel also counts its padding rows)
             assert out["2"][3] == out["0"][3], (name, "rows read differ")
-            assert out["2"][4] < out["0"][4], (name, "the fused path must need fewer launches")
+            if ground:
+                assert out["2"][4] < out["0"][4], (name, "the fused path must need fewer launches")
+            else:   # with the ground left in, these frames outgrow shared memory: both end on the general back half
+                assert out["2"][4] <= out["0"][4], (name, "launch count")
         for f, a in enumerate(fr):
             exp, octr, _ = O.detect(O.view_of_xyzi(a), cfg.detect, g, O.CANONICAL)
             got = out["2"][2][out["2"][1][f]:out["2"][1][f + 1]]
