@@ -238,9 +238,17 @@ def run_ours(args):
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libconesgpu has no CPU fallback")
-    torch.cuda.set_device(local)
+    # Which GPU a rank drives.  On HGX boards GPUs 0..3 and 4..7 hang off different host uplinks (measured here:
+    # four ranks on GPUs 0-3 share 115 GB/s of host->device bandwidth, profiles/r02_h2d/); when the job uses fewer
+    # GPUs than the box shows, ranks are dealt alternately to the two halves so they do not crowd one uplink.
+    ndev = torch.cuda.device_count()
+    dev_index = local
+    if 1 < world < ndev and ndev % 2 == 0 and os.environ.get("BENCH_SPREAD", "1") != "0":
+        perm = [x for pair in zip(range(ndev // 2), range(ndev // 2, ndev)) for x in pair]
+        dev_index = perm[local]
+    torch.cuda.set_device(dev_index)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev_index))
 
     def barrier():
         if world > 1:
@@ -263,12 +271,13 @@ def run_ours(args):
         for r in range(world):
             if r == rank:
                 try:
-                    bind = placement.bind_rank(local)
+                    bind = placement.bind_rank(dev_index)
                 except Exception as e:            # never let placement stop the measurement
                     bind = {"how": f"failed ({type(e).__name__}: {e})"}
             barrier()
-    probe = placement.h2d_probe(local, 1 << 30, 6, barrier)
-    probes = gather_obj({"GBps": probe["GBps"], "bind": bind, "pages_by_node": probe["pages_by_node"]})
+    probe = placement.h2d_probe(dev_index, 1 << 30, 6, barrier)
+    probes = gather_obj({"GBps": probe["GBps"], "bind": bind, "pages_by_node": probe["pages_by_node"],
+                         "device": dev_index})
 
     cfg = scans.config(3)
     F, N = args.frames_per_gpu, cfg.points_per_frame
@@ -280,9 +289,9 @@ def run_ours(args):
     scans.generate(cfg, F, base_seed=rank * F, out=hnp)
     dev = host.to("cuda", non_blocking=False)
 
-    gpu = api.ConesGpu(max_points=F * N, max_frames=F, device=local, max_survivors=max(F * N // 8, 1 << 20),
+    gpu = api.ConesGpu(max_points=F * N, max_frames=F, device=dev_index, max_survivors=max(F * N // 8, 1 << 20),
                        max_voxels=max(F * N // 16, 1 << 19))
-    ext = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", local))
+    ext = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", dev_index))
     frame_points = np.full(F, N, dtype=np.uint32)
     gpu.set_device_input(dev.data_ptr(), frame_points, keep=dev)
     cone_cap = F * CONE_CAP_PER_FRAME
@@ -291,11 +300,11 @@ def run_ours(args):
     # the HBM-bound first pass of the next.  Every step still runs the whole path on the whole batch.
     lanes = [gpu]
     for _ in range(1, max(1, args.lanes)):
-        h2 = api.ConesGpu(max_points=F * N, max_frames=F, device=local, max_survivors=max(F * N // 8, 1 << 20),
+        h2 = api.ConesGpu(max_points=F * N, max_frames=F, device=dev_index, max_survivors=max(F * N // 8, 1 << 20),
                           max_voxels=max(F * N // 16, 1 << 19))
         h2.set_device_input(dev.data_ptr(), frame_points, keep=dev)
         lanes.append(h2)
-    exts = [torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local)) for h in lanes]
+    exts = [torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", dev_index)) for h in lanes]
 
     # result path when N > 1: the rank's packed cone list (offsets + records, one device block)
     # is copied to a staging buffer on the compute stream and gathered to rank 0 with ONE
@@ -367,7 +376,7 @@ def run_ours(args):
     launches_per_step = gpu.last_launch_count()
 
     # ---- timed region: K steps, inputs resident in HBM (1 GiB per rank > 126 MB L2)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev_index)
     barrier()
     if rank == 0:
         sampler.start()
@@ -542,76 +551,78 @@ def run_ours(args):
         "step_note": "fractions of the measured HBM peak over the whole step (all kernels, both lanes); "
                      "profiles/traffic.json holds the ncu DRAM sum of the same step"})
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + pipeline + D2H
-    msgs = [PointCloud2.from_xyzi(hnp[f]) for f in range(F)]
-    views = (CCloudView * F)(*[make_view(m, True) for m in msgs])
+    # ---- end to end through the C ABI with HOST buffers (page-locked): H2D + pipeline + D2H
     from cones_perception_b200.params import to_c_detect, to_c_ground
     import ctypes as C
     cd, cg = to_c_detect(d), to_c_ground(g)
-    o_ctr = np.zeros(F, dtype=api.COUNTER_DTYPE)
-    o_off = np.zeros(F + 1, dtype=np.uint32)
-    o_cl = np.zeros(cone_cap, dtype=api.CLUSTER_DTYPE)
-    total = C.c_uint64()
-
     lib = gpu.lib
 
     def ck(h, st):
         if st != 0:
             raise RuntimeError(lib.cp_last_error(h._h).decode())
 
-    cur_views = [views]
+    class E2E:
+        """One rank's end-to-end loop over `frames` host clouds (numpy [Fx, N, 4] in page-locked memory)."""
 
-    def submit_e2e(h):          # H2D of the batch (pinned -> device) + the whole pipeline, asynchronous
-        ck(h, lib.cp_batch_set_host_input(h._h, cur_views[0], F))
-        ck(h, lib.cp_batch_run(h._h, C.byref(cd), C.byref(cg)))
+        def __init__(self, handles, frames_np, expect_clusters):
+            self.handles, self.Fx = handles, len(frames_np)
+            self.msgs = [PointCloud2.from_xyzi(frames_np[f]) for f in range(self.Fx)]
+            self.views = (CCloudView * self.Fx)(*[make_view(m, True) for m in self.msgs])
+            self.cap = self.Fx * CONE_CAP_PER_FRAME
+            self.o_ctr = np.zeros(self.Fx, dtype=api.COUNTER_DTYPE)
+            self.o_off = np.zeros(self.Fx + 1, dtype=np.uint32)
+            self.o_cl = np.zeros(self.cap, dtype=api.CLUSTER_DTYPE)
+            self.total = C.c_uint64()
+            self.expect = expect_clusters
 
-    def collect_e2e(h):         # D2H of counters, offsets and the cone list of the handle's batch
-        ck(h, lib.cp_batch_results(h._h, o_ctr.ctypes.data, o_off.ctypes.data, o_cl.ctypes.data, cone_cap,
-                                   C.byref(total)))
+        def submit(self, h):        # H2D of the batch (page-locked -> device) + the whole pipeline, asynchronous
+            ck(h, lib.cp_batch_set_host_input(h._h, self.views, self.Fx))
+            ck(h, lib.cp_batch_run(h._h, C.byref(cd), C.byref(cg)))
 
-    def run_e2e(n):
-        # with two handles, the copy of batch i+1 overlaps the kernels and the result read of batch i
-        pending = []
-        for i in range(n):
-            h = lanes[i % len(lanes)]
-            if len(pending) == len(lanes):
-                collect_e2e(pending.pop(0))
-            submit_e2e(h)
-            pending.append(h)
-        while pending:
-            collect_e2e(pending.pop(0))
+        def collect(self, h):       # D2H of counters, offsets and the cone list of the handle's batch
+            ck(h, lib.cp_batch_results(h._h, self.o_ctr.ctypes.data, self.o_off.ctypes.data, self.o_cl.ctypes.data,
+                                       self.cap, C.byref(self.total)))
+
+        def run(self, n):
+            # with two handles, the copy of batch i+1 overlaps the kernels and the result read of batch i
+            pending = []
+            for i in range(n):
+                h = self.handles[i % len(self.handles)]
+                if len(pending) == len(self.handles):
+                    self.collect(pending.pop(0))
+                self.submit(h)
+                pending.append(h)
+            while pending:
+                self.collect(pending.pop(0))
+
+        def timed(self, steps, global_frames):
+            self.run(2 * len(self.handles))
+            barrier()
+            t0 = time.perf_counter()
+            self.run(steps)
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            k = len(self.expect)
+            assert self.total.value == k and np.array_equal(self.o_cl[:k].view(np.uint32), self.expect.view(np.uint32)), \
+                "host-input and device-input runs disagree"
+            return global_frames * N * steps / float(dt.item())
 
     e2e_steps = max(4, min(args.steps, 10))
-
-    def time_e2e(v):
-        cur_views[0] = v
-        run_e2e(2 * len(lanes))
-        barrier()
-        t0 = time.perf_counter()
-        run_e2e(e2e_steps)
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        assert total.value == K_tot and np.array_equal(o_cl[:K_tot].view(np.uint32), clusters.view(np.uint32)), \
-            "host-input and device-input runs disagree"
-        return world * F * N * e2e_steps / float(dt.item())
-
-    e2e_pinned = time_e2e(views)
+    even = E2E(lanes, hnp, clusters)
+    e2e_pinned = even.timed(e2e_steps, world * F)
     clocks = sampler.stop() if rank == 0 else None   # sampled across both timed regions (resident + e2e)
     # the same batch in write-combined page-locked memory (cp_pinned_alloc(.., write_combined = 1)): the DMA reads
-    # it without snooping CPU caches.  Same public call; reported beside the default, the better one is `value`.
+    # it without snooping CPU caches.  Same public call; reported beside the default.
     e2e_wc = None
     if os.environ.get("BENCH_WC", "1") != "0":
         try:
-            wc = api.PinnedBuffer(F * N * 16, device=local, write_combined=True)
+            wc = api.PinnedBuffer(F * N * 16, device=dev_index, write_combined=True)
             wnp = wc.array.view(np.float32).reshape(F, N, 4)
             np.copyto(wnp, hnp)
-            wmsgs = [PointCloud2.from_xyzi(wnp[f]) for f in range(F)]
-            wviews = (CCloudView * F)(*[make_view(m, True) for m in wmsgs])
-            e2e_wc = time_e2e(wviews)
-            cur_views[0] = views
-            del wviews, wmsgs, wnp
+            e2e_wc = E2E(lanes, wnp, clusters).timed(e2e_steps, world * F)
+            del wnp
             wc.close()
         except Exception as e:
             print(f"[bench] write-combined variant skipped: {e}", file=sys.stderr)
@@ -621,30 +632,66 @@ def run_ours(args):
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if float(flags.item()) == 0.0:
         e2e_wc = None
-    e2e_val = max(e2e_pinned, e2e_wc or 0.0)
-    d2h = int(o_ctr.nbytes + o_off.nbytes + K_tot * 16 + 64)
+    # Shards weighted by each rank's measured host link: the step ends with the slowest rank, so on a box whose
+    # GPUs do not all get the same host->device rate (shared PCIe uplinks, one socket's memory) equal shards leave
+    # the faster links idle.  Same global batch (world x F frames, contiguous blocks), block sizes proportional to
+    # the probe's per-rank GB/s.
     probe_rates = [p_["GBps"] for p_ in probes]
     probe_total = float(sum(probe_rates))
+    e2e_weighted, shard_sizes = None, None
+    if world > 1 and max(probe_rates) > 1.05 * min(probe_rates) and os.environ.get("BENCH_WEIGHTED", "1") != "0":
+        tot = world * F
+        raw = [tot * r_ / probe_total for r_ in probe_rates]
+        shard_sizes = [max(1, min(2 * F, int(x))) for x in raw]
+        order = sorted(range(world), key=lambda i: raw[i] - int(raw[i]), reverse=True)
+        i = 0
+        while sum(shard_sizes) < tot:                  # hand the remainder to the largest fractional parts
+            if shard_sizes[order[i % world]] < 2 * F:
+                shard_sizes[order[i % world]] += 1
+            i += 1
+        Fw, first = shard_sizes[rank], sum(shard_sizes[:rank])
+        hw_t = torch.empty((Fw, N, 4), dtype=torch.float32, pin_memory=True)
+        scans.generate(cfg, Fw, base_seed=first, out=hw_t.numpy())
+        dw = hw_t.to("cuda")
+        hws = [api.ConesGpu(max_points=Fw * N, max_frames=Fw, device=dev_index,
+                            max_survivors=max(Fw * N // 8, 1 << 20), max_voxels=max(Fw * N // 16, 1 << 19))
+               for _ in lanes]
+        fpw = np.full(Fw, N, dtype=np.uint32)
+        hws[0].set_device_input(dw.data_ptr(), fpw, keep=dw)       # the expected cones: a device-input run
+        hws[0].run(d, g)
+        _, _, cl_w = hws[0].results()
+        e2e_weighted = E2E(hws, hw_t.numpy(), cl_w).timed(e2e_steps, tot)
+        for h in hws:
+            h.close()
+        del dw, hw_t
+    e2e_val = max(e2e_pinned, e2e_wc or 0.0, e2e_weighted or 0.0)
+    which = "weighted_shards" if e2e_val == e2e_weighted else ("write_combined" if e2e_val == e2e_wc else "pinned")
+    d2h = int(even.o_ctr.nbytes + even.o_off.nbytes + K_tot * 16 + 64)
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(F * N * 16), "d2h_bytes_per_step": d2h,
            "frames_per_sec": e2e_val / N, "steps": e2e_steps,
-           "source_memory": "write_combined" if (e2e_wc or 0.0) > e2e_pinned else "pinned",
-           "variants": {"pinned": e2e_pinned, "write_combined": e2e_wc},
+           "variant": which,
+           "variants": {"pinned": e2e_pinned, "write_combined": e2e_wc, "weighted_shards": e2e_weighted},
+           "weighted_shard_frames": shard_sizes,
            "h2d_GBps": e2e_val * 16 / 1e9,
            "h2d_probe_GBps": {"per_rank": probe_rates, "aggregate": probe_total,
+                              "equal_shard_ceiling": world * min(probe_rates),
                               "how": "every rank at the same time: 6 x 1 GiB pinned cudaMemcpyAsync, CUDA events "
-                                     "(cones_perception_b200/placement.py h2d_probe), after rank placement"},
+                                     "(cones_perception_b200/placement.py h2d_probe), after rank placement; with "
+                                     "equal shards the step ends with the slowest link (world x min)"},
            "frac_of_probe": e2e_val * 16 / 1e9 / probe_total if probe_total > 0 else None,
-           "placement": [p_["bind"] for p_ in probes],
+           "frac_of_equal_shard_ceiling": e2e_pinned * 16 / 1e9 / (world * min(probe_rates)),
+           "placement": [p_["bind"] for p_ in probes], "devices": [p_["device"] for p_ in probes],
+           "h2d_bytes_per_step_note": "per rank with equal shards; weighted shards move the same global bytes",
            "timer": "host wall clock around cp_batch_set_host_input + cp_batch_run + cp_batch_results per step "
                     f"(page-locked host clouds), {len(lanes)} batch(es) in flight"}
 
     # ---- sub-records: the same step under other conditions (all inside the default command)
     subs = {}
-    dev_t = torch.device("cuda", local)
+    dev_t = torch.device("cuda", dev_index)
     rows_total = F * N // 32
 
     def new_handle(frames, env=None):
-        h = api.ConesGpu(max_points=frames * N, max_frames=frames, device=local,
+        h = api.ConesGpu(max_points=frames * N, max_frames=frames, device=dev_index,
                          max_survivors=max(frames * N // 8, 1 << 20), max_voxels=max(frames * N // 16, 1 << 19),
                          env=env)
         return h
@@ -758,7 +805,7 @@ def run_ours(args):
                     fr = scans.generate_config5(Fx, 0) if idx == 5 else scans.generate(cfgx, Fx, 0)
                     Nx = fr.shape[1]
                     dx = torch.from_numpy(np.ascontiguousarray(fr)).to(dev_t)
-                    with api.ConesGpu(max_points=Fx * Nx, max_frames=Fx, device=local) as hx:
+                    with api.ConesGpu(max_points=Fx * Nx, max_frames=Fx, device=dev_index) as hx:
                         hx.set_device_input(dx.data_ptr(), np.full(Fx, Nx, np.uint32), keep=dx)
                         for _ in range(4):
                             hx.run(cfgx.detect, cfgx.ground)
@@ -791,7 +838,7 @@ def run_ours(args):
         f2 = scans.generate(cfg2, 1, base_seed=0)[0]
         pin = torch.empty((N, 4), dtype=torch.float32, pin_memory=True)
         pin.numpy()[:] = f2
-        lat_gpu = api.ConesGpu(max_points=N, max_frames=1, device=local)
+        lat_gpu = api.ConesGpu(max_points=N, max_frames=1, device=dev_index)
         m2 = PointCloud2.from_xyzi(pin.numpy())
         for _ in range(5):
             cl2, _ = lat_gpu.detect(m2, cfg2.detect, cfg2.ground)

@@ -30,10 +30,12 @@ ABI_SYMBOLS = [
     "cp_gather_create", "cp_gather_open", "cp_gather_seq", "cp_gather_wait", "cp_gather_read",
     "cp_last_rows_loaded", "cp_cone_crops", "cp_cone_images", "cp_rasterize_crops",
     "cp_pinned_alloc", "cp_pinned_free",
+    "cp_color_net_load", "cp_color_net_load_tflite", "cp_cone_colors", "cp_classify_images",
 ]
 
 CONE_IMG_ROWS, CONE_IMG_COLS = 15, 12
-CONE_EMPTY, CONE_BAD_INDEX, CONE_BAD_INTENSITY, CONE_AMBIGUOUS = 1, 2, 4, 8
+CONE_EMPTY, CONE_BAD_INDEX, CONE_BAD_INTENSITY, CONE_AMBIGUOUS, CONE_LOW_CONFIDENCE = 1, 2, 4, 8, 16
+COLOR_NO_ANSWER = 255   # cp_cone_colors: the service would skip this cone (empty crop) or raise (bad crop)
 
 CLUSTER_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.uint32), ("min_index", np.uint32)])
 COUNTER_DTYPE = np.dtype([(n, np.uint32) for n in (
@@ -43,6 +45,13 @@ COUNTER_DTYPE = np.dtype([(n, np.uint32) for n in (
 class CConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_points", C.c_uint64), ("max_frames", C.c_uint32),
                 ("max_point_step", C.c_uint32), ("max_survivors", C.c_uint64), ("max_voxels", C.c_uint64)]
+
+
+class CColorNet(C.Structure):
+    """cp_color_net."""
+    _fields_ = [("c1", C.c_uint32), ("c2", C.c_uint32), ("n_classes", C.c_uint32)] + \
+               [(n, C.c_void_p) for n in ("conv1_w", "conv1_b", "conv2_w", "conv2_b", "bn_scale", "bn_shift",
+                                          "dense_w", "dense_b")] + [("threshold", C.c_float)]
 
 
 class ConesGpuError(RuntimeError):
@@ -109,6 +118,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cp_cone_crops.argtypes = [vp, C.POINTER(CCloudView), u32, vp, u32, C.c_float, vp, vp, u32]
     lib.cp_cone_images.argtypes = [vp, C.POINTER(CCloudView), u32, vp, u32, C.c_float, vp, vp, vp]
     lib.cp_rasterize_crops.argtypes = [vp, vp, vp, u32, vp, vp]
+    lib.cp_color_net_load.argtypes = [vp, C.POINTER(CColorNet)]
+    lib.cp_color_net_load_tflite.argtypes = [vp, vp, C.c_size_t, C.c_float]
+    lib.cp_cone_colors.argtypes = [vp, C.POINTER(CCloudView), u32, vp, u32, C.c_float, vp, vp, vp]
+    lib.cp_classify_images.argtypes = [vp, vp, u32, vp, vp, vp]
     lib.cp_pinned_alloc.argtypes = [C.c_int32, C.c_size_t, C.c_int32, C.POINTER(vp)]
     lib.cp_pinned_free.argtypes = [vp]
     lib.cp_pinned_free.restype = None
@@ -269,6 +282,48 @@ class ConesGpu:
         self._ck(self.lib.cp_rasterize_crops(self._h, a.ctypes.data, off.ctypes.data, n, img.ctypes.data,
                                              flags.ctypes.data))
         return img, flags
+
+    # ---- colour classifier (models/dam_net) ---------------------------------------------
+    def color_net_load_tflite(self, model, threshold: float = 0.8):
+        """Load the reference's classifier from a .tflite file (path or bytes): what
+        scripts/color_classifier_server.py:66 hands to tf.lite.Interpreter."""
+        data = model if isinstance(model, (bytes, bytearray)) else open(model, "rb").read()
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        self._ck(self.lib.cp_color_net_load_tflite(self._h, buf, len(data), threshold))
+        self._n_classes = None
+
+    def color_net_load(self, conv1_w, conv1_b, conv2_w, conv2_b, bn_scale, bn_shift, dense_w, dense_b,
+                       threshold: float = 0.8):
+        """Raw tensors in the flatbuffer's layouts: conv [out][3][3][in], dense [classes][2*c2]."""
+        t = [np.ascontiguousarray(a, np.float32) for a in (conv1_w, conv1_b, conv2_w, conv2_b, bn_scale, bn_shift,
+                                                           dense_w, dense_b)]
+        net = CColorNet(t[0].shape[0], t[2].shape[0], t[6].shape[0], *[a.ctypes.data for a in t], threshold)
+        self._ck(self.lib.cp_color_net_load(self._h, C.byref(net)))
+        self._n_classes = t[6].shape[0]
+
+    def classify_images(self, images: np.ndarray, n_classes: int = 3):
+        """The network alone on [n,15,12] uint8 images.  Returns (colors u8 [n], probs [n,classes], logits)."""
+        img = np.ascontiguousarray(images, np.uint8).reshape(-1, CONE_IMG_ROWS, CONE_IMG_COLS)
+        n = len(img)
+        nc = getattr(self, "_n_classes", None) or n_classes
+        colors = np.zeros(n, np.uint8)
+        probs, logits = np.zeros((n, nc), np.float32), np.zeros((n, nc), np.float32)
+        self._ck(self.lib.cp_classify_images(self._h, img.ctypes.data, n, colors.ctypes.data, probs.ctypes.data,
+                                             logits.ctypes.data))
+        return colors, probs, logits
+
+    def cone_colors(self, centers, cone_width: float = 0.228, msg: PointCloud2 | None = None, frame: int = 0,
+                    fake_missing_intensity: bool = True, n_classes: int = 3):
+        """handle_classify_color (scripts/color_classifier_server.py:78-126) on the device for all centres:
+        box gather -> to_image -> network.  Returns (colors u8 [n] with 255 = no answer, probs, flags)."""
+        c = self._centers(centers)
+        view = make_view(msg, fake_missing_intensity) if msg is not None else None
+        nc = getattr(self, "_n_classes", None) or n_classes
+        colors = np.zeros(len(c), np.uint8)
+        probs, flags = np.zeros((len(c), nc), np.float32), np.zeros(len(c), np.uint32)
+        self._ck(self.lib.cp_cone_colors(self._h, C.byref(view) if view is not None else None, frame, c.ctypes.data,
+                                         len(c), cone_width, colors.ctypes.data, probs.ctypes.data, flags.ctypes.data))
+        return colors, probs, flags
 
     # ---- batches ----------------------------------------------------------------------
     def set_device_input(self, d_ptr: int, frame_points, point_step: int = 16, off=(0, 4, 8, 12), keep=None):

@@ -17,11 +17,13 @@
 #include "cluster_front.cuh"
 #include "cluster_kernels.cuh"
 #include "color_kernels.cuh"
+#include "color_net.cuh"
 #include "common.cuh"
 #include "copy_pool.hpp"
 #include "frame_kernels.cuh"
 #include "radix_sort.cuh"
 #include "stream_kernels.cuh"
+#include "tflite_reader.hpp"
 #include "voxel_kernels.cuh"
 
 using namespace cp;
@@ -123,6 +125,15 @@ struct cp_handle {
     size_t mask_n = 0, tile_n = 0, texcl_n = 0, off_n = 0, flags_n = 0, pts_n = 0, img_n = 0;
     void* pin = nullptr;
     size_t pin_bytes = 0;
+    // classifier (color_net.cuh): weights in one device block, per-cone outputs
+    float* net_w = nullptr;
+    size_t net_w_n = 0;
+    ColorNetDev net{};
+    bool net_loaded = false;
+    uint8_t* colors = nullptr;
+    float* probs = nullptr;     // [n][classes] probabilities, then [n][classes] logits
+    u32* net_flags = nullptr;
+    size_t colors_n = 0, probs_n = 0, net_flags_n = 0;
   } color;
   const uint8_t* in_ptr = nullptr;  // current batch input (d_in or caller memory)
   Layout layout{};
@@ -1364,6 +1375,72 @@ cp_status enqueue_raster(cp_handle* h, u32 n_cones) {
   return CP_OK;
 }
 
+// ---- colour classifier (color_net.cuh) ------------------------------------------------------
+static cp_status load_color_net(cp_handle* h, const cp_color_net* n) {
+  if (!n || !n->conv1_w || !n->conv1_b || !n->conv2_w || !n->conv2_b || !n->bn_scale || !n->bn_shift || !n->dense_w ||
+      !n->dense_b) {
+    h->err = "NULL colour-net tensor";
+    return CP_E_PARAM;
+  }
+  if (n->c1 < 1 || n->c1 > (u32)kNetMaxC1 || n->c2 < 1 || n->c2 > (u32)kNetMaxC2 || n->n_classes < 1 ||
+      n->n_classes > (u32)kNetMaxClasses || n->n_classes > 3 || !(n->threshold >= 0.f && n->threshold <= 1.f)) {
+    h->err = "colour net out of range: c1 <= 16, c2 <= 32, classes <= 3 (yellow, blue, orange), threshold in [0, 1]";
+    return CP_E_PARAM;
+  }
+  const u32 C1 = n->c1, C2 = n->c2, NC = n->n_classes, K = kPool2H * kPool2W * C2;
+  // device layout: w1t[9][C1] b1 w2t[9*C1][C2] b2 scale shift wd[NC][K] bd
+  std::vector<float> w;
+  w.reserve(9 * C1 + C1 + 9 * C1 * C2 + 3 * C2 + NC * K + NC);
+  const size_t o_w1 = w.size();
+  for (u32 k = 0; k < 9; ++k)
+    for (u32 c = 0; c < C1; ++c) w.push_back(n->conv1_w[c * 9 + k]);                 // [c][ky][kx][1] -> [k][c]
+  const size_t o_b1 = w.size();
+  w.insert(w.end(), n->conv1_b, n->conv1_b + C1);
+  const size_t o_w2 = w.size();
+  for (u32 k = 0; k < 9; ++k)
+    for (u32 ci = 0; ci < C1; ++ci)
+      for (u32 c = 0; c < C2; ++c) w.push_back(n->conv2_w[((size_t)c * 9 + k) * C1 + ci]);   // [c][k][ci] -> [k][ci][c]
+  const size_t o_b2 = w.size();
+  w.insert(w.end(), n->conv2_b, n->conv2_b + C2);
+  const size_t o_sc = w.size();
+  w.insert(w.end(), n->bn_scale, n->bn_scale + C2);
+  const size_t o_sh = w.size();
+  w.insert(w.end(), n->bn_shift, n->bn_shift + C2);
+  const size_t o_wd = w.size();
+  w.insert(w.end(), n->dense_w, n->dense_w + (size_t)NC * K);
+  const size_t o_bd = w.size();
+  w.insert(w.end(), n->dense_b, n->dense_b + NC);
+  cp_handle::ColorBufs& cb = h->color;
+  CK(cudaSetDevice(h->cfg.device));
+  cp_status st = grow(h, &cb.net_w, &cb.net_w_n, w.size());
+  if (st) return st;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(cb.net_w, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+  cb.net = ColorNetDev{cb.net_w + o_w1, cb.net_w + o_b1, cb.net_w + o_w2, cb.net_w + o_b2, cb.net_w + o_sc,
+                       cb.net_w + o_sh, cb.net_w + o_wd, cb.net_w + o_bd, C1, C2, NC, n->threshold};
+  cb.net_loaded = true;
+  return CP_OK;
+}
+
+// cone_color_kernel over n images already on the device (cb.img or `images_dev`); outputs stay in cb.colors/probs
+static cp_status enqueue_color_net(cp_handle* h, const uint8_t* images_dev, const u32* raster_flags, u32 n) {
+  cp_handle::ColorBufs& cb = h->color;
+  if (!cb.net_loaded) {
+    h->err = "no colour net loaded (cp_color_net_load / cp_color_net_load_tflite)";
+    return CP_E_STATE;
+  }
+  cp_status st;
+  if ((st = grow(h, &cb.colors, &cb.colors_n, (size_t)std::max<u32>(n, 1)))) return st;
+  if ((st = grow(h, &cb.probs, &cb.probs_n, (size_t)std::max<u32>(n, 1) * 2 * kNetMaxClasses))) return st;
+  if ((st = grow(h, &cb.net_flags, &cb.net_flags_n, (size_t)std::max<u32>(n, 1)))) return st;
+  if (n)
+    cone_color_kernel<<<n, kNetThreads, 0, h->stream>>>(images_dev, raster_flags, cb.net, cb.colors, cb.probs,
+                                                        cb.probs + (size_t)n * cb.net.classes, cb.net_flags);
+  CK(cudaGetLastError());
+  h->launches += n ? 1 : 0;
+  return CP_OK;
+}
+
 // Nothing may propagate through the C ABI: host-side allocation failures and the like become a status.
 static cp_status abi_exception(cp_handle* h) noexcept {
   try {
@@ -1591,7 +1668,8 @@ void cp_destroy(cp_handle* h) {
   for (void* p : h->pin_allocs) cudaFreeHost(p);
   if (h->d_out32) cudaFree(h->d_out32);
   for (void* q : {(void*)h->color.mask, (void*)h->color.tcount, (void*)h->color.texcl, (void*)h->color.off,
-                  (void*)h->color.flags, (void*)h->color.pts, (void*)h->color.img})
+                  (void*)h->color.flags, (void*)h->color.pts, (void*)h->color.img, (void*)h->color.net_w,
+                  (void*)h->color.colors, (void*)h->color.probs, (void*)h->color.net_flags})
     if (q) cudaFree(q);
   if (h->color.pin) cudaFreeHost(h->color.pin);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
@@ -2469,6 +2547,113 @@ cp_status cp_rasterize_crops(cp_handle* h, const float* crop_xyzi, const uint32_
     if (flags) CK(cudaMemcpyAsync(flags, cb.flags, sizeof(u32) * n_crops, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
+  return CP_OK;
+} catch (...) {
+  return abi_exception(h);
+}
+
+cp_status cp_color_net_load(cp_handle* h, const cp_color_net* net) try {
+  if (!h) return CP_E_PARAM;
+  return load_color_net(h, net);
+} catch (...) {
+  return abi_exception(h);
+}
+
+cp_status cp_color_net_load_tflite(cp_handle* h, const void* data, size_t bytes, float threshold) try {
+  if (!h) return CP_E_PARAM;
+  if (!data) {
+    h->err = "NULL model data";
+    return CP_E_PARAM;
+  }
+  cp_tflite::ColorNetWeights w;
+  try {
+    w = cp_tflite::read_color_net(static_cast<const uint8_t*>(data), bytes);
+  } catch (const cp_tflite::Error& e) {
+    h->err = "TFLite model refused: " + e.what;
+    return CP_E_PARAM;
+  }
+  cp_color_net n{};
+  n.c1 = w.c1;
+  n.c2 = w.c2;
+  n.n_classes = w.classes;
+  n.conv1_w = w.conv1_w.data();
+  n.conv1_b = w.conv1_b.data();
+  n.conv2_w = w.conv2_w.data();
+  n.conv2_b = w.conv2_b.data();
+  n.bn_scale = w.bn_scale.data();
+  n.bn_shift = w.bn_shift.data();
+  n.dense_w = w.dense_w.data();
+  n.dense_b = w.dense_b.data();
+  n.threshold = threshold;
+  return load_color_net(h, &n);
+} catch (...) {
+  return abi_exception(h);
+}
+
+static cp_status fetch_colors(cp_handle* h, u32 n, uint8_t* colors, float* probs, float* logits, uint32_t* flags) {
+  cp_handle::ColorBufs& cb = h->color;
+  const u32 NC = cb.net.classes;
+  if (n) {
+    CK(cudaMemcpyAsync(colors, cb.colors, n, cudaMemcpyDeviceToHost, h->stream));
+    if (probs) CK(cudaMemcpyAsync(probs, cb.probs, sizeof(float) * n * NC, cudaMemcpyDeviceToHost, h->stream));
+    if (logits) CK(cudaMemcpyAsync(logits, cb.probs + (size_t)n * NC, sizeof(float) * n * NC, cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, cb.net_flags, sizeof(u32) * n, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return CP_OK;
+}
+
+cp_status cp_classify_images(cp_handle* h, const uint8_t* images, uint32_t n_images, uint8_t* colors, float* probs,
+                             float* logits) try {
+  if (!h) return CP_E_PARAM;
+  if (n_images && (!images || !colors)) {
+    h->err = "NULL images or colors";
+    return CP_E_PARAM;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  cp_handle::ColorBufs& cb = h->color;
+  cp_status st = grow(h, &cb.img, &cb.img_n, (size_t)std::max<u32>(n_images, 1) * kImgPix);
+  if (st) return st;
+  if (n_images) CK(cudaMemcpyAsync(cb.img, images, (size_t)n_images * kImgPix, cudaMemcpyHostToDevice, h->stream));
+  h->launches = 0;
+  if ((st = enqueue_color_net(h, cb.img, nullptr, n_images))) return st;
+  return fetch_colors(h, n_images, colors, probs, logits, nullptr);
+} catch (...) {
+  return abi_exception(h);
+}
+
+cp_status cp_cone_colors(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame, const cp_cone_center* centers,
+                         uint32_t n_centers, float cone_width, uint8_t* colors, float* probs, uint32_t* flags) try {
+  if (!h) return CP_E_PARAM;
+  if (n_centers && !colors) {
+    h->err = "NULL colors";
+    return CP_E_PARAM;
+  }
+  if (!h->color.net_loaded) {
+    h->err = "no colour net loaded (cp_color_net_load / cp_color_net_load_tflite)";
+    return CP_E_STATE;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  cp_status st = color_pin(h, n_centers);
+  if (st) return st;
+  size_t want = h->color.pts_n;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // crops -> range images -> classifier, back to back on the stream; one synchronisation, n_centers bytes back
+    st = enqueue_cone_crops(h, attempt == 0 ? cloud : nullptr, attempt == 0 ? frame : (cloud ? 0 : frame), centers,
+                            n_centers, cone_width, want);
+    if (st) return st;
+    if ((st = enqueue_raster(h, n_centers))) return st;
+    if ((st = enqueue_color_net(h, h->color.img, h->color.flags, n_centers))) return st;
+    CK(cudaMemcpyAsync(pin_off(h) + n_centers, h->color.off + n_centers, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+    if ((st = fetch_colors(h, n_centers, colors, probs, nullptr, flags))) return st;
+    const u32 total = pin_off(h)[n_centers];
+    if (total <= h->color.pts_n) break;
+    if (total == 0xFFFFFFFFu || attempt == 1) {
+      h->err = "cone crops exceed the addressable crop buffer";
+      return CP_E_CAPACITY;
+    }
+    want = total;
+  }
   return CP_OK;
 } catch (...) {
   return abi_exception(h);

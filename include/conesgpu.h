@@ -225,9 +225,8 @@ uint32_t cp_last_launch_count(const cp_handle* h);
 /* The handle's stream as a cudaStream_t, for callers that time with their own events. */
 void* cp_stream(cp_handle* h);
 
-/* --- colour path inputs: what sits between a detected cone and the classifier ---
- * Only needed with classify_colors:=true.  The network itself (models/dam_net) stays with the
- * reference's Python service: there is no TFLite oracle to hold an implementation to. */
+/* --- colour path: crops, range images and the classifier network ---
+ * Only needed with classify_colors:=true. */
 typedef struct cp_cone_center {
   float x, y; /* the centroid AFTER the radial extension (src/cone_detection.cpp:276-278), as passed at :309 */
 } cp_cone_center;
@@ -259,6 +258,39 @@ cp_status cp_cone_images(cp_handle* h, const cp_cloud_view* cloud, uint32_t fram
 /* to_image alone, on host crops in the cp_cone_crops format (what handle_classify_color receives, :78-90). */
 cp_status cp_rasterize_crops(cp_handle* h, const float* crop_xyzi, const uint32_t* crop_offsets, uint32_t n_crops,
                              uint8_t* images, uint32_t* flags);
+
+/* The classifier network of scripts/color_classifier_server.py (models/dam_net/dam_net.tflite, evaluated there
+ * by tf.lite.Interpreter, :66-71 and :108-120): conv 3x3 (1 -> c1, ReLU), max-pool 2x2, conv 3x3 (c1 -> c2, ReLU),
+ * max-pool 2x2, per-channel scale + shift (the folded batch normalisation), dense (2*c2 -> n_classes), softmax.
+ * Tensors in the flatbuffer's own layouts.  PARITY UNPINNED: TensorFlow-Lite cannot be installed next to this
+ * library's tests; the implementation is held to a numpy restatement of TFLite's reference kernels and to the
+ * human labels of the reference's 577 recorded crops (tests/test_dam_net.py). */
+typedef struct cp_color_net {
+  uint32_t c1, c2, n_classes; /* dam_net: 16, 32, 3 */
+  const float* conv1_w;       /* [c1][3][3][1]   (OHWI) */
+  const float* conv1_b;       /* [c1] */
+  const float* conv2_w;       /* [c2][3][3][c1] */
+  const float* conv2_b;       /* [c2] */
+  const float* bn_scale;      /* [c2]  the MUL constant */
+  const float* bn_shift;      /* [c2]  the ADD constant */
+  const float* dense_w;       /* [n_classes][2 * c2], features in NHWC order */
+  const float* dense_b;       /* [n_classes] */
+  float threshold;            /* 0.8: below it the colour is 0 = unknown (color_classifier_server.py:116-120) */
+} cp_color_net;
+cp_status cp_color_net_load(cp_handle* h, const cp_color_net* net);
+/* The same from the bytes of the .tflite file the reference's launch parameter ~model_path names.  Any graph other
+ * than the architecture above is refused with CP_E_PARAM (cp_last_error says why). */
+cp_status cp_color_net_load_tflite(cp_handle* h, const void* data, size_t bytes, float threshold);
+/* handle_classify_color (scripts/color_classifier_server.py:78-126) for n_centers cones, entirely on the device:
+ * box gather -> to_image -> network.  colors[c]: 0 unknown, 1 yellow, 2 blue, 3 orange, 255 = no answer for this
+ * cone (flags[c] has CP_CONE_EMPTY: the service skips it; CP_CONE_BAD_*: the service call would raise).
+ * probs (optional) [n_centers][n_classes] softmax outputs; flags (optional) CP_CONE_* bits. */
+#define CP_CONE_LOW_CONFIDENCE 16 /* the largest probability lies within 2e-6 of the threshold */
+cp_status cp_cone_colors(cp_handle* h, const cp_cloud_view* cloud, uint32_t frame, const cp_cone_center* centers,
+                         uint32_t n_centers, float cone_width, uint8_t* colors, float* probs, uint32_t* flags);
+/* The network alone on host images [n][15][12] uint8 (parity tests; logits optional, before the softmax). */
+cp_status cp_classify_images(cp_handle* h, const uint8_t* images, uint32_t n_images, uint8_t* colors, float* probs,
+                             float* logits);
 
 /* --- stage taps for parity tests (valid after cp_sync, whole batch, frame-major) ----
  * Every tap copies device state of the last run to host memory.  count = entries written. */

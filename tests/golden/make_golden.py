@@ -192,6 +192,22 @@ def synthetic(idx, seed):
     print(f"cfg{idx} seed {seed}: K={len(cl)} V={ctr.n_voxels} C={ctr.n_cropped} sha={digest[:12]}")
 
 
+def dam_net():
+    """dam_net_model.npz — the reference's classifier file (models/dam_net/dam_net.tflite, 23.5 kB) carried as a
+    byte array, because /root/reference does not exist on the GPU box, with the numpy forward pass's outputs
+    (oracle/dam_net_ref.py) on the 577 recorded crops' range images as a regression pin."""
+    from cones_perception_b200 import tflite_model
+    from oracle import dam_net_ref as D
+    raw = open("/root/reference/models/dam_net/dam_net.tflite", "rb").read()
+    g = tflite_model.load(raw)
+    imgs = np.load(os.path.join(HERE, "cone_images.npz"))["real_images"]
+    probs, logits = zip(*[D.forward(g, im) for im in imgs])
+    np.savez_compressed(os.path.join(HERE, "dam_net_model.npz"), tflite=np.frombuffer(raw, np.uint8),
+                        sha256=np.array(hashlib.sha256(raw).hexdigest()),
+                        real_probs=np.stack(probs).astype(np.float32), real_logits=np.stack(logits).astype(np.float32))
+    print("dam_net:", len(raw), "bytes,", len(imgs), "images")
+
+
 PCL_PIN_CASES = ((1, 0), (2, 0), (3, 5), (4, 0), (5, 0))      # (config, seed): one frame of each BASELINE.json config
 
 
@@ -230,6 +246,7 @@ if __name__ == "__main__":
         sys.exit(0)
     cone_crops()
     cone_images()
+    dam_net()
     reference_nodes()
     for idx, seed in ((1, 0), (2, 0), (2, 7), (4, 0), (5, 0)):
         synthetic(idx, seed)
