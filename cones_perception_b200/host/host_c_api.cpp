@@ -126,6 +126,16 @@ void ch_detector_set_color_inputs(void* dp, int mode) {
     return probe_images(pr, im, fl);
   };
 }
+// the classifier network on the device (ConeDetector::kGpuColors): model = bytes of the .tflite file
+int ch_detector_load_color_model(void* dp, const void* model, uint64_t bytes) {
+  try {
+    static_cast<ConeDetector*>(dp)->load_color_model(model, static_cast<size_t>(bytes));
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 4;
+  }
+}
 void ch_detector_color_probe(void* dp, uint64_t* n_inputs, uint64_t* n_points, uint64_t* digest) {
   const ColorProbe& pr = g_probes[dp];
   *n_inputs = pr.n_inputs;

@@ -10,6 +10,7 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <cstdio>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -238,7 +239,9 @@ class ConeDetector {
   //   kGpuCrops   cp_cone_crops on the cloud the detection call already staged; get_colors sees the same crops
   //   kGpuImages  cp_cone_images: crops and ColorClassifier.to_image both on the device; the classifier
   //               hook get_colors_from_images receives 15x12 uint8 images + CP_CONE_* flags (180 B per cone)
-  enum ColorInputs { kHostCrops = 0, kGpuCrops = 1, kGpuImages = 2 };
+  //   kGpuColors  cp_cone_colors: crops, images and the classifier network (models/dam_net) all on the device; one
+  //               byte per cone comes back and no colour service is called.  Needs load_color_model().
+  enum ColorInputs { kHostCrops = 0, kGpuCrops = 1, kGpuImages = 2, kGpuColors = 3 };
   ColorInputs color_inputs = kGpuCrops;
   std::function<std::vector<Color>(const std::vector<uint8_t>& images, const std::vector<uint32_t>& flags)>
       get_colors_from_images;
@@ -253,6 +256,23 @@ class ConeDetector {
     if (st != CP_OK) throw GpuError(st, cp_create_error());
   }
   ~ConeDetector() { cp_destroy(gpu_); }
+  // Loads the classifier the reference's service reads from its ~model_path parameter (a .tflite file,
+  // scripts/color_classifier_server.py:44-66) into the library and routes the colour path through it.
+  void load_color_model(const std::string& path, float threshold = 0.8f) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw GpuError(CP_E_PARAM, "cannot open colour model " + path);
+    std::vector<uint8_t> bytes;
+    uint8_t buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) bytes.insert(bytes.end(), buf, buf + n);
+    fclose(f);
+    load_color_model(bytes.data(), bytes.size(), threshold);
+  }
+  void load_color_model(const void* data, size_t size, float threshold = 0.8f) {
+    cp_status st = cp_color_net_load_tflite(gpu_, data, size, threshold);
+    if (st != CP_OK) throw GpuError(st, cp_last_error(gpu_));
+    color_inputs = kGpuColors;
+  }
   ConeDetector(const ConeDetector&) = delete;
   ConeDetector& operator=(const ConeDetector&) = delete;
 
@@ -292,6 +312,8 @@ class ConeDetector {
       whole = from_msg(cloud_msg, in);  // :158 copyPointCloud, colour path only
     } else if (classify_colors && color_inputs == kGpuCrops) {
       tracker_.reconstruct_cones = [this](const std::vector<Point>& need) { return gpu_crops(need); };
+    } else if (classify_colors && color_inputs == kGpuColors) {
+      tracker_.classify_centers = [this](const std::vector<Point>& need) { return gpu_colors(need); };
     } else if (classify_colors) {
       tracker_.classify_centers = [this](const std::vector<Point>& need) { return gpu_classify(need); };
     }
@@ -360,6 +382,24 @@ class ConeDetector {
                                   images.data(), nullptr, flags.data());
     if (st != CP_OK) throw GpuError(st, cp_last_error(gpu_));
     return get_colors_from_images ? get_colors_from_images(images, flags) : std::vector<Color>();
+  }
+  // The whole service on the device.  Response semantics of handle_classify_color (color_classifier_server.py:
+  // 78-126): an empty crop is skipped, so the response is shorter and later colours move up (:83-84); if to_image
+  // would raise for any cone the call fails and the node keeps every cone unknown (src/cone_detection.cpp:356-361).
+  std::vector<Color> gpu_colors(const std::vector<Point>& need) {
+    const std::vector<cp_cone_center> c = centers_of(need);
+    std::vector<uint8_t> colors(c.size());
+    std::vector<uint32_t> flags(c.size());
+    cp_status st = cp_cone_colors(gpu_, nullptr, 0, c.data(), static_cast<uint32_t>(c.size()), CONE_WIDTH, colors.data(),
+                                  nullptr, flags.data());
+    if (st != CP_OK) throw GpuError(st, cp_last_error(gpu_));
+    std::vector<Color> out;
+    for (size_t i = 0; i < c.size(); ++i) {
+      if (flags[i] & (CP_CONE_BAD_INDEX | CP_CONE_BAD_INTENSITY)) return std::vector<Color>();
+      if (flags[i] & CP_CONE_EMPTY) continue;
+      out.push_back(static_cast<Color>(colors[i] < kNumberOfColors ? colors[i] : 0));
+    }
+    return out;
   }
   cp_handle* gpu_ = nullptr;
   bool intensity_in_cloud_checked_ = false, intensity_in_cloud_ = true;

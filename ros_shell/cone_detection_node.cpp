@@ -30,16 +30,24 @@ class ConeDetectorNode {
     private_param("fused_ground_removal", core_.fused_ground_removal);
     private_param("num_of_sectors", core_.num_of_sectors);
     private_param("default_lowest_point", core_.default_lowest_point);
+    // extension (off by default): the classifier network on the device instead of the color_classifier service;
+    // the value is what the reference's launch file passes to the Python service as ~model_path
+    std::string color_model_path;
+    private_param("color_model_path", color_model_path);
+    if (core_.classify_colors && !color_model_path.empty()) {
+      core_.load_color_model(color_model_path);
+      use_color_service_ = false;
+    }
     sub_ = nh_.subscribe<sensor_msgs::PointCloud2>(core_.input_cloud_topic, 2, &ConeDetectorNode::cloud_handler, this);  // :112
     for (int i = 0; i < cones_host::kNumberOfColors; i++)
       pubs_[i] = nh_.advertise<sensor_msgs::PointCloud2>(core_.cones_topics[i], 1);          // :113-115
-    if (core_.classify_colors) {
+    if (core_.classify_colors && use_color_service_) {
       color_srv_client_ = nh_.serviceClient<cones_perception::ClassifyColorSrv>(color_classifier_srv_name_);  // :118
       core_.get_colors = [this](const std::vector<std::vector<cones_host::Point>>& crops) { return get_colors(crops); };
     }
   }
   void run() {
-    if (core_.classify_colors) color_srv_client_.waitForExistence();  // :123-125
+    if (core_.classify_colors && use_color_service_) color_srv_client_.waitForExistence();  // :123-125
     ROS_INFO("Ready to detect cones.");
     ros::spin();
   }
@@ -75,6 +83,7 @@ class ConeDetectorNode {
   ros::Publisher pubs_[cones_host::kNumberOfColors];
   ros::ServiceClient color_srv_client_;
   std::string color_classifier_srv_name_ = "color_classifier";
+  bool use_color_service_ = true;
   cones_host::ConeDetector core_;
 };
 

@@ -30,6 +30,7 @@ def host():
                                        C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ch_detector_set_color_inputs.argtypes = [C.c_void_p, C.c_int]
     lib.ch_detector_set_color_inputs.restype = None
+    lib.ch_detector_load_color_model.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.ch_detector_color_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ch_detector_color_probe.restype = None
     lib.ch_ground_create.restype = C.c_void_p
@@ -109,6 +110,60 @@ def test_cone_detector_cloud_handler_sequence(host, fused_ground, with_intensity
         assert step.value == 32 and nf.value == (4 if with_intensity else 3)   # Q6: input fields, PCL data
         assert nsec.value == 123456789                                         # header copied verbatim
     assert published > 0
+    host.ch_detector_destroy(det)
+
+
+@pytest.mark.gpu
+def test_cone_detector_colours_from_the_device_network(host):
+    """classify_colors:=true with the classifier on the device (ConeDetector::load_color_model -> cp_cone_colors):
+    the published colour clouds must equal the tracker driven by the CPU chain (reference box gather ->
+    to_image -> numpy forward pass of dam_net -> 0.8 threshold) with the service's response semantics."""
+    from cones_perception_b200 import tflite_model
+    from oracle import dam_net_ref as D
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dam_net_model.npz")
+    model = np.load(gold)["tflite"].tobytes()
+    graph = tflite_model.load(model)
+    cfg = scans.config(1)
+    frames = scans.generate(cfg, 4, base_seed=40).copy()
+    frames[..., 3] = np.clip(frames[..., 3] * 2.5, 0, 255)        # intensities in the range the network was trained on
+    d = cfg.detect
+    cd = to_c_detect(d)
+    raw = {}
+
+    def service(need):
+        out = []
+        for p in need:
+            c = O.reconstruct_cone(raw["pts"], float(p[0]), float(p[1]), 0.228)
+            if len(c) == 0:
+                continue                                        # color_classifier_server.py:83-84
+            img, fl = O.to_image(np.stack([c["x"], c["y"], c["z"], c["intensity"]], 1).astype(np.float32))
+            if fl:
+                return []                                       # to_image raises: the service call fails
+            out.append(D.decide(D.forward(graph, img)[0]))
+        return out
+
+    det = host.ch_detector_create(cfg.points_per_frame, 0, C.byref(cd), 1, 1, 0)
+    assert det, host.ch_last_error()
+    buf = (C.c_uint8 * len(model)).from_buffer_copy(model)
+    assert host.ch_detector_load_color_model(det, buf, len(model)) == 0, host.ch_last_error()
+    ref = TrackerReference(True, True, d.cones_matching_dist_theshold, d.cone_position_extension_length,
+                           color_fn=service)
+    coloured = 0
+    for f in frames:
+        out = np.zeros((4, CAP, 2), np.float32)
+        counts = np.zeros(4, np.uint32)
+        step, nf, nsec = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        rc = host.ch_detector_handle(det, f.ctypes.data, len(f), 1, out.ctypes.data, counts.ctypes.data, CAP,
+                                     C.byref(step), C.byref(nf), C.byref(nsec))
+        assert rc == 0, host.ch_last_error()
+        raw["pts"] = O.from_msg(O.view_of_xyzi(f))
+        cl, _, _ = O.detect(O.view_of_xyzi(f), d, None, O.CANONICAL)
+        exp = as_arrays(ref.update([(c["x"], c["y"]) for c in cl]))
+        for k in range(4):
+            assert counts[k] == len(exp[k]), k
+            assert np.array_equal(out[k, :counts[k]].view(np.uint32), exp[k].view(np.uint32))
+        coloured += int(counts[1:].sum())
+    assert coloured > 0
     host.ch_detector_destroy(det)
 
 
