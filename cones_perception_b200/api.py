@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "cp_sync", "cp_batch_results", "cp_detect_batch", "cp_last_run_ms", "cp_last_launch_count", "cp_stream",
     "cp_debug_tap", "cp_debug_sort", "cp_set_stage_timing", "cp_stage_ms", "cp_debug_timeline", "cp_debug_atan2f", "cp_device_results",
     "cp_gather_create", "cp_gather_open", "cp_gather_seq", "cp_gather_wait", "cp_gather_read",
-    "cp_last_rows_loaded", "cp_cone_crops", "cp_cone_images", "cp_rasterize_crops",
+    "cp_last_rows_loaded", "cp_last_pairs", "cp_cone_crops", "cp_cone_images", "cp_rasterize_crops",
     "cp_pinned_alloc", "cp_pinned_free",
     "cp_color_net_load", "cp_color_net_load_tflite", "cp_cone_colors", "cp_classify_images",
 ]
@@ -115,6 +115,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cp_gather_read.argtypes = [vp, u32, vp, u64]
     lib.cp_last_rows_loaded.argtypes = [vp]
     lib.cp_last_rows_loaded.restype = u64
+    lib.cp_last_pairs.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    lib.cp_last_pairs.restype = None
     lib.cp_cone_crops.argtypes = [vp, C.POINTER(CCloudView), u32, vp, u32, C.c_float, vp, vp, u32]
     lib.cp_cone_images.argtypes = [vp, C.POINTER(CCloudView), u32, vp, u32, C.c_float, vp, vp, vp]
     lib.cp_rasterize_crops.argtypes = [vp, vp, vp, u32, vp, vp]
@@ -422,6 +424,12 @@ class ConesGpu:
 
     def last_rows_loaded(self) -> int:
         return int(self.lib.cp_last_rows_loaded(self._h))
+
+    def last_pairs(self) -> tuple[int, int]:
+        """(candidate voxel pairs visited, pairs whose distance was tested) by the clustering of the last run."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.lib.cp_last_pairs(self._h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
 
     def last_launch_count(self) -> int:
         return int(self.lib.cp_last_launch_count(self._h))

@@ -142,8 +142,10 @@ __global__ void __launch_bounds__(256) neighbour_union_kernel(const Ctl* __restr
                                                               const u32* vals_b, const u32* __restrict__ cstart,
                                                               const u64* __restrict__ hkeys,
                                                               const u32* __restrict__ hvals,
-                                                              const float4* __restrict__ vox, u32* __restrict__ parent) {
+                                                              const float4* __restrict__ vox, u32* __restrict__ parent,
+                                                              Ctl* ctl_w) {
   const u32 nv = ctl->n_vox, nc = ctl->n_cells, mask = ctl->hash_mask;
+  u32 n_visited = 0, n_tested = 0;   // statistics (cp_last_pairs)
   const bool inb = sorted_in_b(ctl->csort_bits);
   const u64* keys = inb ? keys_b : keys_a;
   const u32* vals = inb ? vals_b : vals_a;
@@ -176,10 +178,12 @@ __global__ void __launch_bounds__(256) neighbour_union_kernel(const Ctl* __restr
       for (u32 j = cb + lane; j < ce; j += 32u) {
         const u32 u = vals[j];
         if (nb != 13u && u > v) continue;  // each cross-cell pair is seen from both sides: test once
+        ++n_visited;
         // u already hangs under v's root: the edge cannot change anything.  In a solid blob (thousands of
         // mutual neighbours per voxel) almost every candidate leaves here after one 4-byte load.
         if (((volatile u32*)parent)[u] == rv) continue;
         const float4 q = vox[u];
+        ++n_tested;
         // FLANN: dist = L2_Simple(query, point); accepted iff dist < radius (strict)
         if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < k.r2) {
           u32 ru = uf_find(parent, u);
@@ -200,6 +204,12 @@ __global__ void __launch_bounds__(256) neighbour_union_kernel(const Ctl* __restr
       rv = __reduce_min_sync(kFull, rv);  // every lane holds v or an ancestor of v: the smallest is the highest
     }
     if (lane == 0 && rv != v) ((volatile u32*)parent)[v] = rv;
+  }
+  n_visited = __reduce_add_sync(kFull, n_visited);
+  n_tested = __reduce_add_sync(kFull, n_tested);
+  if (lane == 0 && n_visited) {
+    atomicAdd(&ctl_w->pairs_visited, (unsigned long long)n_visited);
+    atomicAdd(&ctl_w->pairs_tested, (unsigned long long)n_tested);
   }
 }
 

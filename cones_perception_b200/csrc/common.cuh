@@ -33,6 +33,9 @@ struct Ctl {
   u32 fast_max_c;      // largest per-frame survivor count seen by it
   u32 fast_max_v;      // largest per-frame voxel count seen by it
   u32 rows_loaded;     // 32-point rows the keep-mask pass actually read (the rest were skipped as all-ground)
+  u32 pad_;
+  unsigned long long pairs_visited;  // clustering: candidate voxel pairs looked at (incl. the one-load exits)
+  unsigned long long pairs_tested;   // ... of which the squared distance was evaluated against r2
 };
 
 enum : u32 { kErrSurvivors = 1u, kErrVoxels = 2u, kErrHash = 4u, kErrInternal = 8u, kErrGather = 16u };

@@ -630,6 +630,7 @@ __global__ void __launch_bounds__(T, T == 256 ? 4 : 1) frame_backend_kernel(Fram
       // does (measured: rows average 26 candidates but the longest have > 100).  The lanes of a row
       // need no communication: each carries the row's root (or an ancestor of it) in a register.
       constexpr u32 kLanesPerRow = 8;
+      u32 n_visited = 0, n_tested = 0;   // statistics (cp_last_pairs): registers, one atomic per warp at the end
       for (u32 r = tid / kLanesPerRow; r < V; r += kFrameThreads / kLanesPerRow) {
         const u32 i = s.u.vox.perm[r];
         const u32 ci = s.u.vox.vcell[i];
@@ -641,12 +642,14 @@ __global__ void __launch_bounds__(T, T == 256 ? 4 : 1) frame_backend_kernel(Fram
 #endif
         for (u32 jp = lo + tid % kLanesPerRow; jp < r; jp += kLanesPerRow) {
           const u32 j = s.u.vox.perm[jp];
+          ++n_visited;
 #ifndef CP_UNION_LEVEL
           // j already hangs under i's root: the edge cannot change anything, so neither the distance nor a
           // find is needed.  The voxels of one cone are mutual neighbours (a clique of up to ~100 at close
           // range); after its first rows almost every candidate takes this one-load exit.
           if (((volatile u32*)s.u.vox.parent)[j] == ri) continue;
 #endif
+          ++n_tested;
           if (l2_simple(xi, yi, zi, s.u.vox.vx[j], s.u.vox.vy[j], s.u.vox.vz[j]) < a.ck.r2) {
 #if defined(CP_UNION_LEVEL) && CP_UNION_LEVEL == 0
             dbg_hits++;
@@ -682,6 +685,12 @@ __global__ void __launch_bounds__(T, T == 256 ? 4 : 1) frame_backend_kernel(Fram
           atomicAdd(&dbg_cnt[1], dbg_hits);
         }
 #endif
+      }
+      n_visited = __reduce_add_sync(kFull, n_visited);
+      n_tested = __reduce_add_sync(kFull, n_tested);
+      if (lane == 0 && n_visited) {
+        atomicAdd(&a.ctl->pairs_visited, (unsigned long long)n_visited);
+        atomicAdd(&a.ctl->pairs_tested, (unsigned long long)n_tested);
       }
       __syncthreads();
       CP_PHASE("union");

@@ -30,7 +30,7 @@ using namespace cp;
 
 namespace {
 
-constexpr u32 kAbiVersion = 1;
+constexpr u32 kAbiVersion = 2;  // 2: colour classifier (cp_color_net_*, cp_cone_colors, cp_classify_images), cp_last_pairs
 constexpr size_t kStageChunk = 32ull << 20;  // pinned staging buffers for pageable host clouds (two of them)
 constexpr size_t kStageMinChunk = 256ull << 10;
 
@@ -715,6 +715,7 @@ __global__ void back_reset_kernel(Ctl* ctl, u32 n_frames, u32* ncomp_f, u32* kco
     ctl->n_vox = ctl->n_cells = ctl->n_comp = ctl->n_clusters = 0;
     ctl->voxel_key_bits = 0;
     ctl->fast_overflow = 0;
+    ctl->pairs_visited = ctl->pairs_tested = 0;   // a retried back half counts its own pairs only
     ctl->error &= kErrSurvivors;
   }
   for (u32 i = t; i < n_frames; i += gridDim.x * blockDim.x) {
@@ -825,7 +826,7 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
                                                    h->d_hvals);
   neighbour_union_kernel<<<grid_for(h->cap_v * 32ull, 256, h->sms, 8), 256, 0, h->stream>>>(
       h->d_ctl, ck, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b, h->d_cstart, h->d_hkeys, h->d_hvals,
-      h->d_vox, h->d_parent);
+      h->d_vox, h->d_parent, h->d_ctl);
   flatten_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_parent, h->d_label, h->d_keys_a, h->d_vals_a);
   h->launches += 6;
   {
@@ -2269,6 +2270,10 @@ uint32_t cp_gather_seq(const cp_handle* h) { return h ? h->gather.seq : 0; }
 
 // rows of 32 points the keep-mask pass read in the last synchronised run (others were skipped)
 uint64_t cp_last_rows_loaded(const cp_handle* h) { return h ? h->h_ctl->rows_loaded : 0; }
+void cp_last_pairs(const cp_handle* h, uint64_t* visited, uint64_t* tested) {
+  if (visited) *visited = h ? h->h_ctl->pairs_visited : 0;
+  if (tested) *tested = h ? h->h_ctl->pairs_tested : 0;
+}
 
 cp_status cp_gather_wait(cp_handle* h, uint32_t seq, uint32_t timeout_ms) try {
   if (!h) return CP_E_PARAM;

@@ -220,6 +220,11 @@ cp_status cp_gather_read(cp_handle* h, uint32_t seq, void* out_host, uint64_t ca
 /* 32-point rows (512 B in the compact layout) that pass 2 actually read in the last synchronised run;
  * rows lying entirely below every sector's ground threshold are skipped without being loaded. */
 uint64_t cp_last_rows_loaded(const cp_handle* h);
+/* Clustering work of the last synchronised run, whole batch (SURVEY.md §5 "pairs tested"): candidate voxel pairs
+ * the union kernels looked at, and how many of those had their squared distance evaluated against r2 (the rest
+ * left early because both voxels already hung under the same root).  The reference's kd-tree visits
+ * O(V * k log k) instead (src/cone_detection.cpp:206-220). */
+void cp_last_pairs(const cp_handle* h, uint64_t* visited, uint64_t* tested);
 /* Kernel launches enqueued by the last cp_batch_run / cp_detect / cp_ground_remove. */
 uint32_t cp_last_launch_count(const cp_handle* h);
 /* The handle's stream as a cudaStream_t, for callers that time with their own events. */

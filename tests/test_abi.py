@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_strerror():
     lib = api.load_library()
-    assert lib.cp_abi_version() == 1
+    assert lib.cp_abi_version() == 2
     assert lib.cp_strerror(0) == b"ok"
     assert b"capacity" in lib.cp_strerror(api.CP_E_CAPACITY)
 

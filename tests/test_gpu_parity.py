@@ -630,3 +630,21 @@ def test_pageable_staging_variants(threads, nt):
             for _ in range(2):
                 cl, _ = h.detect(PointCloud2.from_xyzi(frame), cfg.detect, cfg.ground, cap=1 << 16)
                 assert np.array_equal(cl.view(np.uint32), exp.view(np.uint32)), (idx, threads, nt)
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+def test_pairs_tested_counter(mode):
+    """cp_last_pairs (SURVEY §5 "pairs tested"): both union kernels count the candidate pairs they visit and the
+    distance tests they make.  Every link of the union-find needs one tested pair, so tested >= V - components;
+    the early exit for voxels already under the same root keeps tested well below visited on a scan of cones."""
+    cfg = scans.config(3)
+    frames = list(scans.generate(cfg, 4, base_seed=21))
+    with api.ConesGpu(max_points=4 * cfg.points_per_frame, max_frames=4, back_mode=mode) as h:
+        ctr, off, cl = h.detect_batch([PointCloud2.from_xyzi(f) for f in frames], cfg.detect, cfg.ground)
+        visited, tested = h.last_pairs()
+        V, comps = int(ctr["n_voxels"].sum()), int(ctr["n_components"].sum())
+        assert visited >= tested >= V - comps > 0
+        assert visited <= V * V
+        h.detect_batch([PointCloud2.from_xyzi(f) for f in frames], cfg.detect, cfg.ground)   # counters restart per run
+        v2, t2 = h.last_pairs()
+        assert v2 <= visited * 2 and t2 > 0
