@@ -160,20 +160,14 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* wsum, u32& total) {
   return woff + inc - v;
 }
 
+// The whole back half of frame f by one CTA of T threads (see the file header); called by frame_backend_kernel
+// for batches and by single_frame_kernel (single_frame.cuh) for a node's single frame.
 template <int CMAX, int VMAX, int MODE, int T>
-__global__ void __launch_bounds__(T, T == 256 ? 4 : 1) frame_backend_kernel(FrameArgs a) {
+__device__ __forceinline__ void frame_process(const FrameArgs& a, FrameSmem<CMAX, VMAX, T>& s, const u32 f) {
   constexpr int kFrameThreads = T;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FrameSmem<CMAX, VMAX, T>& s = *reinterpret_cast<FrameSmem<CMAX, VMAX, T>*>(smem_raw);
   const u32 tid = threadIdx.x;
   const int lane = lane_id(), warp = tid >> 5;
-
-  while (true) {
-    __syncthreads();
-    if (tid == 0) s.frame = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const u32 f = s.frame;
-    if (f >= a.n_frames) break;
+  {
 #ifdef CP_PHASE_CLOCKS
     const char* clk_name[16];
     long long clk_t[16];
@@ -803,6 +797,20 @@ __global__ void __launch_bounds__(T, T == 256 ? 4 : 1) frame_backend_kernel(Fram
       printf("%-12s %8lld cyc  (total %lld)\n", "tail", clock64() - prev, clock64() - clk_0);
     }
 #endif
+  }
+}
+
+template <int CMAX, int VMAX, int MODE, int T>
+__global__ void __launch_bounds__(T, T == 256 ? 4 : 1) frame_backend_kernel(FrameArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FrameSmem<CMAX, VMAX, T>& s = *reinterpret_cast<FrameSmem<CMAX, VMAX, T>*>(smem_raw);
+  while (true) {   // frames are handed out by ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s.frame = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const u32 f = s.frame;
+    if (f >= a.n_frames) break;
+    frame_process<CMAX, VMAX, MODE, T>(a, s, f);
   }
 }
 

@@ -22,6 +22,7 @@
 #include "copy_pool.hpp"
 #include "frame_kernels.cuh"
 #include "radix_sort.cuh"
+#include "single_frame.cuh"
 #include "stream_kernels.cuh"
 #include "tflite_reader.hpp"
 #include "voxel_kernels.cuh"
@@ -159,6 +160,9 @@ struct cp_handle {
   u32* d_rowmax = nullptr;     // highest z (ordered key) of every 32-point row, written by pass 1
   bool rowmax_valid = false;   // pass 1 of the current run filled d_rowmax
   bool use_rowskip = true;     // CONESGPU_ROWSKIP=0 disables the skip (A/B measurements)
+  bool use_single = true;      // CONESGPU_SINGLE=0: a single frame takes the multi-launch path (A/B, tests)
+  bool self_published = false; // the last run stored its results into the pinned mirrors itself (single_frame.cuh)
+  bool graph_self_published = false;
   bool tail_priority = false;  // CONESGPU_PRIO=1: greatest-priority stream, pass 1 demoted
   int prio_low = 0;
   int k1_ctas_per_sm = 0;  // CONESGPU_K1_CTAS: separate grid cap for pass 1 (0 = stream_ctas_per_sm)
@@ -900,9 +904,8 @@ void launch_frame_kernel(cp_handle* h, const FrameArgs& fa) {
   h->launches++;
 }
 
-// fast back half: one CTA per frame in shared memory (frame_kernels.cuh)
-template <int CMAX, int VMAX, int T>
-void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
+// arguments of the per-frame back half (frame_kernels.cuh) for the current run
+FrameArgs frame_args(cp_handle* h, const RunParams& rp) {
   FrameArgs fa;
   fa.n_frames = h->hg.n_frames;
   fa.in = h->in_ptr;
@@ -935,6 +938,96 @@ void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
   fa.desc_v = h->d_desc_fv;
   fa.ctl = h->d_ctl;
   fa.ticket = h->d_frame_ticket;
+  fa.tap_vox = h->taps ? h->d_vox : nullptr;
+  fa.tap_vox_cap = (u32)h->cap_v;
+  fa.tap_keys = h->taps ? h->d_tap_keys : nullptr;
+  fa.tap_order = h->taps ? h->d_tap_order : nullptr;
+  fa.tap_labels = h->taps ? h->d_tap_labels : nullptr;
+  return fa;
+}
+
+// ---- a single frame in ONE launch (single_frame.cuh): 16-CTA cluster front end, back half and result publish
+template <int CMAX, int VMAX, int MODE>
+bool launch_single_frame_t(cp_handle* h, const SingleArgs& a, size_t smem) {
+  static bool ready[64] = {};                // per device: attributes set and a cluster of 16 fits
+  static bool usable[64] = {};
+  const int dev = h->cfg.device & 63;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kSfCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(kSfCluster, 1, 1);
+  cfg.blockDim = dim3(kSfThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSfMaxPtsPerCta * 3 * sizeof(float);   // attributes are set for the largest stash
+  cfg.stream = h->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  auto kern = single_frame_kernel<CMAX, VMAX, MODE>;
+  if (!ready[dev]) {
+    ready[dev] = true;
+    const size_t max_smem = std::max<size_t>(cfg.dynamicSmemBytes, sizeof(FrameSmem<CMAX, VMAX, kSfThreads>));
+    int n = 0;
+    cfg.dynamicSmemBytes = max_smem;
+    usable[dev] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) == cudaSuccess &&
+                  cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                  cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n >= 1;
+    cudaGetLastError();
+  }
+  if (!usable[dev]) return false;
+  cfg.dynamicSmemBytes = smem;
+  if (cudaLaunchKernelEx(&cfg, kern, a) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
+bool single_frame_eligible(const cp_handle* h, const Geom& g) {
+  return h->use_single && g.n_frames == 1 && g.uniform_n != 0 && h->layout.mode <= 1 && !h->taps && !h->stage_timing &&
+         h->back_mode < 3 && !h->gather.open && g.uniform_n <= (u32)kSfCluster * kSfMaxPtsPerCta;
+}
+
+bool launch_single_frame(cp_handle* h, const RunParams& rp, float default_low) {
+  SingleArgs a;
+  h->run_fused_mask = false;   // the back half reads the keep mask the front end of the same kernel wrote
+  h->rowmax_valid = false;
+  a.fa = frame_args(h, rp);
+  a.n = h->hg.uniform_n;
+  const u32 per = (a.n + kSfCluster - 1) / kSfCluster;
+  a.pts_per_cta = (per + kSfSub - 1) / kSfSub * kSfSub;
+  a.default_low = default_low;
+  a.o.mask = h->d_mask;
+  a.o.tile_count = h->d_tile_count;
+  a.o.gcount = h->d_gcount;
+  a.o.rows_loaded = &h->d_ctl->rows_loaded;
+  a.low_key = h->d_low_key;
+  a.h_ctl = reinterpret_cast<u32*>(h->h_ctl);
+  a.h_fc = h->h_fc;
+  a.h_res = h->h_result;
+  a.off_words = (u32)h->off_words;
+  a.max_records = (u32)std::min<u64>(h->prefetch_cap, 0xFFFFFFFFu);
+  const size_t stash = (size_t)a.pts_per_cta * 3 * sizeof(float);
+  bool ok;
+#define CP_SF(CM, VM)                                                                                         \
+  do {                                                                                                        \
+    const size_t smem = std::max(stash, sizeof(FrameSmem<CM, VM, kSfThreads>));                               \
+    ok = h->layout.mode == 0 ? launch_single_frame_t<CM, VM, 0>(h, a, smem) : launch_single_frame_t<CM, VM, 1>(h, a, smem); \
+  } while (0)
+  if (h->back_mode == 0) CP_SF(1024, 512);
+  else if (h->back_mode == 1) CP_SF(2048, 1024);
+  else CP_SF(4096, 2048);
+#undef CP_SF
+  return ok;
+}
+
+// fast back half: one CTA per frame in shared memory (frame_kernels.cuh)
+template <int CMAX, int VMAX, int T>
+void enqueue_back_fast(cp_handle* h, const RunParams& rp) {
+  FrameArgs fa = frame_args(h, rp);
+  const bool direct = fa.n_frames == 1;
   cudaMemsetAsync(h->d_frame_ticket, 0, sizeof(u32), h->stream);
   fa.tap_vox = h->taps ? h->d_vox : nullptr;
   fa.tap_vox_cap = (u32)h->cap_v;
@@ -1105,6 +1198,30 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
 
   const Geom g = device_geom(h);
   h->launches = 0;
+  h->rp.d = *d;
+  h->rp.vk = vk;
+  h->rp.ck = ck;
+  h->rp.gk = gk;
+  h->rp.crop = crop;
+  h->rp.csort_bits = csort_bits;
+  h->rp.osort_bits = osort_bits;
+  h->self_published = false;
+  if (single_frame_eligible(h, g)) {
+    // a node's single frame: front end, back half and result publish in one launch (single_frame.cuh)
+    h->ran_cluster = h->ran_fused = false;
+    if (launch_single_frame(h, h->rp, ground ? ground->default_lowest_point : 0.0f)) {
+      h->masked = true;           // keep mask and tile counts are in place for a back-half retry
+      h->gathered = false;
+      h->ran_ground = ground != nullptr;
+      h->ran_frame_kernel = true;
+      h->launches = 1;
+      h->self_published = true;
+      h->fetched = true;
+      h->prefetched = h->prefetch_cap;
+      h->ran = true;
+      return CP_OK;
+    }
+  }
   if (!h->capturing) cudaEventRecord(h->ev0, h->stream);
   launch_init(h, ground ? ground->default_lowest_point : 0.0f);
   h->masked = false;
@@ -1137,13 +1254,6 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   }
   h->gathered = false;
   h->ran_ground = ground != nullptr;
-  h->rp.d = *d;
-  h->rp.vk = vk;
-  h->rp.ck = ck;
-  h->rp.gk = gk;
-  h->rp.crop = crop;
-  h->rp.csort_bits = csort_bits;
-  h->rp.osort_bits = osort_bits;
   if (h->gather.open) h->gather.seq++;
   st = enqueue_back(h, false);
   if (st) return st;
@@ -1554,6 +1664,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
   if (fm_env) h->fuse_mask = fm_env[0] != '0', h->fuse_mask_always = fm_env[0] == '2';
   const char* rs_env = getenv("CONESGPU_ROWSKIP");
   if (rs_env) h->use_rowskip = rs_env[0] != '0';
+  const char* sf_env = getenv("CONESGPU_SINGLE");
+  if (sf_env) h->use_single = sf_env[0] != '0';
   const char* cl_env = getenv("CONESGPU_CLUSTER_FRONT");  // "1": single-pass 16-CTA-cluster front end
   if (cl_env) h->use_cluster = cl_env[0] == '1';
   const char* graph_env = getenv("CONESGPU_GRAPH");  // "0": never replay runs from a CUDA graph
@@ -1858,12 +1970,13 @@ cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_
   h->key_valid = true;
   if (same && h->graph_exec && h->graph_key_valid && memcmp(&key, h->graph_key, sizeof(RunKey)) == 0) {
     if (h->gather.open) h->gather.seq++;
-    cudaEventRecord(h->ev0, h->stream);
+    if (!h->graph_self_published) cudaEventRecord(h->ev0, h->stream);
     CK(cudaGraphLaunch(h->graph_exec, h->stream));
-    cudaEventRecord(h->ev1, h->stream);
+    if (!h->graph_self_published) cudaEventRecord(h->ev1, h->stream);
     h->launches = h->graph_launches;
     h->gathered = false;
-    h->fetched = false;
+    h->self_published = h->graph_self_published;
+    h->fetched = h->graph_self_published;   // a single-frame run stores its results into the pinned mirrors itself
     h->ran = true;
     return CP_OK;
   }
@@ -1899,9 +2012,10 @@ cp_status cp_batch_run(cp_handle* h, const cp_detect_params* d, const cp_ground_
   memcpy(h->graph_key, &key, sizeof(RunKey));
   h->graph_key_valid = true;
   h->graph_launches = h->launches;
-  cudaEventRecord(h->ev0, h->stream);
+  h->graph_self_published = h->self_published;
+  if (!h->self_published) cudaEventRecord(h->ev0, h->stream);
   CK(cudaGraphLaunch(h->graph_exec, h->stream));
-  cudaEventRecord(h->ev1, h->stream);
+  if (!h->self_published) cudaEventRecord(h->ev1, h->stream);
   h->ran = true;
   return CP_OK;
 } catch (...) {
@@ -2050,6 +2164,10 @@ cp_status cp_last_run_ms(cp_handle* h, float* ms) try {
   if (!h || !ms) return CP_E_PARAM;
   if (!h->ran) {
     h->err = "no batch has run";
+    return CP_E_STATE;
+  }
+  if (h->self_published) {
+    h->err = "single-frame runs are one launch and are not bracketed by events; cp_set_stage_timing(h, 1) times them";
     return CP_E_STATE;
   }
   CK(cudaEventSynchronize(h->ev1));

@@ -648,3 +648,54 @@ def test_pairs_tested_counter(mode):
         h.detect_batch([PointCloud2.from_xyzi(f) for f in frames], cfg.detect, cfg.ground)   # counters restart per run
         v2, t2 = h.last_pairs()
         assert v2 <= visited * 2 and t2 > 0
+
+
+@pytest.mark.parametrize("case", ["cfg2_ground", "cfg1_no_ground", "pcl32_no_ground", "tiny", "odd_sizes", "overflow"])
+def test_single_frame_in_one_launch_equals_the_multi_launch_path(case):
+    """A single frame is ONE kernel launch (single_frame.cuh: 16-CTA cluster front end, back half and result publish
+    fused): same cones and counters as the multi-launch path (CONESGPU_SINGLE=0) and as the oracle, on the direct
+    run, the graph capture and the replay; frames that outgrow the shared-memory budget fall back and still agree."""
+    cfg = scans.config(2)
+    g = cfg.ground
+    d = cfg.detect
+    if case == "cfg2_ground":
+        clouds = [scans.generate(cfg, 1, base_seed=11)[0]]
+    elif case == "cfg1_no_ground":
+        cfg = scans.config(1)
+        d, g = cfg.detect, None
+        clouds = [scans.generate(cfg, 1, base_seed=12)[0]]
+    elif case == "pcl32_no_ground":     # what the detection node receives from the ground node: 32-byte PCL points
+        cfg = scans.config(1)
+        d, g = cfg.detect, None
+        clouds = [scans.generate(cfg, 1, base_seed=13)[0]]
+    elif case == "tiny":
+        f = scans.generate(cfg, 1, base_seed=14)[0]
+        clouds = [f[:1], f[:33], f[:2048], f[:4097]]
+    elif case == "odd_sizes":
+        f = scans.generate(cfg, 1, base_seed=15)[0]
+        clouds = [f[:65535], f[:100001], np.concatenate([f, f])[:262144], np.concatenate([f, f])[:262145]]
+    else:                               # ground left in: C and V outgrow every shared-memory budget
+        g = None
+        clouds = [scans.generate(scans.config(3), 1, base_seed=16)[0]]
+    for cloud in clouds:
+        if case == "pcl32_no_ground":
+            msg = _msg_with_layout(cloud, 32, (0, 4, 8, 16))
+        else:
+            msg = PointCloud2.from_xyzi(cloud)
+        out = {}
+        for single in ("1", "0"):
+            with api.ConesGpu(max_points=max(len(cloud), 1), max_frames=1, max_point_step=32,
+                              env={"CONESGPU_SINGLE": single}) as h:
+                runs = [h.detect(msg, d, g, cap=1 << 16) for _ in range(4)]
+                for cl, ctr in runs[1:]:
+                    assert np.array_equal(cl.view(np.uint32), runs[0][0].view(np.uint32))
+                    assert ctr.tobytes() == runs[0][1].tobytes()
+                out[single] = (runs[0][0], runs[0][1], h.last_launch_count())
+        assert np.array_equal(out["1"][0].view(np.uint32), out["0"][0].view(np.uint32)), (case, len(cloud))
+        assert out["1"][1].tobytes() == out["0"][1].tobytes(), (case, len(cloud), out["1"][1], out["0"][1])
+        exp, octr, _ = O.detect(O.view_of_xyzi(cloud), d, g, O.CANONICAL)
+        assert np.array_equal(out["1"][0].view(np.uint32), exp.view(np.uint32)), (case, len(cloud))
+        assert int(out["1"][1]["n_ground_kept"]) == octr.n_ground_kept and int(out["1"][1]["n_cropped"]) == octr.n_cropped
+        if case not in ("overflow",) and len(cloud) <= 262144:
+            assert out["1"][2] == 1, (case, len(cloud), "a single frame must be one launch")
+            assert out["0"][2] > 1
