@@ -163,6 +163,8 @@ struct cp_handle {
   bool use_single = true;      // CONESGPU_SINGLE=0: a single frame takes the multi-launch path (A/B, tests)
   bool self_published = false; // the last run stored its results into the pinned mirrors itself (single_frame.cuh)
   bool graph_self_published = false;
+  cp_ground_params rp_ground{};   // ground parameters of the last run (valid when rp_has_ground)
+  bool rp_has_ground = false;
   bool tail_priority = false;  // CONESGPU_PRIO=1: greatest-priority stream, pass 1 demoted
   int prio_low = 0;
   int k1_ctas_per_sm = 0;  // CONESGPU_K1_CTAS: separate grid cap for pass 1 (0 = stream_ctas_per_sm)
@@ -1205,6 +1207,8 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
   h->rp.crop = crop;
   h->rp.csort_bits = csort_bits;
   h->rp.osort_bits = osort_bits;
+  h->rp_has_ground = ground != nullptr;
+  if (ground) h->rp_ground = *ground;
   h->self_published = false;
   if (single_frame_eligible(h, g)) {
     // a node's single frame: front end, back half and result publish in one launch (single_frame.cuh)
@@ -2040,7 +2044,19 @@ cp_status cp_sync(cp_handle* h) try {
     if (h->back_mode < 1 && mc <= 2048 && mv <= 1024) next = 1;
     else if (h->back_mode < 2 && mc <= 4096 && mv <= 2048) next = 2;
     h->back_mode = next;
-    cp_status st = enqueue_back(h, true);
+    cp_status st;
+    if (h->self_published) {
+      // the one-launch path skips the resets the other back halves rely on (look-back descriptors, tickets):
+      // the frame is run again through the multi-launch path, which the handle then keeps for this budget
+      const bool saved = h->use_single;
+      const cp_detect_params dd = h->rp.d;
+      const cp_ground_params gg = h->rp_ground;
+      h->use_single = false;
+      st = enqueue_pipeline(h, &dd, h->rp_has_ground ? &gg : nullptr);
+      h->use_single = saved;
+    } else {
+      st = enqueue_back(h, true);
+    }
     if (st) return st;
     st = enqueue_result_fetch(h);
     if (st) return st;
