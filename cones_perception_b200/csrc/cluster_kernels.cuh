@@ -2,11 +2,14 @@
 // (reference call site: euclidan_cluster(), src/cone_detection.cpp:206-220; semantics:
 // SURVEY.md Appendix A.5) plus the centroid loop (src/cone_detection.cpp:261-273, A.6).
 //
-//   cell_key      voxel centroid -> cell of a uniform grid with edge > cluster tolerance
+//   cell_key      voxel centroid -> cell of a uniform grid with edge 0.505 x cluster tolerance
 //   (radix sort by cell key)
 //   cell heads    -> cell start offsets;  hash_insert: cell key -> cell id (open addressing)
-//   neighbour_union   27 adjacent cells, exact FLANN distance test, lock-free CAS union-find
-//                     linking the larger root under the smaller (root = min index = label)
+//   cell_union    one warp per occupied cell.  The cell's diagonal is shorter than the tolerance, so its voxels
+//                 are one component without a single distance test; the 62 "forward" cells of the 5x5x5
+//                 neighbourhood are then joined cell to cell: already in one tree -> skipped after two finds,
+//                 otherwise voxel pairs are tested (exact FLANN distance) until the first hit.  Lock-free CAS
+//                 union-find linking the larger root under the smaller (root = min index = label).
 //   flatten_count     label = root, component sizes
 //   (radix sort by label) -> component heads -> size filter + ordering key
 //   (radix sort by frame, size desc) -> emit centroids in canonical cluster order
@@ -18,16 +21,20 @@ namespace cp {
 
 struct ClusterK {
   float r2;          // squared radius handed to FLANN: (float)((double)tol_f * tol_f)
-  float inv_h;       // 1 / cell edge (edge = tolerance * 1.01)
+  float inv_h;       // 1 / sweep cell edge of the per-frame kernel (edge = tolerance * 1.01)
+  float inv_g;       // 1 / cell edge of the general path's grid (edge = tolerance * 0.505: diagonal < tolerance)
   float origin;      // grid origin offset: coordinates + origin >= 0
-  u32 nx;            // cells per axis
+  u32 nx;            // cells per axis of the general path's grid
   u32 min_size, max_size;
   u32 frame_bits, size_bits;
 };
 
-__device__ __forceinline__ u32 cell_coord(float c, const ClusterK& k) {
-  const float t = floorf((c + k.origin) * k.inv_h);
+// `outside` is raised when the coordinate lies beyond the grid (cannot happen behind the distance crop: the grid
+// spans distance_treshold_max plus a margin); the cell arguments of cell_union_kernel do not hold for a clamped cell
+__device__ __forceinline__ u32 cell_coord(float c, const ClusterK& k, bool& outside) {
+  const float t = floorf((c + k.origin) * k.inv_g);
   i32 v = (i32)t;
+  if (!(t >= 0.0f) || !(t < (float)k.nx)) outside = true;
   v = v < 0 ? 0 : v;
   v = v >= (i32)k.nx ? (i32)k.nx - 1 : v;
   return (u32)v;
@@ -42,15 +49,17 @@ __global__ void cluster_bits_kernel(Ctl* ctl, u32 csort_bits, u32 osort_bits) {
 
 __global__ void cell_key_kernel(const Ctl* __restrict__ ctl, ClusterK k, const float4* __restrict__ vox,
                                 const u32* __restrict__ vox_frame, u64* __restrict__ keys,
-                                u32* __restrict__ vals, u32* __restrict__ parent) {
+                                u32* __restrict__ vals, u32* __restrict__ parent, Ctl* ctl_w) {
   const u32 nv = ctl->n_vox;
+  bool outside = false;
   for (u32 v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
     const float4 p = vox[v];
-    const u64 cx = cell_coord(p.x, k), cy = cell_coord(p.y, k), cz = cell_coord(p.z, k);
+    const u64 cx = cell_coord(p.x, k, outside), cy = cell_coord(p.y, k, outside), cz = cell_coord(p.z, k, outside);
     keys[v] = (((u64)vox_frame[v] * k.nx + cz) * k.nx + cy) * k.nx + cx;
     vals[v] = v;
     parent[v] = v;
   }
+  if (outside) atomicOr(&ctl_w->error, kErrInternal);   // never silently: surfaces as an error at cp_sync
 }
 
 // live hash capacity = next pow2 >= 2 * n_cells; clear that prefix
@@ -133,83 +142,113 @@ __device__ __forceinline__ void uf_union(u32* parent, u32 a, u32 b) {
   }
 }
 
-// One warp per sorted voxel position.  Lanes 0..26 look up the 27 neighbour cells (one hash probe each, in
-// parallel); then the warp walks the cells one after the other with its lanes strided over the candidates, so the
-// index and parent loads of a crowded cell (a solid blob puts ~1000 voxels into one tolerance cell) are coalesced
-// instead of 32 lanes each walking a list of their own.
-__global__ void __launch_bounds__(256) neighbour_union_kernel(const Ctl* __restrict__ ctl, ClusterK k,
-                                                              const u64* keys_a, const u64* keys_b, const u32* vals_a,
-                                                              const u32* vals_b, const u32* __restrict__ cstart,
-                                                              const u64* __restrict__ hkeys,
-                                                              const u32* __restrict__ hvals,
-                                                              const float4* __restrict__ vox, u32* __restrict__ parent,
-                                                              Ctl* ctl_w) {
+// The 62 cells of the 5x5x5 neighbourhood that come after the centre in (dz, dy, dx) order — every pair of cells
+// is visited from one side only — nearest first, so that face neighbours (which almost always connect at the
+// first pairs tested) are joined before the far corners are looked at and usually found connected already.
+__device__ const signed char kForwardCells[62][3] = {
+    {1,0,0}, {0,1,0}, {0,0,1}, {-1,1,0}, {1,1,0}, {0,-1,1}, {-1,0,1}, {1,0,1}, {0,1,1}, {-1,-1,1}, {1,-1,1}, {-1,1,1},
+    {1,1,1}, {2,0,0}, {0,2,0}, {0,0,2}, {-2,1,0}, {2,1,0}, {-1,2,0}, {1,2,0}, {0,-2,1}, {-2,0,1}, {2,0,1}, {0,2,1},
+    {0,-1,2}, {-1,0,2}, {1,0,2}, {0,1,2}, {-1,-2,1}, {1,-2,1}, {-2,-1,1}, {2,-1,1}, {-2,1,1}, {2,1,1}, {-1,2,1},
+    {1,2,1}, {-1,-1,2}, {1,-1,2}, {-1,1,2}, {1,1,2}, {-2,2,0}, {2,2,0}, {0,-2,2}, {-2,0,2}, {2,0,2}, {0,2,2},
+    {-2,-2,1}, {2,-2,1}, {-2,2,1}, {2,2,1}, {-1,-2,2}, {1,-2,2}, {-2,-1,2}, {2,-1,2}, {-2,1,2}, {2,1,2}, {-1,2,2},
+    {1,2,2}, {-2,-2,2}, {2,-2,2}, {-2,2,2}, {2,2,2}};
+
+// One warp per occupied cell of the grid with edge g = 0.505 x tolerance.
+//  * 3 g^2 = 0.765 tol^2 < r2: any two voxels of one cell pass FLANN's test (with a 23 % margin against fp32
+//    rounding), so the cell is linked into one tree without evaluating a distance.  Dense data is where the
+//    pair-by-pair version drowned: a solid 1 m^3 blob gives every voxel ~4000 neighbours (62 M pair visits per
+//    frame of config 5); a cell holds ~125 of them.
+//  * two voxels within the tolerance differ by fewer than tol / g = 1.98 cells per axis, i.e. by at most 2 cell
+//    indices: all edges lie inside the 5x5x5 neighbourhood.  For a neighbour cell that already hangs under the
+//    same root nothing is tested; otherwise the warp's lanes walk the voxel pairs of the two cells until one
+//    passes the exact test (strict <, FLANN L2_Simple) and links the two trees.  If no pair passes, the cells are
+//    not directly connected — an edge between them would have been found, every pair is looked at.
+// Components and labels (root = smallest voxel index) are those of the pair-by-pair graph.
+__global__ void __launch_bounds__(256) cell_union_kernel(const Ctl* __restrict__ ctl, ClusterK k,
+                                                         const u64* keys_a, const u64* keys_b, const u32* vals_a,
+                                                         const u32* vals_b, const u32* __restrict__ cstart,
+                                                         const u64* __restrict__ hkeys,
+                                                         const u32* __restrict__ hvals,
+                                                         const float4* __restrict__ vox, u32* __restrict__ parent,
+                                                         Ctl* ctl_w) {
   const u32 nv = ctl->n_vox, nc = ctl->n_cells, mask = ctl->hash_mask;
-  u32 n_visited = 0, n_tested = 0;   // statistics (cp_last_pairs)
   const bool inb = sorted_in_b(ctl->csort_bits);
   const u64* keys = inb ? keys_b : keys_a;
   const u32* vals = inb ? vals_b : vals_a;
   const u32 lane = threadIdx.x & 31u;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 pos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pos < nv; pos += nwarps) {
-    const u64 ck = keys[pos];
-    const u32 cx = (u32)(ck % k.nx), cy = (u32)((ck / k.nx) % k.nx), cz = (u32)((ck / ((u64)k.nx * k.nx)) % k.nx);
-    u32 b = 0, e = 0;  // lane nb: candidate positions [b, e) of neighbour cell nb
-    if (lane < 27u) {
-      const i32 dx = (i32)(lane % 3u) - 1, dy = (i32)((lane / 3u) % 3u) - 1, dz = (i32)(lane / 9u) - 1;
-      const i32 qx = (i32)cx + dx, qy = (i32)cy + dy, qz = (i32)cz + dz;
-      if (qx >= 0 && qy >= 0 && qz >= 0 && qx < (i32)k.nx && qy < (i32)k.nx && qz < (i32)k.nx) {
-        const u64 nk = (u64)((long long)ck + dx + (long long)dy * (long long)k.nx +
-                             (long long)dz * (long long)k.nx * (long long)k.nx);
-        const u32 c = hash_find(hkeys, hvals, mask, nk);
-        if (c != 0xFFFFFFFFu) {
-          b = cstart[c];
-          // own cell: only earlier positions (each pair once); other cells: the whole cell, filtered by u < v
-          e = (lane == 13u) ? pos : ((c + 1 < nc) ? cstart[c + 1] : nv);
-        }
-      }
+  unsigned long long n_visited = 0, n_tested = 0;   // statistics (cp_last_pairs)
+  for (u32 c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nc; c += nwarps) {
+    const u32 b = cstart[c], e = (c + 1 < nc) ? cstart[c + 1] : nv;
+    const u64 ck = keys[b];
+    const i32 cx = (i32)(ck % k.nx), cy = (i32)((ck / k.nx) % k.nx), cz = (i32)((ck / ((u64)k.nx * k.nx)) % k.nx);
+    // ---- the cell itself: one tree under its smallest voxel index, no distance tests
+    u32 m = 0xFFFFFFFFu;
+    for (u32 j = b + lane; j < e; j += 32u) m = min(m, vals[j]);
+    m = __reduce_min_sync(kFull, m);
+    for (u32 j = b + lane; j < e; j += 32u) {
+      const u32 v = vals[j];
+      if (v != m) uf_union(parent, v, m);
     }
-    const u32 v = vals[pos];
-    const float4 p = vox[v];
-    u32 rv = uf_find(parent, v);  // v's root, or (after other lanes' / warps' links) one of v's ancestors
-    for (u32 nb = 0; nb < 27u; ++nb) {
-      const u32 cb = __shfl_sync(kFull, b, nb), ce = __shfl_sync(kFull, e, nb);
-      if (cb >= ce) continue;  // uniform over the warp
-      for (u32 j = cb + lane; j < ce; j += 32u) {
-        const u32 u = vals[j];
-        if (nb != 13u && u > v) continue;  // each cross-cell pair is seen from both sides: test once
-        ++n_visited;
-        // u already hangs under v's root: the edge cannot change anything.  In a solid blob (thousands of
-        // mutual neighbours per voxel) almost every candidate leaves here after one 4-byte load.
-        if (((volatile u32*)parent)[u] == rv) continue;
-        const float4 q = vox[u];
-        ++n_tested;
-        // FLANN: dist = L2_Simple(query, point); accepted iff dist < radius (strict)
-        if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < k.r2) {
-          u32 ru = uf_find(parent, u);
-          if (ru != u) ((volatile u32*)parent)[u] = ru;  // u is not a root: point it at its root for later visitors
-          while (ru != rv) {  // larger root under the smaller; parents always have smaller indices
-            const u32 hi = rv > ru ? rv : ru, sm = rv > ru ? ru : rv;
-            const u32 old = atomicCAS(&parent[hi], hi, sm);
-            if (old == hi) {
-              rv = sm;
-              break;
-            }
-            if (hi == rv) rv = uf_find(parent, old);
-            else ru = uf_find(parent, old);
+    __syncwarp();
+    // ---- the forward neighbour cells, nearest first
+    for (u32 round = 0; round < 2u; ++round) {
+      const u32 q = round * 32u + lane;
+      u32 nb_b = 0, nb_e = 0;
+      if (q < 62u) {
+        const i32 dx = kForwardCells[q][0], dy = kForwardCells[q][1], dz = kForwardCells[q][2];
+        const i32 qx = cx + dx, qy = cy + dy, qz = cz + dz;
+        if (qx >= 0 && qy >= 0 && qz >= 0 && qx < (i32)k.nx && qy < (i32)k.nx && qz < (i32)k.nx) {
+          const u64 nk = (u64)((long long)ck + dx + (long long)dy * (long long)k.nx +
+                               (long long)dz * (long long)k.nx * (long long)k.nx);
+          const u32 n = hash_find(hkeys, hvals, mask, nk);
+          if (n != 0xFFFFFFFFu) {
+            nb_b = cstart[n];
+            nb_e = (n + 1 < nc) ? cstart[n + 1] : nv;
           }
         }
       }
-      __syncwarp();
-      rv = __reduce_min_sync(kFull, rv);  // every lane holds v or an ancestor of v: the smallest is the highest
+      u32 found = __ballot_sync(kFull, nb_e > nb_b);
+      while (found) {
+        const int src = __ffs(found) - 1;
+        found &= found - 1;
+        const u32 ob = __shfl_sync(kFull, nb_b, src), oe = __shfl_sync(kFull, nb_e, src);
+        // already one tree (through this or any other chain of cells): nothing to test
+        u32 same = 0;
+        if (lane == 0) same = uf_find(parent, m) == uf_find(parent, vals[ob]) ? 1u : 0u;
+        if (__shfl_sync(kFull, same, 0)) continue;
+        const u32 nb = oe - ob;
+        const unsigned long long total = (unsigned long long)(e - b) * nb;
+        for (unsigned long long t0 = 0; t0 < total; t0 += 32ull) {
+          const unsigned long long t = t0 + lane;
+          bool hit = false;
+          u32 vi = 0, vj = 0;
+          if (t < total) {
+            vi = vals[b + (u32)(t / nb)];
+            vj = vals[ob + (u32)(t % nb)];
+            const float4 p = vox[vi], r = vox[vj];
+            ++n_visited;
+            ++n_tested;
+            // FLANN: dist = L2_Simple(query, point); accepted iff dist < radius (strict)
+            hit = l2_simple(p.x, p.y, p.z, r.x, r.y, r.z) < k.r2;
+          }
+          const u32 hits = __ballot_sync(kFull, hit);
+          if (hits) {
+            if ((int)lane == __ffs(hits) - 1) uf_union(parent, vi, vj);
+            break;
+          }
+        }
+        __syncwarp();
+      }
     }
-    if (lane == 0 && rv != v) ((volatile u32*)parent)[v] = rv;
   }
-  n_visited = __reduce_add_sync(kFull, n_visited);
-  n_tested = __reduce_add_sync(kFull, n_tested);
+  for (int o = 16; o; o >>= 1) {
+    n_visited += __shfl_xor_sync(kFull, n_visited, o);
+    n_tested += __shfl_xor_sync(kFull, n_tested, o);
+  }
   if (lane == 0 && n_visited) {
-    atomicAdd(&ctl_w->pairs_visited, (unsigned long long)n_visited);
-    atomicAdd(&ctl_w->pairs_tested, (unsigned long long)n_tested);
+    atomicAdd(&ctl_w->pairs_visited, n_visited);
+    atomicAdd(&ctl_w->pairs_tested, n_tested);
   }
 }
 

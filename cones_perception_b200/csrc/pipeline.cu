@@ -325,15 +325,16 @@ cp_status make_cluster(cp_handle* h, const cp_detect_params* d, u32 n_frames, Cl
     h->err = "cone_width/cone_height give a non-positive or non-finite cluster tolerance";
     return CP_E_PARAM;
   }
-  const double edge = (double)tol_f * 1.01;
+  const double edge = (double)tol_f * 0.505;   // general path's grid: cell diagonal < tolerance (cell_union_kernel)
   double reach = fabs(d->distance_treshold_max);
   if (!(reach < 1e6)) {
     h->err = "distance_treshold_max must be finite and below 1e6 m";
     return CP_E_PARAM;
   }
-  reach += 2 * edge;
+  reach += 4 * edge;
   const u64 nx = (u64)ceil(2.0 * reach / edge) + 2;
-  k->inv_h = (float)(1.0 / edge);
+  k->inv_h = (float)(1.0 / ((double)tol_f * 1.01));   // sweep cells of the per-frame kernel
+  k->inv_g = (float)(1.0 / edge);
   k->origin = (float)reach;
   k->nx = (u32)nx;
   const u64 cells = (u64)n_frames * nx * nx * nx;
@@ -803,7 +804,7 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   // ---- Euclidean clustering
   cluster_bits_kernel<<<1, 1, 0, h->stream>>>(h->d_ctl, csort_bits, osort_bits);
   cell_key_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, ck, h->d_vox, h->d_vox_frame, h->d_keys_a, h->d_vals_a,
-                                                h->d_parent);
+                                                h->d_parent, h->d_ctl);
   h->launches += 2;
   {
     SortArgs sa = sort_args(h, false, &h->d_ctl->n_vox, &h->d_ctl->csort_bits);
@@ -830,7 +831,7 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   hash_clear_kernel<<<grid_for(h->hash_cap, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_ctl, h->d_hkeys);
   hash_insert_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_cstart, h->d_hkeys,
                                                    h->d_hvals);
-  neighbour_union_kernel<<<grid_for(h->cap_v * 32ull, 256, h->sms, 8), 256, 0, h->stream>>>(
+  cell_union_kernel<<<grid_for(h->cap_v * 32ull, 256, h->sms, 8), 256, 0, h->stream>>>(
       h->d_ctl, ck, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b, h->d_cstart, h->d_hkeys, h->d_hvals,
       h->d_vox, h->d_parent, h->d_ctl);
   flatten_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_parent, h->d_label, h->d_keys_a, h->d_vals_a);
