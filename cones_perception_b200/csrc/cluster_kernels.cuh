@@ -336,7 +336,9 @@ struct ClusterRec {
   u32 size, min_index;
 };
 
-// one thread per kept cluster, in canonical order (frame, size desc, min index asc)
+// one warp per kept cluster, in canonical order (frame, size desc, min index asc): the lanes fetch 32 members at
+// a time and every lane adds them in ascending voxel index, so the fp32 sums stay sequential
+// (src/cone_detection.cpp:264-268) without one thread chasing index -> voxel loads one by one
 __global__ void emit_clusters_kernel(const Ctl* __restrict__ ctl, const u32* ovals_a, const u32* ovals_b,
                                      const u64* lkeys_a, const u64* lkeys_b, const u32* lvals_a,
                                      const u32* lvals_b, const u32* __restrict__ comp_start,
@@ -348,29 +350,41 @@ __global__ void emit_clusters_kernel(const Ctl* __restrict__ ctl, const u32* ova
   const bool lb = sorted_in_b(ctl->lsort_bits);
   const u64* lkeys = lb ? lkeys_b : lkeys_a;
   const u32* lvals = lb ? lvals_b : lvals_a;
-  for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < nk; r += gridDim.x * blockDim.x) {
+  const u32 lane = threadIdx.x & 31u;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nk; r += nwarps) {
     if (r >= out_cap) {
-      atomicOr(&ctl_w->error, kErrVoxels);
+      if (lane == 0) atomicOr(&ctl_w->error, kErrVoxels);
       continue;
     }
     const u32 c = ovals[r];
     const u32 b = comp_start[c];
     const u32 e = (c + 1 < ncomp) ? comp_start[c + 1] : nv;
     const u32 root = (u32)lkeys[b];
-    // src/cone_detection.cpp:264-268: float x, y accumulated over ascending voxel indices
     float x = 0.0f, y = 0.0f;
-    for (u32 j = b; j < e; ++j) {
-      const float4 p = vox[lvals[j]];
-      x = __fadd_rn(x, p.x);
-      y = __fadd_rn(y, p.y);
+    for (u32 j0 = b; j0 < e; j0 += 32u) {
+      const u32 j = j0 + lane;
+      float px = 0.f, py = 0.f;
+      if (j < e) {
+        const float4 p = vox[lvals[j]];
+        px = p.x;
+        py = p.y;
+      }
+      const u32 m = e - j0 < 32u ? e - j0 : 32u;
+      for (u32 q = 0; q < m; ++q) {
+        x = __fadd_rn(x, __shfl_sync(kFull, px, q));
+        y = __fadd_rn(y, __shfl_sync(kFull, py, q));
+      }
     }
-    const float cnt = (float)(i32)(e - b);
-    ClusterRec o;
-    o.x = __fdiv_rn(x, cnt);
-    o.y = __fdiv_rn(y, cnt);
-    o.size = e - b;
-    o.min_index = root - v_off[vox_frame[root]];
-    out[r] = o;
+    if (lane == 0) {
+      const float cnt = (float)(i32)(e - b);
+      ClusterRec o;
+      o.x = __fdiv_rn(x, cnt);
+      o.y = __fdiv_rn(y, cnt);
+      o.size = e - b;
+      o.min_index = root - v_off[vox_frame[root]];
+      out[r] = o;
+    }
   }
 }
 

@@ -148,7 +148,7 @@ struct cp_handle {
   u32 *d_src = nullptr, *d_frame = nullptr;
   u64 *d_keys_a = nullptr, *d_keys_b = nullptr, *d_okeys_a = nullptr, *d_okeys_b = nullptr;
   u32 *d_vals_a = nullptr, *d_vals_b = nullptr, *d_ovals_a = nullptr, *d_ovals_b = nullptr;
-  u32 *d_tile_hist = nullptr, *d_digit_total = nullptr;
+  u32 *d_sort_hdr = nullptr, *d_sort_state = nullptr;   // radix_sort.cuh: tickets + digit totals, look-back words
   u32 *d_excl = nullptr, *d_vstart = nullptr, *d_cstart = nullptr, *d_comp_start = nullptr;
   float4* d_vox = nullptr;
   u32 *d_vox_frame = nullptr, *d_parent = nullptr, *d_label = nullptr;
@@ -710,8 +710,8 @@ SortArgs sort_args(cp_handle* h, bool order_sort, const u32* d_n, const u32* d_b
   a.vals_b = order_sort ? h->d_ovals_b : h->d_vals_b;
   a.d_n = d_n;
   a.d_bits = d_bits;
-  a.tile_hist = h->d_tile_hist;
-  a.digit_total = h->d_digit_total;
+  a.hdr = h->d_sort_hdr;
+  a.state = h->d_sort_state;
   a.tiles_cap = h->sort_tiles_cap;
   return a;
 }
@@ -1717,8 +1717,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
   A(dalloc(h, &h->d_okeys_b, h->cap_v));
   A(dalloc(h, &h->d_ovals_a, h->cap_v));
   A(dalloc(h, &h->d_ovals_b, h->cap_v));
-  A(dalloc(h, &h->d_tile_hist, (size_t)kRadix * h->sort_tiles_cap));
-  A(dalloc(h, &h->d_digit_total, kRadix));
+  A(dalloc(h, &h->d_sort_state, (size_t)2 * kRadix * h->sort_tiles_cap));
+  A(dalloc(h, &h->d_sort_hdr, kSortHdrWords));
   A(dalloc(h, &h->d_excl, h->cap_c));
   A(dalloc(h, &h->d_vstart, h->cap_v));
   A(dalloc(h, &h->d_cstart, h->cap_v));

@@ -1,10 +1,13 @@
 // radix_sort.cuh — hand-written stable LSD radix sort of (u64 key, u32 value) pairs.
 //
-// No CUB / Thrust.  8-bit digits, three kernels per pass (tile histogram, per-digit scan
-// over tiles, stable scatter).  The element count and the number of significant key bits
-// are read from device memory, so a sort whose size depends on earlier kernels needs no
-// host synchronisation: the host enqueues ceil(max_bits/8) passes and passes beyond the
-// live bit count exit immediately.  Data ping-pongs A -> B -> A ...; after the sort the
+// No CUB / Thrust.  8-bit digits, ONE kernel per pass ("onesweep"): a tile ranks its 2048 items per digit
+// (stable: warp-contiguous chunks + match_any), publishes its 256 digit counts and finds the counts of the tiles
+// before it by decoupled look-back (tiles are handed out by ticket, so every earlier tile is already running);
+// the global digit bases of ALL passes come from one histogram kernel up front — the key multiset does not change
+// between passes.  A sort is therefore 1 small memset + 1 + passes launches instead of 3 x passes.
+// The element count and the number of significant key bits are read from device memory, so a sort whose size
+// depends on earlier kernels needs no host synchronisation: the host enqueues ceil(max_bits/8) passes and passes
+// beyond the live bit count exit immediately.  Data ping-pongs A -> B -> A ...; after the sort the
 // result sits in sorted_in_b(bits) ? B : A.
 #pragma once
 #include "common.cuh"
@@ -20,6 +23,10 @@ constexpr int kRadix = 256;
 __host__ __device__ __forceinline__ u32 sort_passes(u32 bits) { return (bits + 7u) >> 3; }
 __host__ __device__ __forceinline__ bool sorted_in_b(u32 bits) { return sort_passes(bits) & 1u; }
 
+constexpr u32 kSortMaxPasses = 8;
+constexpr u32 kSortHdrWords = kSortMaxPasses + kSortMaxPasses * kRadix;   // tickets, then digit totals per pass
+constexpr u32 kFlagAgg = 1u << 30, kFlagPre = 2u << 30, kSortValMask = (1u << 30) - 1u;
+
 struct SortArgs {
   u64* keys_a;
   u64* keys_b;
@@ -27,80 +34,42 @@ struct SortArgs {
   u32* vals_b;
   const u32* d_n;     // device: element count
   const u32* d_bits;  // device: significant key bits
-  u32* tile_hist;     // [256][tiles_cap] digit-major per-tile counts -> exclusive offsets
-  u32* digit_total;   // [256]
+  u32* hdr;           // [8] tile tickets per pass, [8][256] digit totals per pass (zeroed by the host per sort)
+  u32* state;         // [2][tiles_cap][256] look-back words: flag | count, double-buffered by pass parity
   u32 tiles_cap;
 };
 
-// pass kernel 1: per-tile digit histogram
-__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(SortArgs a, u32 pass) {
+// once per sort: digit histograms of every live pass (one read of the keys) and a clean look-back buffer for pass 0
+__global__ void __launch_bounds__(kSortThreads) sort_prepare_kernel(SortArgs a) {
   const u32 bits = *a.d_bits, n = *a.d_n;
-  if (pass * 8 >= bits || n == 0) return;
+  if (bits == 0 || n == 0) return;
+  const u32 passes = sort_passes(bits) < kSortMaxPasses ? sort_passes(bits) : kSortMaxPasses;
   const u32 tiles = (n + kSortTile - 1) / kSortTile;
-  const u64* src = (pass & 1) ? a.keys_b : a.keys_a;
-  const u32 shift = pass * 8;
-  __shared__ u32 hist[kRadix];
+  __shared__ u32 hist[kSortMaxPasses][kRadix];
+  for (u32 p = 0; p < passes; ++p) hist[p][threadIdx.x] = 0;
+  __syncthreads();
   for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    hist[threadIdx.x] = 0;
-    __syncthreads();
+    a.state[(u64)tile * kRadix + threadIdx.x] = 0u;
     const u32 base = tile * kSortTile;
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
       const u32 i = base + r * kSortThreads + threadIdx.x;
-      if (i < n) atomicAdd(&hist[(u32)(src[i] >> shift) & 0xFFu], 1u);
-    }
-    __syncthreads();
-    a.tile_hist[(u64)threadIdx.x * tiles + tile] = hist[threadIdx.x];
-    __syncthreads();
-  }
-}
-
-// pass kernel 2: one CTA per digit — exclusive scan of that digit's counts over tiles
-__global__ void __launch_bounds__(1024) sort_scan_kernel(SortArgs a, u32 pass) {
-  const u32 bits = *a.d_bits, n = *a.d_n;
-  if (pass * 8 >= bits || n == 0) return;
-  const u32 tiles = (n + kSortTile - 1) / kSortTile;
-  u32* row = a.tile_hist + (u64)blockIdx.x * tiles;
-  __shared__ u32 warp_sum[32];
-  __shared__ u32 carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
-  for (u32 c0 = 0; c0 < tiles; c0 += blockDim.x) {
-    const u32 i = c0 + threadIdx.x;
-    const u32 v = (i < tiles) ? row[i] : 0u;
-    u32 inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      u32 t = __shfl_up_sync(kFull, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_sum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      u32 w = warp_sum[lane];
-      u32 winc = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        u32 t = __shfl_up_sync(kFull, winc, o);
-        if (lane >= o) winc += t;
+      if (i < n) {
+        const u64 k = a.keys_a[i];
+        for (u32 p = 0; p < passes; ++p) atomicAdd(&hist[p][(u32)(k >> (8 * p)) & 0xFFu], 1u);
       }
-      warp_sum[lane] = winc - w;  // exclusive over warps
     }
-    __syncthreads();
-    const u32 carry = carry_s;
-    const u32 excl = carry + warp_sum[warp] + inc - v;
-    if (i < tiles) row[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
-    __syncthreads();
   }
-  if (threadIdx.x == 0) a.digit_total[blockIdx.x] = carry_s;
+  __syncthreads();
+  for (u32 p = 0; p < passes; ++p) {
+    const u32 c = hist[p][threadIdx.x];
+    if (c) atomicAdd(&a.hdr[kSortMaxPasses + p * kRadix + threadIdx.x], c);
+  }
 }
 
-// pass kernel 3: stable scatter.  Warp w of a tile owns the contiguous items
-// [w*256, (w+1)*256) and walks them 32 at a time, so ranks follow input order.
-__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortArgs a, u32 pass) {
+// one pass.  Warp w of a tile owns the contiguous items [w*256, (w+1)*256) and walks them 32 at a time, so ranks
+// follow input order (stable).
+__global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(SortArgs a, u32 pass) {
   const u32 bits = *a.d_bits, n = *a.d_n;
   if (pass * 8 >= bits || n == 0) return;
   const u32 tiles = (n + kSortTile - 1) / kSortTile;
@@ -110,14 +79,18 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortArgs a, 
   const u32* vsrc = odd ? a.vals_b : a.vals_a;
   u32* vdst = odd ? a.vals_a : a.vals_b;
   const u32 shift = pass * 8;
+  u32* st = a.state + (u64)(pass & 1u) * a.tiles_cap * kRadix;
+  u32* st_next = a.state + (u64)((pass + 1u) & 1u) * a.tiles_cap * kRadix;
 
   __shared__ u32 whist[kSortWarps][kRadix];
   __shared__ u32 gbase[kRadix];
+  __shared__ u32 excl_s[kRadix];
+  __shared__ u32 s_tile;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
 
-  // exclusive scan of the 256 digit totals (every CTA recomputes it; 256 values)
+  // exclusive scan of this pass's 256 digit totals (every CTA recomputes it; 256 values)
   {
-    u32 v = a.digit_total[threadIdx.x];
+    u32 v = a.hdr[kSortMaxPasses + pass * kRadix + threadIdx.x];
     u32 inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -130,13 +103,16 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortArgs a, 
     u32 off = 0;
     for (int w = 0; w < warp; ++w) off += wtot[w];
     gbase[threadIdx.x] = off + inc - v;
-    __syncthreads();
   }
 
-  for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = atomicAdd(&a.hdr[pass], 1u);   // ticket: earlier tiles are already running
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) whist[w][threadIdx.x] = 0;
     __syncthreads();
+    const u32 tile = s_tile;
+    if (tile >= tiles) break;
     const u32 base = tile * kSortTile + warp * (32 * kSortRounds);
     u64 key[kSortRounds];
     u32 off[kSortRounds];
@@ -158,7 +134,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortArgs a, 
       __syncwarp();
     }
     __syncthreads();
-    // exclusive scan across the warps of the tile, per digit
+    // per digit (thread = digit): exclusive scan across the warps of the tile, then the tiles before this one
     {
       u32 run = 0;
 #pragma unroll
@@ -167,6 +143,28 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortArgs a, 
         whist[w][threadIdx.x] = run;
         run += t;
       }
+      volatile u32* mine = st + (u64)tile * kRadix + threadIdx.x;
+      u32 ex = 0;
+      if (tile == 0) {
+        *mine = kFlagPre | run;
+      } else {
+        *mine = kFlagAgg | run;
+        const volatile u32* p = st + (u64)(tile - 1) * kRadix + threadIdx.x;
+        while (true) {
+          const u32 sv = *p;
+          if (sv & kFlagPre) {
+            ex += sv & kSortValMask;
+            break;
+          }
+          if (sv & kFlagAgg) {
+            ex += sv & kSortValMask;
+            p -= kRadix;      // tile 0 always publishes a prefix: the walk ends there at the latest
+          }
+        }
+        *mine = kFlagPre | (ex + run);
+      }
+      st_next[(u64)tile * kRadix + threadIdx.x] = 0u;   // clean look-back words for the next pass
+      excl_s[threadIdx.x] = ex;
     }
     __syncthreads();
 #pragma unroll
@@ -174,27 +172,27 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortArgs a, 
       const u32 i = base + r * 32 + lane;
       if (i < n) {
         const u32 d = (u32)(key[r] >> shift) & 0xFFu;
-        const u32 pos = gbase[d] + a.tile_hist[(u64)d * tiles + tile] + whist[warp][d] + off[r];
+        const u32 pos = gbase[d] + excl_s[d] + whist[warp][d] + off[r];
         kdst[pos] = key[r];
         vdst[pos] = vsrc[i];
       }
     }
-    __syncthreads();
   }
 }
 
 // enqueue every pass the host-side upper bound on the key width can need
 inline int radix_sort_enqueue(cudaStream_t st, const SortArgs& a, u32 max_bits, u32 max_n, int sms) {
-  const u32 passes = sort_passes(max_bits);
+  u32 passes = sort_passes(max_bits);
+  if (passes > kSortMaxPasses) passes = kSortMaxPasses;
   u32 tiles = (max_n + kSortTile - 1) / kSortTile;
   if (tiles == 0) tiles = 1;
   u32 grid = tiles < (u32)(sms * 8) ? tiles : (u32)(sms * 8);
-  int launches = 0;
+  cudaMemsetAsync(a.hdr, 0, sizeof(u32) * kSortHdrWords, st);
+  sort_prepare_kernel<<<grid, kSortThreads, 0, st>>>(a);
+  int launches = 1;
   for (u32 p = 0; p < passes; ++p) {
-    sort_hist_kernel<<<grid, kSortThreads, 0, st>>>(a, p);
-    sort_scan_kernel<<<kRadix, 1024, 0, st>>>(a, p);
-    sort_scatter_kernel<<<grid, kSortThreads, 0, st>>>(a, p);
-    launches += 3;
+    sort_onesweep_kernel<<<grid, kSortThreads, 0, st>>>(a, p);
+    ++launches;
   }
   return launches;
 }

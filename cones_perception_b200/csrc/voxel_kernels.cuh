@@ -196,39 +196,57 @@ struct VoxelOut {
   u32* v_off;        // [F+1]
 };
 
+// Eight lanes per voxel: the lanes fetch eight records of the segment at a time (index, then point: two dependent
+// loads per record, which one thread walking the segment alone would serialise), and every lane then adds the eight
+// points in record order — the fp32 sums stay sequential, as the reference's accumulator is.
 __global__ void voxel_mean_kernel(const Ctl* __restrict__ ctl, const u64* keys_a, const u64* keys_b,
                                   const u32* vals_a, const u32* vals_b, const u32* __restrict__ starts,
                                   const float4* __restrict__ pts, const u32* __restrict__ src,
                                   const u32* __restrict__ frame_n, u32 uniform_n,
                                   const u32* __restrict__ gcount, VoxelOut o) {
+  constexpr u32 G = 8;
   const u32 nv = ctl->n_vox, n = ctl->n_surv;
   const bool inb = sorted_in_b(ctl->vsort_bits);
   const u64* keys = inb ? keys_b : keys_a;
   const u32* vals = inb ? vals_b : vals_a;
   const u32 kb = ctl->voxel_key_bits;
-  for (u32 v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+  const u32 sub = threadIdx.x & (G - 1);
+  const u32 gmask = 0xFFu << (threadIdx.x & 24u);           // the eight lanes of this group
+  const u32 ngroups = gridDim.x * blockDim.x / G;
+  for (u32 v = (blockIdx.x * blockDim.x + threadIdx.x) / G; v < nv; v += ngroups) {
     const u32 b = starts[v];
     const u32 e = (v + 1 < nv) ? starts[v + 1] : n;
     const u32 f = (u32)(keys[b] >> kb);
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     u32 cnt = e - b;
-    for (u32 r = b; r < e; ++r) {
-      const u32 pi = vals[r];
-      const float4 p = pts[pi];
-      sx = __fadd_rn(sx, p.x);
-      sy = __fadd_rn(sy, p.y);
-      sz = __fadd_rn(sz, p.z);
-      si = __fadd_rn(si, p.w);
-      if (src[pi] == 0xFFFFFFFFu) {
+    for (u32 r0 = b; r0 < e; r0 += G) {
+      const u32 r = r0 + sub;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool pad = false;
+      if (r < e) {
+        const u32 pi = vals[r];
+        p = pts[pi];
+        pad = src[pi] == 0xFFFFFFFFu;
+      }
+      const u32 m = e - r0 < G ? e - r0 : G;
+      for (u32 k = 0; k < m; ++k) {
+        sx = __fadd_rn(sx, __shfl_sync(gmask, p.x, k, G));
+        sy = __fadd_rn(sy, __shfl_sync(gmask, p.y, k, G));
+        sz = __fadd_rn(sz, __shfl_sync(gmask, p.z, k, G));
+        si = __fadd_rn(si, __shfl_sync(gmask, p.w, k, G));
+      }
+      if (__ballot_sync(gmask, pad) & gmask) {
         // the record standing for the ground node's zero padding: adding zeros leaves the
         // sums unchanged, only the count grows by (N - G) - 1
         const u32 nf = uniform_n ? uniform_n : frame_n[f];
         cnt += (nf - gcount[f]) - 1u;
       }
     }
-    const float c = (float)cnt;
-    o.vox[v] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
-    o.vox_frame[v] = f;
+    if (sub == 0) {
+      const float c = (float)cnt;
+      o.vox[v] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+      o.vox_frame[v] = f;
+    }
   }
 }
 
