@@ -163,6 +163,10 @@ struct cp_handle {
   bool use_single = true;      // CONESGPU_SINGLE=0: a single frame takes the multi-launch path (A/B, tests)
   bool self_published = false; // the last run stored its results into the pinned mirrors itself (single_frame.cuh)
   bool graph_self_published = false;
+  // survivor / voxel counts of the last synchronised run: the general back half sizes its grids for about twice
+  // these instead of the handle's capacity (every kernel is a grid-stride loop over device-resident bounds, so
+  // any grid is correct; a grid sized for millions of slots costs microseconds per launch in empty CTAs)
+  u64 hint_c = 0, hint_v = 0;
   cp_ground_params rp_ground{};   // ground parameters of the last run (valid when rp_has_ground)
   bool rp_has_ground = false;
   bool tail_priority = false;  // CONESGPU_PRIO=1: greatest-priority stream, pass 1 demoted
@@ -505,6 +509,8 @@ Geom device_geom(const cp_handle* h) {
   return g;
 }
 
+u64 hinted(u64 cap, u64 hint) { return hint ? std::min<u64>(cap, 2 * hint + 8192) : cap; }
+
 u32 grid_for(u64 work, u32 block, int sms, int per_sm) {
   u64 b = (work + block - 1) / block;
   if (b == 0) b = 1;
@@ -759,21 +765,22 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   const u32 fgrid = (F + 255) / 256;
   voxel_setup_kernel<<<fgrid, 256, 0, h->stream>>>(F, vk, h->d_bbox, h->d_c_off, h->d_vf, h->d_ctl);
   voxel_bits_kernel<<<1, 1, 0, h->stream>>>(h->d_ctl, vk.frame_bits);
-  const u32 cgrid = grid_for(h->cap_c, 256, h->sms, 8);
+  const u64 work_c = hinted(h->cap_c, h->hint_c), work_v = hinted(h->cap_v, h->hint_v);
+  const u32 cgrid = grid_for(work_c, 256, h->sms, 8);
   voxel_key_kernel<<<cgrid, 256, 0, h->stream>>>(h->d_ctl, vk, h->d_pts, h->d_frame, h->d_c_off, h->d_vf,
                                                  h->d_keys_a, h->d_vals_a);
   h->launches += 3;
   {
     SortArgs sa = sort_args(h, false, &h->d_ctl->n_surv, &h->d_ctl->vsort_bits);
     h->launches += radix_sort_enqueue(h->stream, sa, voxel_bits_bound(d, vk, h->cap_c) + vk.frame_bits,
-                                      (u32)h->cap_c, h->sms);
+                                      (u32)work_c, h->sms);
   }
   if (h->taps) {
     tap_voxel_kernel<<<cgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b,
                                                    h->d_tap_keys, h->d_tap_order);
     h->launches++;
   }
-  const u32 hgrid = grid_for(h->cap_c, kHeadTile, h->sms, 4);
+  const u32 hgrid = grid_for(work_c, kHeadTile, h->sms, 4);
   {
     HeadArgs ha;
     ha.keys_a = h->d_keys_a;
@@ -790,12 +797,12 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
     ha.err_bit = kErrVoxels;
     segment_heads_kernel<<<hgrid, kHeadThreads, 0, h->stream>>>(ha);
   }
-  const u32 vgrid = grid_for(h->cap_v, 256, h->sms, 8);
+  const u32 vgrid = grid_for(work_v, 256, h->sms, 8);
   VoxelOut vo;
   vo.vox = h->d_vox;
   vo.vox_frame = h->d_vox_frame;
   vo.v_off = h->d_v_off;
-  voxel_mean_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b,
+  voxel_mean_kernel<<<grid_for(work_v * 8ull, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b,
                                                   h->d_vstart, h->d_pts, h->d_src, h->d_frame_n, h->hg.uniform_n,
                                                   h->d_gcount, vo);
   voxel_offsets_kernel<<<(F + 1 + 255) / 256, 256, 0, h->stream>>>(h->d_ctl, F, h->d_c_off, h->d_excl, h->d_v_off);
@@ -808,9 +815,9 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   h->launches += 2;
   {
     SortArgs sa = sort_args(h, false, &h->d_ctl->n_vox, &h->d_ctl->csort_bits);
-    h->launches += radix_sort_enqueue(h->stream, sa, csort_bits, (u32)h->cap_v, h->sms);
+    h->launches += radix_sort_enqueue(h->stream, sa, csort_bits, (u32)work_v, h->sms);
   }
-  const u32 hvgrid = grid_for(h->cap_v, kHeadTile, h->sms, 4);
+  const u32 hvgrid = grid_for(work_v, kHeadTile, h->sms, 4);
   {
     HeadArgs ha;
     ha.keys_a = h->d_keys_a;
@@ -828,17 +835,17 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
     segment_heads_kernel<<<hvgrid, kHeadThreads, 0, h->stream>>>(ha);
   }
   hash_setup_kernel<<<1, 1, 0, h->stream>>>(h->d_ctl, h->hash_cap);
-  hash_clear_kernel<<<grid_for(h->hash_cap, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_ctl, h->d_hkeys);
+  hash_clear_kernel<<<grid_for(std::min<u64>(h->hash_cap, 4 * work_v + 64), 256, h->sms, 8), 256, 0, h->stream>>>(h->d_ctl, h->d_hkeys);
   hash_insert_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_cstart, h->d_hkeys,
                                                    h->d_hvals);
-  cell_union_kernel<<<grid_for(h->cap_v * 32ull, 256, h->sms, 8), 256, 0, h->stream>>>(
+  cell_union_kernel<<<grid_for(work_v * 32ull, 256, h->sms, 8), 256, 0, h->stream>>>(
       h->d_ctl, ck, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b, h->d_cstart, h->d_hkeys, h->d_hvals,
       h->d_vox, h->d_parent, h->d_ctl);
   flatten_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_parent, h->d_label, h->d_keys_a, h->d_vals_a);
   h->launches += 6;
   {
     SortArgs sa = sort_args(h, false, &h->d_ctl->n_vox, &h->d_ctl->lsort_bits);
-    h->launches += radix_sort_enqueue(h->stream, sa, ceil_log2_host(h->cap_v) + 1, (u32)h->cap_v, h->sms);
+    h->launches += radix_sort_enqueue(h->stream, sa, ceil_log2_host(h->cap_v) + 1, (u32)work_v, h->sms);
   }
   {
     HeadArgs ha;
@@ -863,7 +870,7 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   h->launches += 3;
   {
     SortArgs sa = sort_args(h, true, &h->d_ctl->n_comp, &h->d_ctl->osort_bits);
-    h->launches += radix_sort_enqueue(h->stream, sa, osort_bits, (u32)h->cap_v, h->sms);
+    h->launches += radix_sort_enqueue(h->stream, sa, osort_bits, (u32)work_v, h->sms);
   }
   emit_clusters_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_ovals_a, h->d_ovals_b, h->d_keys_a, h->d_keys_b,
                                                      h->d_vals_a, h->d_vals_b, h->d_comp_start, h->d_vox,
@@ -2037,6 +2044,8 @@ cp_status cp_sync(cp_handle* h) try {
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   if (!h->ran) return CP_OK;
+  if (h->h_ctl->n_surv) h->hint_c = h->h_ctl->n_surv;   // (the per-frame back half leaves these at zero)
+  if (h->h_ctl->n_vox) h->hint_v = h->h_ctl->n_vox;
   // the shared-memory back half reports frames it could not hold: pick the next variant
   // (bigger shared-memory budget, then the general global-memory path) and redo the back half
   while (h->back_mode < 3 && h->h_ctl->fast_overflow != 0 && !(h->h_ctl->error & kErrSurvivors)) {

@@ -116,11 +116,17 @@ __global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(SortArgs a,
     const u32 base = tile * kSortTile + warp * (32 * kSortRounds);
     u64 key[kSortRounds];
     u32 off[kSortRounds];
+    // all eight loads first: the __syncwarp() of the ranking rounds would otherwise put one memory round trip
+    // between every two rounds
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+      const u32 i = base + r * 32 + lane;
+      key[r] = i < n ? ksrc[i] : 0ull;
+    }
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
       const u32 i = base + r * 32 + lane;
       const bool valid = i < n;
-      key[r] = valid ? ksrc[i] : 0ull;
       const u32 d = valid ? ((u32)(key[r] >> shift) & 0xFFu) : 0x100u;
       const u32 peers = __match_any_sync(kFull, d);
       const int leader = __ffs(peers) - 1;
@@ -149,17 +155,29 @@ __global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(SortArgs a,
         *mine = kFlagPre | run;
       } else {
         *mine = kFlagAgg | run;
-        const volatile u32* p = st + (u64)(tile - 1) * kRadix + threadIdx.x;
-        while (true) {
-          const u32 sv = *p;
-          if (sv & kFlagPre) {
-            ex += sv & kSortValMask;
-            break;
+        // look-back, eight predecessors per round trip (independent loads in flight together): counts of tiles
+        // that have only published their own aggregate are added and the walk goes on; the first inclusive
+        // prefix ends it (tile 0 always publishes one).  A word that is not written yet is read again.
+        const volatile u32* col = st + threadIdx.x;
+        i32 t = (i32)tile - 1;
+        bool done = false;
+        while (!done) {
+          u32 sv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) sv[q] = (t - q >= 0) ? col[(u64)(t - q) * kRadix] : kFlagPre;
+          int consumed = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (done || consumed != q) continue;      // stop at the first word that is not ready
+            if (sv[q] & kFlagPre) {
+              ex += sv[q] & kSortValMask;
+              done = true;
+            } else if (sv[q] & kFlagAgg) {
+              ex += sv[q] & kSortValMask;
+              ++consumed;
+            }
           }
-          if (sv & kFlagAgg) {
-            ex += sv & kSortValMask;
-            p -= kRadix;      // tile 0 always publishes a prefix: the walk ends there at the latest
-          }
+          t -= consumed;
         }
         *mine = kFlagPre | (ex + run);
       }
@@ -186,7 +204,7 @@ inline int radix_sort_enqueue(cudaStream_t st, const SortArgs& a, u32 max_bits, 
   if (passes > kSortMaxPasses) passes = kSortMaxPasses;
   u32 tiles = (max_n + kSortTile - 1) / kSortTile;
   if (tiles == 0) tiles = 1;
-  u32 grid = tiles < (u32)(sms * 8) ? tiles : (u32)(sms * 8);
+  u32 grid = tiles < (u32)(sms * 3) ? tiles : (u32)(sms * 3);   // persistent CTAs, tiles by ticket
   cudaMemsetAsync(a.hdr, 0, sizeof(u32) * kSortHdrWords, st);
   sort_prepare_kernel<<<grid, kSortThreads, 0, st>>>(a);
   int launches = 1;
