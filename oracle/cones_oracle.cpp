@@ -438,6 +438,22 @@ float orc_r2(const orc_detect_params* d) { return tolerance(*d).r2; }
 
 float orc_atan2f(float y, float x) { return oracle_atan2f(y, x); }
 
+// bench.py's cpu_baseline note: one pass of atan2f over n (y, x) pairs with the restated routine (use_libm = 0) or
+// with this box's libm (use_libm = 1); returns seconds.  The ground node calls it twice per point
+// (src/ground_removal.cpp:60,72), which is most of the CPU path's time.
+double orc_time_atan2f(const float* y, const float* x, uint32_t n, int use_libm, float* checksum) {
+  const auto t0 = std::chrono::steady_clock::now();
+  float acc = 0.0f;
+  if (use_libm) {
+    for (uint32_t i = 0; i < n; ++i) acc += atan2f(y[i], x[i]);
+  } else {
+    for (uint32_t i = 0; i < n; ++i) acc += oracle_atan2f(y[i], x[i]);
+  }
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (checksum) *checksum = acc;
+  return dt;
+}
+
 int orc_from_msg(const orc_view* v, orc_point* out) {
   if (!v || v->off_x < 0 || v->off_y < 0 || v->off_z < 0 || v->is_bigendian) return 2;
   const uint64_t n = static_cast<uint64_t>(v->width) * v->height;

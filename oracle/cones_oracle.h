@@ -76,6 +76,8 @@ int orc_from_msg(const orc_view* v, orc_point* out /* width*height */);
 
 /* the reference's atan2(float, float) = libm atan2f = fdlibm's single-precision routine (not correctly rounded) */
 float orc_atan2f(float y, float x);
+/* seconds for one pass of atan2f over n pairs: the restated routine (use_libm = 0) or this box's libm (1) */
+double orc_time_atan2f(const float* y, const float* x, uint32_t n, int use_libm, float* checksum);
 
 /* A.2  src/ground_removal.cpp:58-68 (pass 1) */
 int orc_sector_of(float x, float y);

@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
         L.orc_sector_of.argtypes = [C.c_float, C.c_float]
         L.orc_atan2f.argtypes = [C.c_float, C.c_float]
         L.orc_atan2f.restype = C.c_float
+        L.orc_time_atan2f.argtypes = [vp, vp, u32, C.c_int, vp]
+        L.orc_time_atan2f.restype = C.c_double
         L.orc_ground_minima.argtypes = [vp, u32, C.c_float, vp]
         L.orc_ground_minima.restype = None
         L.orc_ground_mask.argtypes = [vp, u32, vp, vp]
@@ -230,6 +232,14 @@ def detect(view: View, d, g=None, mode: int = CANONICAL, cap: int = 1 << 16):
     if rc:
         raise ValueError(f"orc_detect failed: {rc}")
     return out[:k.value].copy(), ctr, tm
+
+
+def time_atan2f(y: np.ndarray, x: np.ndarray, use_libm: bool) -> float:
+    """Seconds for one pass of atan2f over the pairs (restated routine or this box's libm)."""
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    chk = C.c_float()
+    return float(lib().orc_time_atan2f(y.ctypes.data, x.ctypes.data, len(y), 1 if use_libm else 0, C.byref(chk)))
 
 
 def extend(x: float, y: float, length: float):
