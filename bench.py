@@ -155,6 +155,24 @@ def cpu_frames_per_sec(frames: np.ndarray, cfg, threads: int, mode_faithful: boo
     return dt, {k: 1e3 * v / n for k, v in stage.items()}
 
 
+def host_description() -> dict:
+    """CPU model, core count and compiler of the CPU arm (stated in the result file)."""
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    try:
+        cc = subprocess.run(["g++", "--version"], capture_output=True, text=True).stdout.splitlines()[0]
+    except Exception:
+        cc = "g++ (version unknown)"
+    return {"cpu_model": model, "host_cores": os.cpu_count(), "compiler": cc,
+            "flags": "-O2 -std=c++17 -ffp-contract=off -fno-fast-math (oracle/Makefile)"}
+
+
 def compare_with_oracle(kept, ctr, k_off, clusters, tol=1e-5):
     """GPU results of a batch against the oracle's (pcl_faithful mode: PCL's own cluster order and summation
     order) for the first len(kept) frames: counters identical, the multiset of (size, min voxel index) per frame
@@ -204,7 +222,8 @@ def run_reference(args):
                    "frames_per_step": sample, "points_per_frame": n, "parallelism": f"{cores} host threads"},
         "cpu_baseline": {"value": pts, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} frames/step of the same scans, oracle pcl_faithful mode, "
-                                   f"g++ -O2, frame-parallel over {cores} threads"},
+                                   f"g++ -O2, frame-parallel over {cores} threads",
+                         "host": host_description()},
         "e2e": {"value": pts, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -884,6 +903,7 @@ def run_ours(args):
             lat.append(1e3 * (time.perf_counter() - t))
             assert st == 0
         assert k2.value == len(cl2) and np.array_equal(out2[:k2.value].view(np.uint32), cl2.view(np.uint32))
+        lat_launches = lat_gpu.last_launch_count()
         # the same from pageable memory (a ROS message's std::vector): staged through the library's pinned ring
         m2p = PointCloud2.from_xyzi(f2.copy())
         lat_page = []
@@ -928,7 +948,7 @@ def run_ours(args):
                    "frames_per_sec": passes * ns / dt, "ms_per_frame": 1e3 * dt / (passes * ns),
                    "stage_ms_per_frame": stages,
                    "host_cores_available": os.cpu_count(), "parity_of_timed_batch": parity,
-                   "atan2f": atan_note}
+                   "atan2f": atan_note, "host": host_description()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -936,7 +956,10 @@ def run_ours(args):
             "frames_per_sec": value / N,
             "p50_frame_latency_ms": float(np.percentile(lat, 50)), "p99_frame_latency_ms": float(np.percentile(lat, 99)),
             "p50_frame_latency_pageable_ms": float(np.percentile(lat_page, 50)),
+            "p99_frame_latency_pageable_ms": float(np.percentile(lat_page, 99)),
             "p50_frame_latency_device_resident_ms": float(np.percentile(lat_dev, 50)),
+            "p99_frame_latency_device_resident_ms": float(np.percentile(lat_dev, 99)),
+            "latency_launches_per_frame": lat_launches,
             "config": {"workload": "cfg3: batch of 64-beam 131072-pt scans (simulation params, ground removal on), "
                                    f"{F} frames per GPU, frame-sharded; when N>1 every rank publishes its cone list into rank 0's "
                                    "memory (CUDA-IPC peer stores over NVLink), NCCL for setup / barriers only",
