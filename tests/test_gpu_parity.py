@@ -699,3 +699,32 @@ def test_single_frame_in_one_launch_equals_the_multi_launch_path(case):
         if case not in ("overflow",) and len(cloud) <= 262144:
             assert out["1"][2] == 1, (case, len(cloud), "a single frame must be one launch")
             assert out["0"][2] > 1
+
+
+def test_results_do_not_depend_on_batching_or_frame_order():
+    """Size-independent properties of the path (frames are independent units): a frame's cones are the same whether
+    it runs alone (one-launch kernel), inside a batch, or inside the same batch in another order; running a batch
+    twice changes nothing (idempotence); within every frame the list is sorted by size descending, then min index."""
+    cfg = scans.config(3)
+    F = 48
+    frames = list(scans.generate(cfg, F, base_seed=300))
+    rng = np.random.default_rng(9)
+    perm = rng.permutation(F)
+    msgs = [PointCloud2.from_xyzi(f) for f in frames]
+    with api.ConesGpu(max_points=F * cfg.points_per_frame, max_frames=F) as h:
+        ctr, off, cl = h.detect_batch(msgs, cfg.detect, cfg.ground)
+        ctr2, off2, cl2 = h.detect_batch(msgs, cfg.detect, cfg.ground)
+        assert np.array_equal(off, off2) and cl.tobytes() == cl2.tobytes() and ctr.tobytes() == ctr2.tobytes()
+        pctr, poff, pcl = h.detect_batch([msgs[i] for i in perm], cfg.detect, cfg.ground)
+        for k, f in enumerate(perm):
+            assert pcl[poff[k]:poff[k + 1]].tobytes() == cl[off[f]:off[f + 1]].tobytes(), f
+            assert pctr[k].tobytes() == ctr[f].tobytes()
+        for f in range(F):
+            c = cl[off[f]:off[f + 1]]
+            key = list(zip((-c["size"].astype(np.int64)).tolist(), c["min_index"].tolist()))
+            assert key == sorted(key), f
+            assert (c["size"] >= cfg.detect.min_cluster_size).all() and (c["size"] <= cfg.detect.max_cluster_size).all()
+    with api.ConesGpu(max_points=cfg.points_per_frame, max_frames=1) as h1:
+        for f in (0, 17, F - 1):
+            one, c1 = h1.detect(msgs[f], cfg.detect, cfg.ground)
+            assert one.tobytes() == cl[off[f]:off[f + 1]].tobytes() and c1.tobytes() == ctr[f].tobytes()
