@@ -215,18 +215,21 @@ class ConesGpu:
             raise ConesGpuError(st, self.lib.cp_last_error(self._h).decode())
 
     # ---- node-equivalent calls --------------------------------------------------------
-    def ground_remove(self, msg: PointCloud2, g: GroundParams):
+    def ground_remove(self, msg: PointCloud2, g: GroundParams, copy: bool = True):
         """GroundRemover::cloud_handler body (src/ground_removal.cpp:54-79).
         Returns (cloud32 [N,8] float32 in PCL layout, n_kept, low17)."""
         view = make_view(msg, fake_missing_intensity=False)
         n = msg.n_points
-        out = np.empty((n, 8), dtype=np.float32)
+        if getattr(self, "_gr_n", None) != n:            # the output buffer is reused between calls (a node
+            self._gr_out = np.empty((n, 8), dtype=np.float32)   # publishes from one message object too)
+            self._gr_n = n
+        out = self._gr_out
         low = np.empty(17, dtype=np.float32)
         kept = C.c_uint32()
         cg = to_c_ground(g)
         self._ck(self.lib.cp_ground_remove(self._h, C.byref(view), C.byref(cg), out.ctypes.data, C.byref(kept),
                                            low.ctypes.data))
-        return out, kept.value, low
+        return out.copy() if copy else out, kept.value, low
 
     def detect(self, msg: PointCloud2, d: DetectParams, g: GroundParams | None = None, cap: int = 4096,
                fake_missing_intensity: bool = True):

@@ -38,6 +38,25 @@ inline void copy_streaming(uint8_t* dst, const uint8_t* src, size_t len) {
   _mm_sfence();
 }
 
+// `len` bytes (a multiple of 32) of value-initialised pcl::PointXYZI records: x = y = z = 0, data[3] = 1.0f,
+// intensity = 0, padding 0 — what GroundRemover's cloud->points.resize(N) appends (src/ground_removal.cpp:79).
+// Non-temporal stores when the destination allows it: 4 MB of padding should not evict a node's working set.
+inline void fill_pad_points(uint8_t* dst, size_t len) {
+  const __m128i lo = _mm_castps_si128(_mm_set_ps(1.0f, 0.0f, 0.0f, 0.0f)), hi = _mm_setzero_si128();
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) != 0) {
+    for (size_t i = 0; i + 32 <= len; i += 32) {
+      _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), lo);
+      _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i + 16), hi);
+    }
+    return;
+  }
+  for (size_t i = 0; i + 32 <= len; i += 32) {
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), lo);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), hi);
+  }
+  _mm_sfence();
+}
+
 class CopyPool {
  public:
   struct Batch {
@@ -68,7 +87,8 @@ class CopyPool {
     void copy_piece(uint32_t j) {
       const size_t off = (size_t)j * piece;
       const size_t len = off + piece <= total ? piece : total - off;
-      if (streaming) copy_streaming(dst + off, src + off, len);
+      if (!src) fill_pad_points(dst + off, len);          // src == NULL: a fill with PCL's padding point
+      else if (streaming) copy_streaming(dst + off, src + off, len);
       else std::memcpy(dst + off, src + off, len);
       group_left[j / pieces_per_group].fetch_sub(1, std::memory_order_release);
     }

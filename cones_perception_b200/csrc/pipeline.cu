@@ -2169,14 +2169,40 @@ cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_groun
   gk.pad_survives = 0;
   launch_keep_mask(h, geo, crop, gk, sgrid);
   launch_scan_gather<true>(h, geo, gk, n, h->d_out32);
-  pad_zero_points_kernel<<<grid_for(n, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_out32, h->d_ctl, n);
-  h->launches += 1;
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(out_xyzi32, h->d_out32, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
   static_assert(kNSect <= kSectStride, "h_frame_u32 holds at least kSectStride words");
   if (low17) CK(cudaMemcpyAsync(h->h_frame_u32, h->d_low_key, sizeof(u32) * kNSect, cudaMemcpyDeviceToHost, h->stream));
+  // Only the G survivors cross PCIe.  The N - G padding points the node appends (:79: value-initialised
+  // PointXYZI, 1.0f at offset 12) are the same 32 bytes over and over: the host writes them into the caller's buffer
+  // itself — in parallel, while the GPU is still working — instead of the GPU writing them to HBM and a 4 MB
+  // device-to-host copy carrying them back (that copy was most of the call).
+  uint8_t* out8 = static_cast<uint8_t*>(out_xyzi32);
+  const size_t out_bytes = (size_t)n * 32;
+  bool filled = false;
+  if (h->stage_threads > 1 && out_bytes >= kParallelStageMin) {
+    if (!h->copy_pool) {
+      try {
+        h->copy_pool.reset(new CopyPool(h->stage_threads - 1));
+      } catch (...) {
+        h->stage_threads = 1;
+      }
+    }
+    if (h->copy_pool) {
+      std::shared_ptr<CopyPool::Batch> b = h->copy_pool->start(out8, nullptr, out_bytes, kStagePiece, 1, true);
+      b->work();
+      for (u32 gi = 0; gi < b->n_groups; ++gi)
+        while (!b->group_done(gi)) std::this_thread::yield();
+      filled = true;
+    }
+  }
+  if (!filled) fill_pad_points(out8, out_bytes);
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
+  const u32 kept = h->h_ctl->n_surv;
+  if (kept) {
+    CK(cudaMemcpyAsync(out8, h->d_out32, (size_t)std::min(kept, n) * 32, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   if (n_kept) *n_kept = h->h_ctl->n_surv;
   if (low17)
     for (int s = 0; s < kNSect; ++s) low17[s] = ord2f(h->h_frame_u32[s]);

@@ -877,14 +877,4 @@ gather_survivors_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, Ground
   }
 }
 
-// node-equivalent zero padding, src/ground_removal.cpp:79 (value-initialised PointXYZI)
-__global__ void pad_zero_points_kernel(uint8_t* out32, const Ctl* ctl, u32 n) {
-  const u32 g0 = ctl->n_surv;
-  for (u32 i = g0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float4* dst = reinterpret_cast<float4*>(out32 + (u64)i * 32);
-    dst[0] = make_float4(0.f, 0.f, 0.f, 1.0f);
-    dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
 }  // namespace cp

@@ -37,6 +37,30 @@ int main(int argc, char** argv) {
           return 1;
         }
       }
+  // fill mode (src == NULL): PCL's value-initialised PointXYZI, 32 bytes per point, aligned and unaligned targets
+  for (size_t npts : {(size_t)1, (size_t)2047, (size_t)16384, (size_t)131072, (size_t)250001})
+    for (size_t mis : {(size_t)0, (size_t)4}) {
+      uint8_t* d = dst.data() + ((reinterpret_cast<uintptr_t>(dst.data()) + 63) & ~(uintptr_t)63) - reinterpret_cast<uintptr_t>(dst.data()) + mis;
+      const size_t total = npts * 32;
+      std::memset(d, 0xAB, total + 8);
+      auto b = pool.start(d, nullptr, total, 64 << 10, 1, true);
+      b->work();
+      for (uint32_t g = 0; g < b->n_groups; ++g)
+        while (!b->group_done(g)) std::this_thread::yield();
+      const float one = 1.0f;
+      for (size_t i = 0; i < npts; ++i) {
+        uint8_t expect[32] = {0};
+        std::memcpy(expect + 12, &one, 4);
+        if (std::memcmp(d + 32 * i, expect, 32) != 0) {
+          std::printf("FILL MISMATCH npts=%zu mis=%zu at %zu\n", npts, mis, i);
+          return 1;
+        }
+      }
+      if (d[total] != 0xAB) {
+        std::printf("FILL OVERRUN npts=%zu\n", npts);
+        return 1;
+      }
+    }
   std::printf("ok workers=%d\n", workers);
   return 0;
 }
