@@ -572,6 +572,35 @@ void launch_scan_gather(cp_handle* h, const Geom& g, const GroundK& gk, u32 cap,
   h->launches += 2;
   h->gathered = true;
 }
+// pass 2 + ordered compaction in one pass over the scan (mask_compact_kernel): the general back half's and the
+// ground node's front end when no keep mask exists yet
+template <bool OUT32>
+void launch_mask_compact(cp_handle* h, const Geom& g, const CropK& c, const GroundK& gk, u32 cap, uint8_t* out32) {
+  GatherOut go;
+  go.pts = h->d_pts;
+  go.src = h->d_src;
+  go.frame = h->d_frame;
+  go.cap = cap;
+  go.bbox_key = h->d_bbox;
+  go.out32 = out32;
+  if (gk.do_ground) {
+    ground_thresholds_kernel<<<(g.n_frames + 127) / 128, 128, 0, h->stream>>>(g.n_frames, h->d_low_key, h->d_thr_f);
+    h->launches++;
+  }
+  const u32* rm = h->rowmax_valid ? h->d_rowmax : nullptr;
+  const u32 grid = std::min<u32>(g.n_tiles ? g.n_tiles : 1u, (u32)h->sms * 4u);
+  u32* ticket = &h->d_ctl->ticket[0];
+#define CP_MC(M) mask_compact_kernel<M, OUT32><<<grid, kStreamThreads, 0, h->stream>>>(                         \
+      h->in_ptr, h->layout, g, c, gk, h->d_thr_f, rm, h->d_desc_a, ticket, go, h->d_c_off, h->d_gcount, h->d_ctl)
+  switch (h->layout.mode) {
+    case 0: CP_MC(0); break;
+    case 1: CP_MC(1); break;
+    default: CP_MC(2); break;
+  }
+#undef CP_MC
+  h->launches++;
+  h->gathered = true;
+}
 // single HBM pass: one 16-CTA cluster per frame, points stashed in shared memory (cluster_front.cuh)
 bool cluster_front_eligible(const cp_handle* h, const Geom& g, bool ground) {
   return h->use_cluster && ground && g.uniform_n && h->layout.mode == 0 &&
@@ -1124,8 +1153,12 @@ cp_status enqueue_back(cp_handle* h, bool retry) {
   else if (h->back_mode == 1) enqueue_back_fast<2048, 1024, 512>(h, rp);
   else if (h->back_mode == 2) enqueue_back_fast<4096, 2048, 512>(h, rp);
   else {
-    if (!h->masked) launch_keep_mask(h, device_geom(h), rp.crop, rp.gk, h->run_sgrid);
-    if (!h->gathered) launch_scan_gather<false>(h, device_geom(h), rp.gk, (u32)h->cap_c, nullptr);
+    if (!h->masked && !h->gathered) {
+      launch_mask_compact<false>(h, device_geom(h), rp.crop, rp.gk, (u32)h->cap_c, nullptr);
+    } else {   // a keep mask exists already (single-pass front ends, a retried one-launch frame)
+      if (!h->masked) launch_keep_mask(h, device_geom(h), rp.crop, rp.gk, h->run_sgrid);
+      if (!h->gathered) launch_scan_gather<false>(h, device_geom(h), rp.gk, (u32)h->cap_c, nullptr);
+    }
     enqueue_back_general(h, rp);
   }
   if (h->gather.open) enqueue_gather_publish(h, retry);
@@ -1262,7 +1295,8 @@ cp_status enqueue_pipeline(cp_handle* h, const cp_detect_params* d, const cp_gro
     // serves the general back half and — a few frames without ground removal, where every row is live and one
     // CTA per frame would be too few — small unskippable batches
     h->run_fused_mask = h->fuse_mask && h->back_mode < 3 && (ground != nullptr || g.n_frames >= (u32)h->sms || h->fuse_mask_always);
-    if (!h->run_fused_mask) launch_keep_mask(h, g, crop, gk, sgrid);
+    // (the general back half judges and compacts the points in one pass of its own: no keep mask for it)
+    if (!h->run_fused_mask && h->back_mode < 3) launch_keep_mask(h, g, crop, gk, sgrid);
   }
   h->gathered = false;
   h->ran_ground = ground != nullptr;
@@ -2167,8 +2201,7 @@ cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_groun
   gk.do_ground = 1;
   gk.want_count = 1;
   gk.pad_survives = 0;
-  launch_keep_mask(h, geo, crop, gk, sgrid);
-  launch_scan_gather<true>(h, geo, gk, n, h->d_out32);
+  launch_mask_compact<true>(h, geo, crop, gk, n, h->d_out32);
   CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
   static_assert(kNSect <= kSectStride, "h_frame_u32 holds at least kSectStride words");
   if (low17) CK(cudaMemcpyAsync(h->h_frame_u32, h->d_low_key, sizeof(u32) * kNSect, cudaMemcpyDeviceToHost, h->stream));
