@@ -197,13 +197,23 @@ def compare_with_oracle(kept, ctr, k_off, clusters, tol=1e-5):
             "identical; centroids within tolerance"}
 
 
+WORKLOAD = ("cfg3: batch of 64-beam 131072-pt scans (simulation params, ground removal on), "
+            "{F} frames per GPU, frame-sharded")
+
+
+def workload_config(F: int, n: int, world: int) -> dict:
+    """The part of `config` both arms share (the reference arm is timed on this arm's workload)."""
+    return {"workload": WORKLOAD.format(F=F), "frames_per_gpu": F, "points_per_frame": n, "global_frames": world * F}
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return  # only rank 0 measures the CPU path
     cfg = scans.config(3)
     cores = os.cpu_count() or 1
-    sample = args.cpu_step_frames
+    # a step = the same batch the CUDA arm times per GPU (512 frames: about 0.3 s on 16 host threads)
+    sample = args.cpu_step_frames if args.cpu_step_frames > 0 else args.frames_per_gpu
     frames = scans.generate(cfg, sample, base_seed=0)
     n = cfg.points_per_frame
     for _ in range(args.warmup):
@@ -218,8 +228,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_sec": pts / n,
-        "config": {"workload": "cfg3: 64-beam 131072-pt scans, simulation params, ground removal on",
-                   "frames_per_step": sample, "points_per_frame": n, "parallelism": f"{cores} host threads"},
+        "config": {**workload_config(args.frames_per_gpu, n, max(1, env_int("WORLD_SIZE", 1))),
+                   "frames_per_step": sample, "parallelism": f"{cores} host threads (rank 0 only)"},
         "cpu_baseline": {"value": pts, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} frames/step of the same scans, oracle pcl_faithful mode, "
                                    f"g++ -O2, frame-parallel over {cores} threads",
@@ -989,11 +999,10 @@ def run_ours(args):
                 "p50_detection_node_on_32B_cloud_ms": float(np.percentile(lat_det32, 50)),
                 "what": "cp_ground_remove (pinned cloud in, N x 32 B PCL cloud out) and cp_detect on that cloud "
                         "without ground removal, through the Python wrapper; the fused call above does both"},
-            "config": {"workload": "cfg3: batch of 64-beam 131072-pt scans (simulation params, ground removal on), "
-                                   f"{F} frames per GPU, frame-sharded; when N>1 every rank publishes its cone list into rank 0's "
-                                   "memory (CUDA-IPC peer stores over NVLink), NCCL for setup / barriers only",
-                       "frames_per_gpu": F, "points_per_frame": N, "global_frames": world * F,
-                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+            "config": {**workload_config(F, N, world),
+                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective; when N>1 every "
+                                      "rank publishes its cone list into rank 0's memory (CUDA-IPC peer stores over "
+                                      "NVLink), NCCL for setup / barriers only",
                        "result_gather": gather_mode, "result_gather_check": gather_check,
                        "batches_in_flight": len(lanes),
                        "cache": f"inputs larger than L2 ({F * N * 16 / 1e6:.0f} MB per rank vs 126 MB), no flush needed",
@@ -1028,7 +1037,8 @@ def main():
     ap.add_argument("--no-sub-records", dest="sub_records", action="store_false",
                     help="skip rowskip_off / azimuth_major / strong_4096 / cfg4 / cfg5")
     ap.add_argument("--strong-frames", type=int, default=4096, help="global batch of the strong-scaling sub-record")
-    ap.add_argument("--cpu-step-frames", type=int, default=128, help="frames per step of --impl reference")
+    ap.add_argument("--cpu-step-frames", type=int, default=0,
+                    help="frames per step of --impl reference (0 = --frames-per-gpu, the CUDA arm's batch)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
