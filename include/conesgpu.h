@@ -121,7 +121,9 @@ void cp_pinned_free(void* p);
 /* src/ground_removal.cpp:54-79.  out_xyzi32 receives width*height points in the PCL
  * PointXYZI layout toROSMsg emits (:86): x@0 y@4 z@8 1.0f@12 intensity@16, 32 B/point,
  * survivors first (input order) then zero points.  low17 (optional) receives the 17
- * per-sector minima. */
+ * per-sector minima.  Only the survivors are copied back from the device; the padding points
+ * (value-initialised PointXYZI: 1.0f at offset 12) are written into out_xyzi32 by the host while
+ * the GPU works, so the whole buffer is overwritten by the call. */
 cp_status cp_ground_remove(cp_handle* h, const cp_cloud_view* in, const cp_ground_params* g,
                            void* out_xyzi32, uint32_t* n_kept, float* low17);
 
@@ -170,7 +172,9 @@ cp_status cp_detect_batch(cp_handle* h, const cp_cloud_view* frames, uint32_t n_
                           cp_frame_counters* counters, uint32_t* cluster_offsets, cp_cluster* out,
                           uint64_t cap, uint64_t* n_total);
 
-/* Device time of the last cp_batch_run (CUDA events on the handle's stream), ms. */
+/* Device time of the last cp_batch_run (CUDA events on the handle's stream), ms.  A one-frame batch that took the
+ * single-launch path is not bracketed by events (each record costs about a microsecond of a ~50 us call):
+ * CP_E_STATE; cp_set_stage_timing(h, 1) routes such a frame through the multi-launch path, which is timed. */
 cp_status cp_last_run_ms(cp_handle* h, float* ms);
 /* Per-kernel device times of the two streaming passes (CUDA events on the handle's stream
  * around each launch).  Off by default; bench.py switches it on for the roofline pass. */
