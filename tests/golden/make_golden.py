@@ -202,7 +202,14 @@ def dam_net():
     g = tflite_model.load(raw)
     imgs = np.load(os.path.join(HERE, "cone_images.npz"))["real_images"]
     probs, logits = zip(*[D.forward(g, im) for im in imgs])
+    # the same network as the Keras SavedModel the reference ships beside the .tflite file
+    # (models/dam_net/variables/variables.data-00000-of-00001): the head of the tensor bundle holds, back to back,
+    # conv2d/kernel (3,3,1,16 HWIO) conv2d/bias conv2d_1/kernel (3,3,16,32) conv2d_1/bias, batch_normalization
+    # gamma / beta / moving_mean / moving_variance (32 each), dense/kernel (64,3), dense/bias — the optimizer
+    # slots that follow are not needed
+    kv = open("/root/reference/models/dam_net/variables/variables.data-00000-of-00001", "rb").read()[:20492]
     np.savez_compressed(os.path.join(HERE, "dam_net_model.npz"), tflite=np.frombuffer(raw, np.uint8),
+                        keras_variables=np.frombuffer(kv, np.uint8),
                         sha256=np.array(hashlib.sha256(raw).hexdigest()),
                         real_probs=np.stack(probs).astype(np.float32), real_logits=np.stack(logits).astype(np.float32))
     print("dam_net:", len(raw), "bytes,", len(imgs), "images")

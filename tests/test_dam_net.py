@@ -55,6 +55,39 @@ def test_reader_extracts_the_dam_net_graph():
             T.load(bad)
 
 
+def test_tflite_tensors_are_the_keras_models_variables():
+    """Second artifact of the reference: the Keras SavedModel beside the .tflite file.  The tensors the reader
+    extracts must be its variables byte for byte (kernels transposed HWIO -> OHWI, dense (64,3) -> (3,64)), and
+    the MUL / ADD constants must be its batch normalisation folded with epsilon 0.001 (keras_metadata.pb):
+    scale = gamma / sqrt(var + eps), shift = beta - mean * scale.  This pins which tensor plays which role."""
+    g = T.load(model_bytes())
+    kv = np.load(os.path.join(GOLD, "dam_net_model.npz"))["keras_variables"].tobytes()
+    f = np.frombuffer(kv, np.float32)
+    pos = 0
+
+    def take(*shape):
+        nonlocal pos
+        n = int(np.prod(shape))
+        a = f[pos:pos + n].reshape(shape)
+        pos += n
+        return a
+
+    k1, b1 = take(3, 3, 1, 16), take(16)
+    k2, b2 = take(3, 3, 16, 32), take(32)
+    gamma, beta, mean, var = take(32), take(32), take(32), take(32)
+    kd, bd = take(64, 3), take(3)
+    assert pos * 4 == len(kv)
+    conv1, conv2, mul, add, fc = g.ops[0], g.ops[2], g.ops[4], g.ops[5], g.ops[7]
+    tens = lambda i: g.tensors[i].data
+    assert np.array_equal(tens(conv1.inputs[1]), np.transpose(k1, (3, 0, 1, 2))) and np.array_equal(tens(conv1.inputs[2]), b1)
+    assert np.array_equal(tens(conv2.inputs[1]), np.transpose(k2, (3, 0, 1, 2))) and np.array_equal(tens(conv2.inputs[2]), b2)
+    assert np.array_equal(tens(fc.inputs[1]), kd.T) and np.array_equal(tens(fc.inputs[2]), bd)
+    scale = gamma / np.sqrt(var + np.float32(1e-3))
+    shift = beta - mean * scale
+    assert np.max(np.abs(tens(mul.inputs[1]) - scale)) <= 2e-7 and np.max(np.abs(tens(add.inputs[1]) - shift)) <= 2e-7
+    assert (var > 0).all()
+
+
 def test_forward_pass_regression_pin():
     g = T.load(model_bytes())
     z = np.load(os.path.join(GOLD, "dam_net_model.npz"))
