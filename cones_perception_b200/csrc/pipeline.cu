@@ -172,6 +172,7 @@ struct cp_handle {
   bool tail_priority = false;  // CONESGPU_PRIO=1: greatest-priority stream, pass 1 demoted
   int prio_low = 0;
   int k1_ctas_per_sm = 0;  // CONESGPU_K1_CTAS: separate grid cap for pass 1 (0 = stream_ctas_per_sm)
+  int frame_ctas_per_sm = 0;  // CONESGPU_FRAME_CTAS: grid cap of the per-frame kernel (0 = what fits)
   u32 run_sgrid = 0;  // grid of the streaming kernels of the current run
   int stream_ctas_per_sm = 8;  // grid cap of the streaming kernels (CONESGPU_STREAM_CTAS: leave room for a second handle)
   u64 *d_desc_a = nullptr, *d_desc_b = nullptr, *d_desc_c = nullptr, *d_desc_d = nullptr;
@@ -934,7 +935,7 @@ void launch_frame_kernel(cp_handle* h, const FrameArgs& fa) {
       per_sm = 1;
     per_sm_dev[dev] = per_sm;
   }
-  const int per_sm = per_sm_dev[dev];
+  const int per_sm = h->frame_ctas_per_sm ? std::min(h->frame_ctas_per_sm, per_sm_dev[dev]) : per_sm_dev[dev];
   const u32 grid = std::min<u32>(fa.n_frames, (u32)h->sms * (u32)per_sm);
   if (h->stage_timing && !h->capturing) cudaEventRecord(h->ev_k[4], h->stream);
   frame_backend_kernel<CMAX, VMAX, MODE, T><<<grid, T, smem, h->stream>>>(fa);
@@ -1682,6 +1683,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
   cudaDeviceGetStreamPriorityRange(&h->prio_low, &prio_hi);
   const char* k1_env = getenv("CONESGPU_K1_CTAS");
   if (k1_env && atoi(k1_env) >= 1 && atoi(k1_env) <= 256) h->k1_ctas_per_sm = atoi(k1_env);
+  const char* fc_env = getenv("CONESGPU_FRAME_CTAS");
+  if (fc_env && atoi(fc_env) >= 1 && atoi(fc_env) <= 16) h->frame_ctas_per_sm = atoi(fc_env);
   if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, h->tail_priority ? prio_hi : h->prio_low) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
