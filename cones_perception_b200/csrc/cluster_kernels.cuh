@@ -16,6 +16,7 @@
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"
+#include "voxel_kernels.cuh"
 
 namespace cp {
 
@@ -40,69 +41,57 @@ __device__ __forceinline__ u32 cell_coord(float c, const ClusterK& k, bool& outs
   return (u32)v;
 }
 
-__global__ void cluster_bits_kernel(Ctl* ctl, u32 csort_bits, u32 osort_bits) {
-  ctl->csort_bits = csort_bits;
-  ctl->lsort_bits = ceil_log2_u64(ctl->n_vox ? ctl->n_vox : 1);
-  if (ctl->lsort_bits == 0) ctl->lsort_bits = 1;
-  ctl->osort_bits = osort_bits;
-}
-
-__global__ void cell_key_kernel(const Ctl* __restrict__ ctl, ClusterK k, const float4* __restrict__ vox,
-                                const u32* __restrict__ vox_frame, u64* __restrict__ keys,
-                                u32* __restrict__ vals, u32* __restrict__ parent, Ctl* ctl_w) {
-  const u32 nv = ctl->n_vox;
-  bool outside = false;
-  for (u32 v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
-    const float4 p = vox[v];
-    const u64 cx = cell_coord(p.x, k, outside), cy = cell_coord(p.y, k, outside), cz = cell_coord(p.z, k, outside);
-    keys[v] = (((u64)vox_frame[v] * k.nx + cz) * k.nx + cy) * k.nx + cx;
-    vals[v] = v;
-    parent[v] = v;
-  }
-  if (outside) atomicOr(&ctl_w->error, kErrInternal);   // never silently: surfaces as an error at cp_sync
-}
-
-// live hash capacity = next pow2 >= 2 * n_cells; clear that prefix
-__global__ void hash_setup_kernel(Ctl* ctl, u32 hash_cap) {
-  u32 need = ctl->n_cells * 2u;
+// live hash capacity: next power of two >= 2 x the voxel count (an upper bound of the occupied cells, known before
+// the cells are); every thread can work it out for itself
+__device__ __forceinline__ u32 hash_capacity(u32 n_vox, u32 hash_cap) {
+  const u32 need = n_vox * 2u;
   u32 cap = 64;
   while (cap < need && cap < hash_cap) cap <<= 1;
-  if (cap < need) atomicOr(&ctl->error, kErrHash);
-  ctl->hash_mask = cap - 1;
+  return cap;
 }
-constexpr u64 kHashEmpty = 0xFFFFFFFFFFFFFFFFull;
-__global__ void hash_clear_kernel(const Ctl* __restrict__ ctl, u64* __restrict__ hkeys) {
-  const u32 cap = ctl->hash_mask + 1;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x)
-    hkeys[i] = kHashEmpty;
-}
-__device__ __forceinline__ u32 hash_u64(u64 k) {
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdull;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ull;
-  k ^= k >> 33;
-  return (u32)k;
-}
-__global__ void hash_insert_kernel(const Ctl* __restrict__ ctl, const u64* keys_a, const u64* keys_b,
-                                   const u32* __restrict__ cstart, u64* __restrict__ hkeys,
-                                   u32* __restrict__ hvals) {
-  const u32 nc = ctl->n_cells, mask = ctl->hash_mask;
-  const u64* keys = sorted_in_b(ctl->csort_bits) ? keys_b : keys_a;
-  for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
-    const u64 key = keys[cstart[c]];
-    u32 slot = hash_u64(key) & mask;
-    for (u32 probe = 0; probe <= mask; ++probe) {
-      const u64 old = atomicCAS((unsigned long long*)&hkeys[slot], (unsigned long long)kHashEmpty,
-                                (unsigned long long)key);
-      if (old == kHashEmpty || old == key) {
-        hvals[slot] = c;
-        break;
-      }
-      slot = (slot + 1) & mask;
-    }
+
+// one thread per voxel: key of its neighbour-grid cell (prefixed by the frame), union-find parent = itself.  The
+// kernel also settles what used to be kernels of their own: the key widths of the three cluster-stage sorts, the
+// live size of the cell hash and its clearing, and the digit histograms of the cell sort (sort_feed_*).
+__global__ void __launch_bounds__(256) cell_key_kernel(Ctl* ctl, ClusterK k, const float4* __restrict__ vox,
+                                                       const u32* __restrict__ vox_frame, u64* __restrict__ keys,
+                                                       u32* __restrict__ vals, u32* __restrict__ parent,
+                                                       u32 csort_bits, u32 osort_bits, u32 hash_cap,
+                                                       u64* __restrict__ hkeys, u32* sort_hdr, u32* sort_state) {
+  __shared__ SortFeedSmem feed;
+  const u32 nv = ctl->n_vox;
+  const u32 hcap = hash_capacity(nv, hash_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->csort_bits = csort_bits;
+    u32 lb = ceil_log2_u64(nv ? nv : 1);
+    ctl->lsort_bits = lb ? lb : 1u;
+    ctl->osort_bits = osort_bits;
+    ctl->hash_mask = hcap - 1;
+    if (hcap < nv * 2u) atomicOr(&ctl->error, kErrHash);
   }
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += stride) hkeys[i] = kHashEmpty;
+  const u32 passes = sort_feed_passes(csort_bits, nv);
+  sort_feed_begin(feed, passes);
+  bool outside = false;
+  for (u32 base = blockIdx.x * blockDim.x; base < nv; base += stride) {   // warp-uniform bounds (sort_feed_key)
+    const u32 v = base + threadIdx.x;
+    const bool valid = v < nv;
+    u64 key = 0;
+    if (valid) {
+      const float4 p = vox[v];
+      const u64 cx = cell_coord(p.x, k, outside), cy = cell_coord(p.y, k, outside), cz = cell_coord(p.z, k, outside);
+      key = (((u64)vox_frame[v] * k.nx + cz) * k.nx + cy) * k.nx + cx;
+      keys[v] = key;
+      vals[v] = v;
+      parent[v] = v;
+    }
+    sort_feed_key(feed, key, valid, passes);
+  }
+  if (outside) atomicOr(&ctl->error, kErrInternal);   // never silently: surfaces as an error at cp_sync
+  sort_feed_flush(feed, sort_hdr, sort_state, passes, nv);
 }
+
 __device__ __forceinline__ u32 hash_find(const u64* hkeys, const u32* hvals, u32 mask, u64 key) {
   u32 slot = hash_u64(key) & mask;
   for (u32 probe = 0; probe <= mask; ++probe) {
@@ -208,17 +197,24 @@ __global__ void __launch_bounds__(256) cell_union_kernel(const Ctl* __restrict__
           }
         }
       }
-      u32 found = __ballot_sync(kFull, nb_e > nb_b);
-      while (found) {
-        const int src = __ffs(found) - 1;
-        found &= found - 1;
+      // Which of the found neighbour cells are not in the cell's tree yet?  Every lane answers for its own
+      // neighbour at once (one find each, in parallel) instead of lane 0 answering for one neighbour after the
+      // other: in dense data most of the 62 are connected through some other chain of cells already, and the
+      // serial version paid two dependent find chains for each of them.
+      const bool have = nb_e > nb_b;
+      const u32 nb_first = have ? vals[nb_b] : 0u;
+      u32 rm = uf_find(parent, m);
+      bool apart = false;
+      if (have) apart = uf_find(parent, nb_first) != rm;
+      __syncwarp();
+      u32 pending = __ballot_sync(kFull, apart);
+      while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
         const u32 ob = __shfl_sync(kFull, nb_b, src), oe = __shfl_sync(kFull, nb_e, src);
-        // already one tree (through this or any other chain of cells): nothing to test
-        u32 same = 0;
-        if (lane == 0) same = uf_find(parent, m) == uf_find(parent, vals[ob]) ? 1u : 0u;
-        if (__shfl_sync(kFull, same, 0)) continue;
         const u32 nb = oe - ob;
         const unsigned long long total = (unsigned long long)(e - b) * nb;
+        bool linked = false;
         for (unsigned long long t0 = 0; t0 < total; t0 += 32ull) {
           const unsigned long long t = t0 + lane;
           bool hit = false;
@@ -235,10 +231,19 @@ __global__ void __launch_bounds__(256) cell_union_kernel(const Ctl* __restrict__
           const u32 hits = __ballot_sync(kFull, hit);
           if (hits) {
             if ((int)lane == __ffs(hits) - 1) uf_union(parent, vi, vj);
+            linked = true;
             break;
           }
         }
         __syncwarp();
+        // a new link may have brought other waiting neighbours into the tree: ask again, in parallel
+        if (linked && pending) {
+          rm = uf_find(parent, m);
+          apart = false;
+          if ((pending >> lane) & 1u) apart = uf_find(parent, nb_first) != rm;
+          __syncwarp();
+          pending = __ballot_sync(kFull, apart);
+        }
       }
     }
   }
@@ -252,55 +257,79 @@ __global__ void __launch_bounds__(256) cell_union_kernel(const Ctl* __restrict__
   }
 }
 
-// label = root (= min voxel index of the component); keys for the label sort
-__global__ void flatten_kernel(const Ctl* __restrict__ ctl, u32* __restrict__ parent, u32* __restrict__ label,
-                               u64* __restrict__ keys, u32* __restrict__ vals) {
+// label = root (= min voxel index of the component); keys and digit histograms of the label sort
+__global__ void __launch_bounds__(256) flatten_kernel(const Ctl* __restrict__ ctl, u32* __restrict__ parent,
+                                                      u32* __restrict__ label, u64* __restrict__ keys,
+                                                      u32* __restrict__ vals, u32* sort_hdr, u32* sort_state) {
+  __shared__ SortFeedSmem feed;
   const u32 nv = ctl->n_vox;
-  for (u32 v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
-    const u32 r = uf_find(parent, v);
-    label[v] = r;
-    keys[v] = r;
-    vals[v] = v;
+  const u32 passes = sort_feed_passes(ctl->lsort_bits, nv);
+  sort_feed_begin(feed, passes);
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 base = blockIdx.x * blockDim.x; base < nv; base += stride) {
+    const u32 v = base + threadIdx.x;
+    const bool valid = v < nv;
+    u64 key = 0;
+    if (valid) {
+      const u32 r = uf_find(parent, v);
+      label[v] = r;
+      key = r;
+      keys[v] = key;
+      vals[v] = v;
+    }
+    sort_feed_key(feed, key, valid, passes);
   }
+  sort_feed_flush(feed, sort_hdr, sort_state, passes, nv);
 }
 
 // one thread per component (segment of the label-sorted voxel list)
-__global__ void component_kernel(const Ctl* __restrict__ ctl, ClusterK k, const u64* keys_a, const u64* keys_b,
-                                 const u32* __restrict__ comp_start, const u32* __restrict__ vox_frame,
-                                 u32* __restrict__ ncomp_f, u32* __restrict__ kcount_f,
-                                 u64* __restrict__ okeys, u32* __restrict__ ovals, Ctl* ctl_w) {
+__global__ void __launch_bounds__(256) component_kernel(const Ctl* __restrict__ ctl, ClusterK k, const u64* keys_a,
+                                                        const u64* keys_b, const u32* __restrict__ comp_start,
+                                                        const u32* __restrict__ vox_frame,
+                                                        u32* __restrict__ ncomp_f, u32* __restrict__ kcount_f,
+                                                        u64* __restrict__ okeys, u32* __restrict__ ovals, Ctl* ctl_w,
+                                                        u32* sort_hdr, u32* sort_state) {
+  __shared__ SortFeedSmem feed;
   const u32 ncomp = ctl->n_comp, nv = ctl->n_vox;
   const u64* keys = sorted_in_b(ctl->lsort_bits) ? keys_b : keys_a;
-  for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < ncomp; c += gridDim.x * blockDim.x) {
-    const u32 b = comp_start[c];
-    const u32 e = (c + 1 < ncomp) ? comp_start[c + 1] : nv;
-    const u32 size = e - b;
-    const u32 root = (u32)keys[b];
-    const u32 f = vox_frame[root];
-    atomicAdd(&ncomp_f[f], 1u);
-    const bool kept = size >= k.min_size && size <= k.max_size;
-    u64 ok;
-    if (kept) {
-      atomicAdd(&kcount_f[f], 1u);
-      atomicAdd(&ctl_w->n_clusters, 1u);
-      ok = ((u64)f << k.size_bits) | (u64)(k.max_size - size);  // size descending inside the frame
-    } else {
-      ok = 1ull << (k.frame_bits + k.size_bits);  // dropped components sort behind every kept one
+  const u32 passes = sort_feed_passes(ctl->osort_bits, ncomp);
+  sort_feed_begin(feed, passes);
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 base = blockIdx.x * blockDim.x; base < ncomp; base += stride) {
+    const u32 c = base + threadIdx.x;
+    const bool valid = c < ncomp;
+    u64 ok = 0;
+    if (valid) {
+      const u32 b = comp_start[c];
+      const u32 e = (c + 1 < ncomp) ? comp_start[c + 1] : nv;
+      const u32 size = e - b;
+      const u32 root = (u32)keys[b];
+      const u32 f = vox_frame[root];
+      atomicAdd(&ncomp_f[f], 1u);
+      const bool kept = size >= k.min_size && size <= k.max_size;
+      if (kept) {
+        atomicAdd(&kcount_f[f], 1u);
+        atomicAdd(&ctl_w->n_clusters, 1u);
+        ok = ((u64)f << k.size_bits) | (u64)(k.max_size - size);  // size descending inside the frame
+      } else {
+        ok = 1ull << (k.frame_bits + k.size_bits);  // dropped components sort behind every kept one
+      }
+      okeys[c] = ok;
+      ovals[c] = c;
     }
-    okeys[c] = ok;
-    ovals[c] = c;
+    sort_feed_key(feed, ok, valid, passes);
   }
+  sort_feed_flush(feed, sort_hdr, sort_state, passes, ncomp);
 }
 
-// exclusive scan of the per-frame cluster counts (one CTA; F is small)
-__global__ void __launch_bounds__(1024) frame_scan_kernel(u32 n_frames, const u32* __restrict__ cnt,
-                                                          u32* __restrict__ off) {
-  __shared__ u32 wsum[32];
+// exclusive scan of the per-frame cluster counts by one CTA of 256 threads (F is small)
+__device__ __forceinline__ void frame_scan_block(u32 n_frames, const u32* __restrict__ cnt, u32* __restrict__ off) {
+  __shared__ u32 wsum[8];
   __shared__ u32 carry_s;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  for (u32 c0 = 0; c0 < n_frames; c0 += blockDim.x) {
+  for (u32 c0 = 0; c0 < n_frames; c0 += 256u) {
     const u32 i = c0 + threadIdx.x;
     const u32 v = i < n_frames ? cnt[i] : 0u;
     u32 inc = v;
@@ -311,25 +340,37 @@ __global__ void __launch_bounds__(1024) frame_scan_kernel(u32 n_frames, const u3
     }
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
-    if (warp == 0) {
-      const u32 w = wsum[lane];
-      u32 winc = w;
+    u32 woff = 0, total = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(kFull, winc, o);
-        if (lane >= o) winc += t;
-      }
-      wsum[lane] = winc - w;
+    for (int w = 0; w < 8; ++w) {
+      const u32 t = wsum[w];
+      if (w < warp) woff += t;
+      total += t;
     }
-    __syncthreads();
-    const u32 excl = carry_s + wsum[warp] + inc - v;
+    const u32 excl = carry_s + woff + inc - v;
     if (i < n_frames) off[i] = excl;
     __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+    if (threadIdx.x == 0) carry_s += total;
     __syncthreads();
   }
   if (threadIdx.x == 0) off[n_frames] = carry_s;
 }
+
+// what the last kernel of the general back half also settles (its CTA 0): cluster offsets per frame and the
+// per-frame counters in the cp_frame_counters layout
+struct FinishArgs {
+  u32 n_frames;
+  const u32* frame_n;
+  u32 uniform_n;
+  const u32* c_off;
+  const u32* ncomp_f;
+  const u32* kcount_f;
+  const VoxelFrame* vf;
+  const u32* gcount;
+  int counted_ground;
+  u32* k_off;   // [F+1]
+  u32* fc;      // [F][8]
+};
 
 struct ClusterRec {
   float x, y;
@@ -339,12 +380,26 @@ struct ClusterRec {
 // one warp per kept cluster, in canonical order (frame, size desc, min index asc): the lanes fetch 32 members at
 // a time and every lane adds them in ascending voxel index, so the fp32 sums stay sequential
 // (src/cone_detection.cpp:264-268) without one thread chasing index -> voxel loads one by one
-__global__ void emit_clusters_kernel(const Ctl* __restrict__ ctl, const u32* ovals_a, const u32* ovals_b,
+__global__ void __launch_bounds__(256) emit_clusters_kernel(const Ctl* __restrict__ ctl, const u32* ovals_a, const u32* ovals_b,
                                      const u64* lkeys_a, const u64* lkeys_b, const u32* lvals_a,
                                      const u32* lvals_b, const u32* __restrict__ comp_start,
                                      const float4* __restrict__ vox, const u32* __restrict__ vox_frame,
                                      const u32* __restrict__ v_off, ClusterRec* __restrict__ out, u32 out_cap,
-                                     Ctl* ctl_w) {
+                                     Ctl* ctl_w, FinishArgs fin) {
+  if (blockIdx.x == 0) {
+    frame_scan_block(fin.n_frames, fin.kcount_f, fin.k_off);
+    for (u32 f = threadIdx.x; f < fin.n_frames; f += blockDim.x) {
+      u32* o = fin.fc + (u64)f * 8;
+      o[0] = fin.uniform_n ? fin.uniform_n : fin.frame_n[f];
+      o[1] = fin.counted_ground ? fin.gcount[f] : o[0];   // G (= N without ground removal)
+      o[2] = fin.c_off[f + 1] - fin.c_off[f];
+      o[3] = v_off[f + 1] - v_off[f];
+      o[4] = fin.ncomp_f[f];
+      o[5] = fin.kcount_f[f];
+      o[6] = fin.vf[f].bits;
+      o[7] = fin.vf[f].passthrough;
+    }
+  }
   const u32 nk = ctl->n_clusters, ncomp = ctl->n_comp, nv = ctl->n_vox;
   const u32* ovals = sorted_in_b(ctl->osort_bits) ? ovals_b : ovals_a;
   const bool lb = sorted_in_b(ctl->lsort_bits);

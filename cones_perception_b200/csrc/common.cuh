@@ -92,39 +92,56 @@ __device__ __forceinline__ u64 desc_load(const u64* p) {
   return v;
 }
 
-// Called by ONE full warp of the CTA that owns `tile` (tiles are handed out by ticket, so
-// every predecessor is already running or done: the spin cannot deadlock).
-// Returns the exclusive prefix of `tile` and publishes its inclusive prefix.
-__device__ __forceinline__ u32 lookback_exclusive(u64* desc, u32 tile, u32 aggregate) {
+// The look-back in two steps, so that a kernel can publish a tile's aggregate as soon as it is known and come back
+// for the prefix later (by then the tiles before it have long published theirs and nothing spins):
+//   lookback_publish   one thread, as early as possible;
+//   lookback_resolve   ONE full warp of the CTA that owns `tile`: returns the exclusive prefix of `tile` and
+//                      publishes its inclusive prefix.
+// Tiles are handed out by ticket and a CTA publishes a tile's aggregate before it waits for anything, so every
+// predecessor a resolve spins on is published by a running CTA: the spin cannot deadlock.
+__device__ __forceinline__ void lookback_publish(u64* desc, u32 tile, u32 aggregate) {
+  desc_store(desc + tile, (tile == 0 ? kStInc : kStAgg) | aggregate);
+}
+__device__ __forceinline__ u32 lookback_resolve(u64* desc, u32 tile, u32 aggregate) {
   const int lane = lane_id();
-  if (tile == 0) {
-    if (lane == 0) desc_store(desc, kStInc | aggregate);
-    return 0;
-  }
-  if (lane == 0) desc_store(desc + tile, kStAgg | aggregate);
+  if (tile == 0) return 0;
   u32 excl = 0;
   i32 base = (i32)tile - 1;
-  while (true) {
-    const i32 t = base - lane;
-    u64 d = kStInc;  // lanes before tile 0 read as "inclusive 0"
-    if (t >= 0) {
-      do {
-        d = desc_load(desc + t);
-      } while ((d >> 62) == 0);
+  // kLookWin x 32 predecessors per round trip: with several hundred tiles in flight the nearest inclusive prefix
+  // can lie that many tiles back
+  constexpr int kLookWin = 4;
+  bool done = false;
+  while (!done) {
+    u64 d[kLookWin];
+#pragma unroll
+    for (int w = 0; w < kLookWin; ++w) {   // all loads in flight together
+      const i32 t = base - w * 32 - lane;
+      d[w] = t >= 0 ? desc_load(desc + t) : kStInc;  // lanes before tile 0 read as "inclusive 0"
     }
-    const u32 inc_mask = __ballot_sync(kFull, (d >> 62) == 2);
-    u32 v = (u32)d;
-    if (inc_mask) {
-      const int first = __ffs(inc_mask) - 1;  // nearest predecessor with an inclusive prefix
-      if (lane > first) v = 0;
+#pragma unroll
+    for (int w = 0; w < kLookWin; ++w) {
+      if (done) continue;                  // uniform across the warp
+      const i32 t = base - w * 32 - lane;
+      while ((d[w] >> 62) == 0) d[w] = desc_load(desc + t);   // not published yet
+      const u32 inc_mask = __ballot_sync(kFull, (d[w] >> 62) == 2);
+      u32 v = (u32)d[w];
+      if (inc_mask) {
+        const int first = __ffs(inc_mask) - 1;  // nearest predecessor with an inclusive prefix
+        if (lane > first) v = 0;
+        done = true;
+      }
       excl += __reduce_add_sync(kFull, v);
-      break;
     }
-    excl += __reduce_add_sync(kFull, v);
-    base -= 32;
+    base -= 32 * kLookWin;
   }
   if (lane == 0) desc_store(desc + tile, kStInc | (u64)(excl + aggregate));
   return excl;
+}
+// both steps at once (called by ONE full warp)
+__device__ __forceinline__ u32 lookback_exclusive(u64* desc, u32 tile, u32 aggregate) {
+  if (lane_id() == 0) lookback_publish(desc, tile, aggregate);
+  __syncwarp();
+  return lookback_resolve(desc, tile, aggregate);
 }
 
 // FLANN L2_Simple<float> restated: fp32, separate multiplies and adds, x then y then z.

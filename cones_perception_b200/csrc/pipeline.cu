@@ -173,6 +173,12 @@ struct cp_handle {
   int prio_low = 0;
   int k1_ctas_per_sm = 0;  // CONESGPU_K1_CTAS: separate grid cap for pass 1 (0 = stream_ctas_per_sm)
   int frame_ctas_per_sm = 0;  // CONESGPU_FRAME_CTAS: grid cap of the per-frame kernel (0 = what fits)
+  // one CTA per tile in the kernels that end a tile with a decoupled look-back (mask_compact, segment heads, tile
+  // scan, sort passes).  A persistent CTA cannot publish its next tile's aggregate before its current look-back
+  // has resolved, which chains every round of tiles to the slowest CTA of the previous one (ncu: 39 spins per
+  // look-back window, 1.7 TB/s); CTAs that retire after one tile leave the load / judge phases of the tiles behind
+  // them free of that wait.  CONESGPU_TILE_CTAS=0 restores the persistent grids.
+  bool tile_ctas = true;
   u32 run_sgrid = 0;  // grid of the streaming kernels of the current run
   int stream_ctas_per_sm = 8;  // grid cap of the streaming kernels (CONESGPU_STREAM_CTAS: leave room for a second handle)
   u64 *d_desc_a = nullptr, *d_desc_b = nullptr, *d_desc_c = nullptr, *d_desc_d = nullptr;
@@ -562,7 +568,7 @@ void launch_scan_gather(cp_handle* h, const Geom& g, const GroundK& gk, u32 cap,
   go.bbox_key = h->d_bbox;
   go.out32 = out32;
   const u32 stiles = (g.n_tiles + kScanTile - 1) / kScanTile;
-  tile_scan_kernel<<<stiles < (u32)h->sms * 4 ? stiles : (u32)h->sms * 4, kScanThreads, 0, h->stream>>>(
+  tile_scan_kernel<<<(h->tile_ctas || stiles < (u32)h->sms * 4) ? stiles : (u32)h->sms * 4, kScanThreads, 0, h->stream>>>(
       g, h->d_tile_count, h->d_tile_excl, h->d_c_off, h->d_desc_a, h->d_ctl, cap);
   const u32 ggrid = grid_for((u64)g.n_tiles * 32, 256, h->sms, 8);
   switch (h->layout.mode) {
@@ -589,6 +595,7 @@ void launch_mask_compact(cp_handle* h, const Geom& g, const CropK& c, const Grou
     h->launches++;
   }
   const u32* rm = h->rowmax_valid ? h->d_rowmax : nullptr;
+  // persistent CTAs: a tile's look-back is resolved while the CTA's next tile is already judged
   const u32 grid = std::min<u32>(g.n_tiles ? g.n_tiles : 1u, (u32)h->sms * 4u);
   u32* ticket = &h->d_ctl->ticket[0];
 #define CP_MC(M) mask_compact_kernel<M, OUT32><<<grid, kStreamThreads, 0, h->stream>>>(                         \
@@ -767,57 +774,49 @@ __global__ void back_reset_kernel(Ctl* ctl, u32 n_frames, u32* ncomp_f, u32* kco
   }
 }
 
-// per-frame counters of the general path in the cp_frame_counters layout
-__global__ void counters_kernel(u32 n_frames, const u32* frame_n, u32 uniform_n, const u32* c_off, const u32* v_off,
-                                const u32* ncomp_f, const u32* kcount_f, const VoxelFrame* vf, const u32* gcount,
-                                int counted_ground, u32* fc) {
-  const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n_frames) return;
-  u32* o = fc + (u64)f * 8;
-  o[0] = uniform_n ? uniform_n : frame_n[f];
-  o[1] = counted_ground ? gcount[f] : o[0];   // G (= N without ground removal)
-  o[2] = c_off[f + 1] - c_off[f];
-  o[3] = v_off[f + 1] - v_off[f];
-  o[4] = ncomp_f[f];
-  o[5] = kcount_f[f];
-  o[6] = vf[f].bits;
-  o[7] = vf[f].passthrough;
-}
-
-// general back half: global-memory kernels, any frame size
+// general back half: global-memory kernels, any frame size.  Every sort's keys are produced by a kernel of this
+// sequence, which also counts their digits (sort_feed_*), so a sort is its passes and nothing else; the one-thread
+// bookkeeping steps live inside their neighbours.
 void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   const cp_detect_params* d = &rp.d;
   const VoxelK& vk = rp.vk;
   const ClusterK& ck = rp.ck;
   const u32 csort_bits = rp.csort_bits, osort_bits = rp.osort_bits;
   const u32 F = h->hg.n_frames;
+  const bool persistent = !h->tile_ctas;
+  // the four sorts (voxel, cell, label, order) have a header each: one memset in front of all of them
+  cudaMemsetAsync(h->d_sort_hdr, 0, sizeof(u32) * kSortHdrWords * 4, h->stream);
+  auto sort_of = [&](int which, bool order_sort, const u32* d_n, const u32* d_bits) {
+    SortArgs a = sort_args(h, order_sort, d_n, d_bits);
+    a.hdr = h->d_sort_hdr + (size_t)which * kSortHdrWords;
+    return a;
+  };
   // ---- VoxelGrid
   const u32 fgrid = (F + 255) / 256;
   voxel_setup_kernel<<<fgrid, 256, 0, h->stream>>>(F, vk, h->d_bbox, h->d_c_off, h->d_vf, h->d_ctl);
-  voxel_bits_kernel<<<1, 1, 0, h->stream>>>(h->d_ctl, vk.frame_bits);
   const u64 work_c = hinted(h->cap_c, h->hint_c), work_v = hinted(h->cap_v, h->hint_v);
   const u32 cgrid = grid_for(work_c, 256, h->sms, 8);
-  voxel_key_kernel<<<cgrid, 256, 0, h->stream>>>(h->d_ctl, vk, h->d_pts, h->d_frame, h->d_c_off, h->d_vf,
-                                                 h->d_keys_a, h->d_vals_a);
-  h->launches += 3;
   {
-    SortArgs sa = sort_args(h, false, &h->d_ctl->n_surv, &h->d_ctl->vsort_bits);
-    h->launches += radix_sort_enqueue(h->stream, sa, voxel_bits_bound(d, vk, h->cap_c) + vk.frame_bits,
-                                      (u32)work_c, h->sms);
+    SortArgs sa = sort_of(0, false, &h->d_ctl->n_surv, &h->d_ctl->vsort_bits);
+    voxel_key_kernel<<<cgrid, 256, 0, h->stream>>>(h->d_ctl, vk, h->d_pts, h->d_frame, h->d_c_off, h->d_vf,
+                                                   h->d_keys_a, h->d_vals_a, sa.hdr, sa.state);
+    h->launches += 2;
+    h->launches += radix_sort_passes(h->stream, sa, voxel_bits_bound(d, vk, h->cap_c) + vk.frame_bits, (u32)work_c,
+                                     h->sms, persistent);
   }
   if (h->taps) {
     tap_voxel_kernel<<<cgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b,
                                                    h->d_tap_keys, h->d_tap_order);
     h->launches++;
   }
-  const u32 hgrid = grid_for(work_c, kHeadTile, h->sms, 4);
+  const u32 hgrid = grid_for(work_c, kHeadTile, h->sms, h->tile_ctas ? (1 << 20) : 4);
   {
-    HeadArgs ha;
+    HeadArgs ha = {};
     ha.keys_a = h->d_keys_a;
     ha.keys_b = h->d_keys_b;
     ha.d_bits = &h->d_ctl->vsort_bits;
     ha.d_n = &h->d_ctl->n_surv;
-    ha.excl = h->d_excl;
+    ha.excl = nullptr;
     ha.starts = h->d_vstart;
     ha.starts_cap = (u32)h->cap_v;
     ha.d_total = &h->d_ctl->n_vox;
@@ -832,24 +831,23 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   vo.vox = h->d_vox;
   vo.vox_frame = h->d_vox_frame;
   vo.v_off = h->d_v_off;
-  voxel_mean_kernel<<<grid_for(work_v * 8ull, 256, h->sms, 8), 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b,
-                                                  h->d_vstart, h->d_pts, h->d_src, h->d_frame_n, h->hg.uniform_n,
-                                                  h->d_gcount, vo);
-  voxel_offsets_kernel<<<(F + 1 + 255) / 256, 256, 0, h->stream>>>(h->d_ctl, F, h->d_c_off, h->d_excl, h->d_v_off);
-  h->launches += 3;
+  voxel_mean_kernel<<<grid_for(work_v * 8ull, 256, h->sms, 8), 256, 0, h->stream>>>(
+      h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b, h->d_vstart, h->d_pts, h->d_src, h->d_frame_n,
+      h->hg.uniform_n, h->d_gcount, rp.gk.pad_survives, F, vo);
+  h->launches += 2;
 
   // ---- Euclidean clustering
-  cluster_bits_kernel<<<1, 1, 0, h->stream>>>(h->d_ctl, csort_bits, osort_bits);
-  cell_key_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, ck, h->d_vox, h->d_vox_frame, h->d_keys_a, h->d_vals_a,
-                                                h->d_parent, h->d_ctl);
-  h->launches += 2;
   {
-    SortArgs sa = sort_args(h, false, &h->d_ctl->n_vox, &h->d_ctl->csort_bits);
-    h->launches += radix_sort_enqueue(h->stream, sa, csort_bits, (u32)work_v, h->sms);
+    SortArgs sa = sort_of(1, false, &h->d_ctl->n_vox, &h->d_ctl->csort_bits);
+    cell_key_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, ck, h->d_vox, h->d_vox_frame, h->d_keys_a, h->d_vals_a,
+                                                  h->d_parent, csort_bits, osort_bits, h->hash_cap, h->d_hkeys,
+                                                  sa.hdr, sa.state);
+    h->launches++;
+    h->launches += radix_sort_passes(h->stream, sa, csort_bits, (u32)work_v, h->sms, persistent);
   }
-  const u32 hvgrid = grid_for(work_v, kHeadTile, h->sms, 4);
+  const u32 hvgrid = grid_for(work_v, kHeadTile, h->sms, h->tile_ctas ? (1 << 20) : 4);
   {
-    HeadArgs ha;
+    HeadArgs ha = {};
     ha.keys_a = h->d_keys_a;
     ha.keys_b = h->d_keys_b;
     ha.d_bits = &h->d_ctl->csort_bits;
@@ -862,23 +860,24 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
     ha.ticket = &h->d_ctl->ticket[2];
     ha.error = &h->d_ctl->error;
     ha.err_bit = kErrInternal;
+    ha.hkeys = h->d_hkeys;       // cell key -> cell id, entered as the heads are found
+    ha.hvals = h->d_hvals;
+    ha.d_hash_mask = &h->d_ctl->hash_mask;
     segment_heads_kernel<<<hvgrid, kHeadThreads, 0, h->stream>>>(ha);
   }
-  hash_setup_kernel<<<1, 1, 0, h->stream>>>(h->d_ctl, h->hash_cap);
-  hash_clear_kernel<<<grid_for(std::min<u64>(h->hash_cap, 4 * work_v + 64), 256, h->sms, 8), 256, 0, h->stream>>>(h->d_ctl, h->d_hkeys);
-  hash_insert_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_cstart, h->d_hkeys,
-                                                   h->d_hvals);
   cell_union_kernel<<<grid_for(work_v * 32ull, 256, h->sms, 8), 256, 0, h->stream>>>(
       h->d_ctl, ck, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b, h->d_cstart, h->d_hkeys, h->d_hvals,
       h->d_vox, h->d_parent, h->d_ctl);
-  flatten_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_parent, h->d_label, h->d_keys_a, h->d_vals_a);
-  h->launches += 6;
+  h->launches += 2;
   {
-    SortArgs sa = sort_args(h, false, &h->d_ctl->n_vox, &h->d_ctl->lsort_bits);
-    h->launches += radix_sort_enqueue(h->stream, sa, ceil_log2_host(h->cap_v) + 1, (u32)work_v, h->sms);
+    SortArgs sa = sort_of(2, false, &h->d_ctl->n_vox, &h->d_ctl->lsort_bits);
+    flatten_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_parent, h->d_label, h->d_keys_a, h->d_vals_a, sa.hdr,
+                                                 sa.state);
+    h->launches++;
+    h->launches += radix_sort_passes(h->stream, sa, ceil_log2_host(h->cap_v) + 1, (u32)work_v, h->sms, persistent);
   }
   {
-    HeadArgs ha;
+    HeadArgs ha = {};
     ha.keys_a = h->d_keys_a;
     ha.keys_b = h->d_keys_b;
     ha.d_bits = &h->d_ctl->lsort_bits;
@@ -893,29 +892,36 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
     ha.err_bit = kErrInternal;
     segment_heads_kernel<<<hvgrid, kHeadThreads, 0, h->stream>>>(ha);
   }
-  component_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, ck, h->d_keys_a, h->d_keys_b, h->d_comp_start,
-                                                 h->d_vox_frame, h->d_ncomp_f, h->d_kcount_f, h->d_okeys_a,
-                                                 h->d_ovals_a, h->d_ctl);
-  frame_scan_kernel<<<1, 1024, 0, h->stream>>>(F, h->d_kcount_f, h->d_k_off);
-  h->launches += 3;
   {
-    SortArgs sa = sort_args(h, true, &h->d_ctl->n_comp, &h->d_ctl->osort_bits);
-    h->launches += radix_sort_enqueue(h->stream, sa, osort_bits, (u32)work_v, h->sms);
+    SortArgs sa = sort_of(3, true, &h->d_ctl->n_comp, &h->d_ctl->osort_bits);
+    component_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, ck, h->d_keys_a, h->d_keys_b, h->d_comp_start,
+                                                   h->d_vox_frame, h->d_ncomp_f, h->d_kcount_f, h->d_okeys_a,
+                                                   h->d_ovals_a, h->d_ctl, sa.hdr, sa.state);
+    h->launches += 2;
+    h->launches += radix_sort_passes(h->stream, sa, osort_bits, (u32)work_v, h->sms, persistent);
   }
+  FinishArgs fin;
+  fin.n_frames = F;
+  fin.frame_n = h->d_frame_n;
+  fin.uniform_n = h->hg.uniform_n;
+  fin.c_off = h->d_c_off;
+  fin.ncomp_f = h->d_ncomp_f;
+  fin.kcount_f = h->d_kcount_f;
+  fin.vf = h->d_vf;
+  fin.gcount = h->d_gcount;
+  fin.counted_ground = h->counted_ground ? 1 : 0;
+  fin.k_off = h->d_k_off;
+  fin.fc = h->d_fc;
   emit_clusters_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_ovals_a, h->d_ovals_b, h->d_keys_a, h->d_keys_b,
                                                      h->d_vals_a, h->d_vals_b, h->d_comp_start, h->d_vox,
                                                      h->d_vox_frame, h->d_v_off, h->d_clusters, (u32)h->cap_v,
-                                                     h->d_ctl);
+                                                     h->d_ctl, fin);
   h->launches++;
   if (h->taps) {
     local_labels_kernel<<<vgrid, 256, 0, h->stream>>>(h->d_ctl, h->d_label, h->d_vox_frame, h->d_v_off,
                                                       h->d_tap_labels);
     h->launches++;
   }
-  counters_kernel<<<(F + 255) / 256, 256, 0, h->stream>>>(F, h->d_frame_n, h->hg.uniform_n, h->d_c_off, h->d_v_off,
-                                                          h->d_ncomp_f, h->d_kcount_f, h->d_vf, h->d_gcount,
-                                                          h->counted_ground ? 1 : 0, h->d_fc);
-  h->launches++;
 }
 
 // fast back half: one CTA per frame in shared memory (frame_kernels.cuh)
@@ -1683,6 +1689,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
   cudaDeviceGetStreamPriorityRange(&h->prio_low, &prio_hi);
   const char* k1_env = getenv("CONESGPU_K1_CTAS");
   if (k1_env && atoi(k1_env) >= 1 && atoi(k1_env) <= 256) h->k1_ctas_per_sm = atoi(k1_env);
+  const char* tc_env = getenv("CONESGPU_TILE_CTAS");
+  if (tc_env) h->tile_ctas = tc_env[0] != '0';
   const char* fc_env = getenv("CONESGPU_FRAME_CTAS");
   if (fc_env && atoi(fc_env) >= 1 && atoi(fc_env) <= 16) h->frame_ctas_per_sm = atoi(fc_env);
   if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, h->tail_priority ? prio_hi : h->prio_low) != cudaSuccess ||
@@ -1762,8 +1770,8 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
   A(dalloc(h, &h->d_ovals_a, h->cap_v));
   A(dalloc(h, &h->d_ovals_b, h->cap_v));
   A(dalloc(h, &h->d_sort_state, (size_t)2 * kRadix * h->sort_tiles_cap));
-  A(dalloc(h, &h->d_sort_hdr, kSortHdrWords));
-  A(dalloc(h, &h->d_excl, h->cap_c));
+  A(dalloc(h, &h->d_sort_hdr, kSortHdrWords * 4));   // one header per sort of the general back half
+  // (d_excl — per-survivor voxel ranks — is gone: v_off comes from voxel_mean_kernel)
   A(dalloc(h, &h->d_vstart, h->cap_v));
   A(dalloc(h, &h->d_cstart, h->cap_v));
   A(dalloc(h, &h->d_comp_start, h->cap_v));
@@ -2608,7 +2616,7 @@ cp_status cp_debug_sort(cp_handle* h, uint64_t* keys, uint32_t* vals, uint32_t n
   z.osort_bits = bits;
   CK(cudaMemcpyAsync(h->d_ctl, &z, sizeof(z), cudaMemcpyHostToDevice, h->stream));
   SortArgs sa = sort_args(h, true, &h->d_ctl->n_comp, &h->d_ctl->osort_bits);
-  radix_sort_enqueue(h->stream, sa, bits, n, h->sms);
+  radix_sort_enqueue(h->stream, sa, bits, n, h->sms, !h->tile_ctas);
   const bool inb = sorted_in_b(bits);
   CK(cudaMemcpyAsync(keys, inb ? h->d_okeys_b : h->d_okeys_a, sizeof(u64) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(vals, inb ? h->d_ovals_b : h->d_ovals_a, sizeof(u32) * n, cudaMemcpyDeviceToHost, h->stream));

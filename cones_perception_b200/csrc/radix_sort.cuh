@@ -67,9 +67,46 @@ __global__ void __launch_bounds__(kSortThreads) sort_prepare_kernel(SortArgs a) 
   }
 }
 
+// ---- producer side of a sort whose keys come from one of this library's kernels -------------------------------
+// The kernel that writes keys_a also counts their digits for every live pass and clears the look-back words of
+// pass 0 — the work of sort_prepare_kernel without a launch (and a second read of the keys) of its own.  The host
+// clears the header before the producer (radix_sort_clear_hdr) and enqueues the passes behind it
+// (radix_sort_passes).  Every thread of the CTA must call begin / flush; sort_feed_key is called by whole warps
+// (`valid` = this lane has a key).
+struct SortFeedSmem {
+  u32 hist[kSortMaxPasses][kRadix];
+};
+__device__ __forceinline__ u32 sort_feed_passes(u32 bits, u32 n) {
+  if (bits == 0 || n == 0) return 0;
+  return sort_passes(bits) < kSortMaxPasses ? sort_passes(bits) : kSortMaxPasses;
+}
+__device__ __forceinline__ void sort_feed_begin(SortFeedSmem& s, u32 passes) {
+  for (u32 i = threadIdx.x; i < passes * kRadix; i += blockDim.x) (&s.hist[0][0])[i] = 0;
+  __syncthreads();
+}
+__device__ __forceinline__ void sort_feed_key(SortFeedSmem& s, u64 key, bool valid, u32 passes) {
+  for (u32 p = 0; p < passes; ++p) {
+    // neighbouring keys share their high digits: one shared-memory atomic per distinct digit of the warp
+    const u32 d = valid ? ((u32)(key >> (8 * p)) & 0xFFu) : 0x100u;
+    const u32 peers = __match_any_sync(kFull, d);
+    if (valid && lane_id() == __ffs(peers) - 1) atomicAdd(&s.hist[p][d], (u32)__popc(peers));
+  }
+}
+__device__ __forceinline__ void sort_feed_flush(SortFeedSmem& s, u32* hdr, u32* state, u32 passes, u32 n) {
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
+    const u32 c = (&s.hist[0][0])[i];
+    if (c) atomicAdd(&hdr[kSortMaxPasses + i], c);
+  }
+  if (passes) {
+    const u32 words = ((n + kSortTile - 1) / kSortTile) * kRadix;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) state[i] = 0u;
+  }
+}
+
 // one pass.  Warp w of a tile owns the contiguous items [w*256, (w+1)*256) and walks them 32 at a time, so ranks
 // follow input order (stable).
-__global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(SortArgs a, u32 pass) {
+__global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs a, u32 pass) {
   const u32 bits = *a.d_bits, n = *a.d_n;
   if (pass * 8 >= bits || n == 0) return;
   const u32 tiles = (n + kSortTile - 1) / kSortTile;
@@ -155,19 +192,20 @@ __global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(SortArgs a,
         *mine = kFlagPre | run;
       } else {
         *mine = kFlagAgg | run;
-        // look-back, eight predecessors per round trip (independent loads in flight together): counts of tiles
+        // look-back, kLook predecessors per round trip (independent loads in flight together): counts of tiles
         // that have only published their own aggregate are added and the walk goes on; the first inclusive
         // prefix ends it (tile 0 always publishes one).  A word that is not written yet is read again.
         const volatile u32* col = st + threadIdx.x;
         i32 t = (i32)tile - 1;
         bool done = false;
         while (!done) {
-          u32 sv[8];
+          constexpr int kLook = 16;
+          u32 sv[kLook];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) sv[q] = (t - q >= 0) ? col[(u64)(t - q) * kRadix] : kFlagPre;
+          for (int q = 0; q < kLook; ++q) sv[q] = (t - q >= 0) ? col[(u64)(t - q) * kRadix] : kFlagPre;
           int consumed = 0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < kLook; ++q) {
             if (done || consumed != q) continue;      // stop at the first word that is not ready
             if (sv[q] & kFlagPre) {
               ex += sv[q] & kSortValMask;
@@ -198,15 +236,30 @@ __global__ void __launch_bounds__(kSortThreads) sort_onesweep_kernel(SortArgs a,
   }
 }
 
-// enqueue every pass the host-side upper bound on the key width can need
-inline int radix_sort_enqueue(cudaStream_t st, const SortArgs& a, u32 max_bits, u32 max_n, int sms) {
+// the passes alone, behind a producer kernel that fed the histograms (sort_feed_*)
+inline int radix_sort_passes(cudaStream_t st, const SortArgs& a, u32 max_bits, u32 max_n, int sms, bool persistent) {
   u32 passes = sort_passes(max_bits);
   if (passes > kSortMaxPasses) passes = kSortMaxPasses;
   u32 tiles = (max_n + kSortTile - 1) / kSortTile;
   if (tiles == 0) tiles = 1;
-  u32 grid = tiles < (u32)(sms * 3) ? tiles : (u32)(sms * 3);   // persistent CTAs, tiles by ticket
+  const u32 grid = (!persistent || tiles < (u32)(sms * 3)) ? tiles : (u32)(sms * 3);
+  for (u32 p = 0; p < passes; ++p) sort_onesweep_kernel<<<grid, kSortThreads, 0, st>>>(a, p);
+  return (int)passes;
+}
+
+// enqueue every pass the host-side upper bound on the key width can need
+inline int radix_sort_enqueue(cudaStream_t st, const SortArgs& a, u32 max_bits, u32 max_n, int sms,
+                              bool persistent = false) {
+  u32 passes = sort_passes(max_bits);
+  if (passes > kSortMaxPasses) passes = kSortMaxPasses;
+  u32 tiles = (max_n + kSortTile - 1) / kSortTile;
+  if (tiles == 0) tiles = 1;
+  // tiles by ticket; one CTA per tile unless `persistent` (see cp_handle::tile_ctas in pipeline.cu): a CTA that
+  // goes on to another tile cannot publish that tile's counts before its current look-back has resolved
+  u32 grid = (!persistent || tiles < (u32)(sms * 3)) ? tiles : (u32)(sms * 3);
   cudaMemsetAsync(a.hdr, 0, sizeof(u32) * kSortHdrWords, st);
-  sort_prepare_kernel<<<grid, kSortThreads, 0, st>>>(a);
+  const u32 pgrid = tiles < (u32)(sms * 3) ? tiles : (u32)(sms * 3);   // histograms: grid-stride, no look-back
+  sort_prepare_kernel<<<pgrid, kSortThreads, 0, st>>>(a);
   int launches = 1;
   for (u32 p = 0; p < passes; ++p) {
     sort_onesweep_kernel<<<grid, kSortThreads, 0, st>>>(a, p);

@@ -883,136 +883,206 @@ gather_survivors_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, Ground
 // wrong one for the frames that reach the general back half (config 4: 10 % of 2.6 M points survive, no ground
 // removal, so no row can be skipped).  Here a CTA takes a 2048-point tile by ticket, judges its points once
 // (same keep_point as everywhere else), ranks the survivors with ballots, finds the tile's offset by decoupled
-// look-back and stores the survivors straight from the registers they were loaded into — in input order, so the
-// result is the one the three kernels produce.
+// look-back and stores the survivors in input order, so the result is the one the three kernels produce.
+//
+// The look-back is deferred by one tile.  Resolved on the spot, it spent half of the kernel spinning (ncu: 39
+// polls per look-back window; 209 us for 8 x 2.6 M points, 106 us with the prefixes replayed from a buffer): the
+// tiles just before a tile were ticketed microseconds earlier and are in the same phase, so their aggregates are
+// not there yet.  Now a tile publishes its aggregate, parks its survivors (compacted, tile order) in shared
+// memory, and its CTA goes on to load and judge its next tile; only then does it come back for the parked tile's
+// prefix — by then published long ago — and copies the survivors out with coalesced stores.  A tile with more
+// survivors than the stash holds (and every tile of the ground node, whose output keeps most points) resolves on
+// the spot and stores from the registers the points were loaded into, as before.
+constexpr u32 kStashCap = 1024;   // survivors a parked tile may hold (2 x 18 KB per CTA, 4 CTAs per SM)
+
 template <int MODE, bool OUT32>
 __global__ void __launch_bounds__(kStreamThreads, 4)
 mask_compact_kernel(const uint8_t* __restrict__ in, Layout L, Geom g, CropK c, GroundK gk,
                     const float* __restrict__ thr_f, const u32* __restrict__ rowmax, u64* desc, u32* ticket,
                     GatherOut o, u32* __restrict__ c_off, u32* __restrict__ gcount, Ctl* ctl) {
+  constexpr u32 kStash = OUT32 ? 1u : kStashCap;
+  __shared__ float4 st_pts[2][kStash];
+  __shared__ unsigned short st_idx[2][kStash];
   __shared__ u32 wtot[kStreamWarps];
   __shared__ u32 s_tile, s_excl;
   __shared__ u32 s_bb[8];
   __shared__ float s_thr[kSectStride];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const float kInf = __int_as_float(0x7f800000);
+  // the parked tile (uniform across the CTA)
+  bool parked = false;
+  u32 p_tile = 0, p_frame = 0, p_local0 = 0, p_total = 0, p_pad = 0, p_last = 0;
+  u32 cur = 0, my_rows = 0;
   while (true) {
     __syncthreads();
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     if (threadIdx.x < 8) s_bb[threadIdx.x] = threadIdx.x < 4 ? 0xFFFFFFFFu : 0u;
     __syncthreads();
     const u32 tile = s_tile;
-    if (tile >= g.n_tiles) break;
-    u32 frame, local0, count;
-    u64 first;
-    tile_lookup(g, tile, frame, local0, count, first);
-    if (threadIdx.x < kSectStride) s_thr[threadIdx.x] = gk.do_ground ? thr_f[frame * kSectStride + threadIdx.x] : -kInf;
-    __syncthreads();
-    const float thr_min = s_thr[31], thr_max = s_thr[30];
-    // rows lying entirely below every threshold are ground everywhere: never loaded (see keep_mask_kernel)
-    u32 rows = 0xFFu;
-    if (gk.do_ground && rowmax) {
-      const u32 key_min = f2ord(thr_min);
-      const u32 rm = lane < kStreamRows ? rowmax[(u64)tile * kTileWords + warp * kStreamRows + lane] : 0u;
-      rows = __ballot_sync(kFull, lane < kStreamRows && rm >= key_min) & 0xFFu;
-      const u32 live = (u32)__popc(rows);
-      if (lane == 0 && live) atomicAdd(&ctl->rows_loaded, live);
-    } else if (lane == 0) {
-      atomicAdd(&ctl->rows_loaded, (count + 31u) / 32u > (u32)warp * kStreamRows
-                                       ? min((count + 31u) / 32u - (u32)warp * kStreamRows, (u32)kStreamRows) : 0u);
-    }
-    float4 p[kStreamRows];
-    load_tile<MODE>(in, L, first + local0, count, -kInf, p, rows);
-    const u32 wbase = (u32)warp * (32 * kStreamRows);
-    u32 bal[kStreamRows], gkept = 0, wcount = 0;
-#pragma unroll
-    for (int r = 0; r < kStreamRows; ++r) {
-      const u32 i = wbase + r * 32 + lane;
-      bal[r] = __ballot_sync(kFull, keep_point(p[r], i < count, c, gk, s_thr, thr_min, thr_max, gkept));
-      wcount += __popc(bal[r]);
-    }
-    if (lane == 0) wtot[warp] = wcount;
-    if (gk.do_ground) {
-      gkept = __reduce_add_sync(kFull, gkept);
-      if (lane == 0 && gkept) atomicAdd(&gcount[frame], gkept);
-    }
-    __syncthreads();
-    u32 woff = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kStreamWarps; ++w) {
-      const u32 t = wtot[w];
-      if (w < warp) woff += t;
-      total += t;
-    }
-    const bool last_of_frame = (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]);
-    // one record stands for the N-G zero points appended by src/ground_removal.cpp:79 (see gather_survivors_kernel)
-    const u32 pad = (!OUT32 && gk.pad_survives && last_of_frame) ? 1u : 0u;
-    if (warp == 0) {
-      const u32 e = lookback_exclusive(desc, tile, total + pad);
-      if (lane == 0) s_excl = e;
-    }
-    __syncthreads();
-    const u32 excl = s_excl;
-    if (threadIdx.x == 0) {
-      const u32 run = excl + total + pad;
-      if (last_of_frame) c_off[frame + 1] = run;
-      if (tile + 1 == g.n_tiles) {
-        ctl->n_surv = run < o.cap ? run : o.cap;
-        if (run > o.cap) atomicOr(&ctl->error, kErrSurvivors);
+    const bool valid = tile < g.n_tiles;
+    bool park = false;
+    u32 frame = 0, local0 = 0, count = 0, total = 0, pad = 0;
+    bool last_of_frame = false;
+    if (valid) {
+      u64 first;
+      tile_lookup(g, tile, frame, local0, count, first);
+      if (threadIdx.x < kSectStride) s_thr[threadIdx.x] = gk.do_ground ? thr_f[frame * kSectStride + threadIdx.x] : -kInf;
+      __syncthreads();
+      const float thr_min = s_thr[31], thr_max = s_thr[30];
+      // rows lying entirely below every threshold are ground everywhere: never loaded (see keep_mask_kernel)
+      u32 rows = 0xFFu;
+      if (gk.do_ground && rowmax) {
+        const u32 key_min = f2ord(thr_min);
+        const u32 rm = lane < kStreamRows ? rowmax[(u64)tile * kTileWords + warp * kStreamRows + lane] : 0u;
+        rows = __ballot_sync(kFull, lane < kStreamRows && rm >= key_min) & 0xFFu;
+        my_rows += (u32)__popc(rows);
+      } else {
+        my_rows += (count + 31u) / 32u > (u32)warp * kStreamRows
+                       ? min((count + 31u) / 32u - (u32)warp * kStreamRows, (u32)kStreamRows) : 0u;
       }
-    }
-    u32 mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0, mxy = 0, mxz = 0;
-    u32 pos = excl + woff;
+      float4 p[kStreamRows];
+      load_tile<MODE>(in, L, first + local0, count, -kInf, p, rows);
+      const u32 wbase = (u32)warp * (32 * kStreamRows);
+      u32 bal[kStreamRows], gkept = 0, wcount = 0;
 #pragma unroll
-    for (int r = 0; r < kStreamRows; ++r) {
-      if ((bal[r] >> lane) & 1u) {
-        const u32 at = pos + __popc(bal[r] & lanemask_lt());
-        if (at < o.cap) {
-          if (OUT32) {
-            float4* dst = reinterpret_cast<float4*>(o.out32 + (u64)at * 32);
-            dst[0] = make_float4(p[r].x, p[r].y, p[r].z, 1.0f);
-            dst[1] = make_float4(p[r].w, 0.f, 0.f, 0.f);
-          } else {
-            o.pts[at] = p[r];
-            o.src[at] = local0 + wbase + r * 32 + lane;
-            o.frame[at] = frame;
-          }
-        }
-        const u32 kx = f2ord(p[r].x), ky = f2ord(p[r].y), kz = f2ord(p[r].z);
-        mnx = min(mnx, kx); mxx = max(mxx, kx);
-        mny = min(mny, ky); mxy = max(mxy, ky);
-        mnz = min(mnz, kz); mxz = max(mxz, kz);
+      for (int r = 0; r < kStreamRows; ++r) {
+        const u32 i = wbase + r * 32 + lane;
+        bal[r] = __ballot_sync(kFull, keep_point(p[r], i < count, c, gk, s_thr, thr_min, thr_max, gkept));
+        wcount += __popc(bal[r]);
       }
-      pos += __popc(bal[r]);
-    }
-    if (!OUT32) {
-      if (pad && threadIdx.x == 0) {
-        const u32 at = excl + total;
-        if (at < o.cap) {
-          o.pts[at] = make_float4(0.f, 0.f, 0.f, 0.f);
-          o.src[at] = 0xFFFFFFFFu;
-          o.frame[at] = frame;
-        }
-        const u32 kz = f2ord(0.0f);
-        mnx = min(mnx, kz); mxx = max(mxx, kz);
-        mny = min(mny, kz); mxy = max(mxy, kz);
-        mnz = min(mnz, kz); mxz = max(mxz, kz);
-      }
-      mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny);
-      mnz = __reduce_min_sync(kFull, mnz); mxx = __reduce_max_sync(kFull, mxx);
-      mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
-      if (lane == 0 && mxx >= mnx) {
-        atomicMin(&s_bb[0], mnx); atomicMin(&s_bb[1], mny); atomicMin(&s_bb[2], mnz);
-        atomicMax(&s_bb[4], mxx); atomicMax(&s_bb[5], mxy); atomicMax(&s_bb[6], mxz);
+      if (lane == 0) wtot[warp] = wcount;
+      if (gk.do_ground) {
+        gkept = __reduce_add_sync(kFull, gkept);
+        if (lane == 0 && gkept) atomicAdd(&gcount[frame], gkept);
       }
       __syncthreads();
-      if (threadIdx.x < 8 && (threadIdx.x & 3u) != 3u && s_bb[4] >= s_bb[0]) {
-        u32* bb = o.bbox_key + frame * 8;
-        if (threadIdx.x < 4) atomicMin(bb + threadIdx.x, s_bb[threadIdx.x]);
-        else atomicMax(bb + threadIdx.x, s_bb[threadIdx.x]);
+      u32 woff = 0;
+#pragma unroll
+      for (int w = 0; w < kStreamWarps; ++w) {
+        const u32 t = wtot[w];
+        if (w < warp) woff += t;
+        total += t;
+      }
+      last_of_frame = (local0 + count) == (g.uniform_n ? g.uniform_n : g.frame_n[frame]);
+      // one record stands for the N-G zero points appended by src/ground_removal.cpp:79 (see gather_survivors_kernel)
+      pad = (!OUT32 && gk.pad_survives && last_of_frame) ? 1u : 0u;
+      park = !OUT32 && total <= kStash;
+      u32 excl = 0;
+      if (park) {
+        if (threadIdx.x == 0) lookback_publish(desc, tile, total + pad);
+      } else {
+        if (warp == 0) {
+          const u32 e = lookback_exclusive(desc, tile, total + pad);
+          if (lane == 0) s_excl = e;
+        }
+        __syncthreads();
+        excl = s_excl;
+        if (threadIdx.x == 0) {
+          const u32 run = excl + total + pad;
+          if (last_of_frame) c_off[frame + 1] = run;
+          if (tile + 1 == g.n_tiles) {
+            ctl->n_surv = run < o.cap ? run : o.cap;
+            if (run > o.cap) atomicOr(&ctl->error, kErrSurvivors);
+          }
+        }
+      }
+      u32 mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mnz = 0xFFFFFFFFu, mxx = 0, mxy = 0, mxz = 0;
+      u32 pos = excl + woff;    // parked: position inside the tile's compacted list
+#pragma unroll
+      for (int r = 0; r < kStreamRows; ++r) {
+        if ((bal[r] >> lane) & 1u) {
+          const u32 at = pos + __popc(bal[r] & lanemask_lt());
+          if (park) {
+            st_pts[cur][at] = p[r];
+            st_idx[cur][at] = (unsigned short)(wbase + r * 32 + lane);
+          } else if (at < o.cap) {
+            if (OUT32) {
+              float4* dst = reinterpret_cast<float4*>(o.out32 + (u64)at * 32);
+              dst[0] = make_float4(p[r].x, p[r].y, p[r].z, 1.0f);
+              dst[1] = make_float4(p[r].w, 0.f, 0.f, 0.f);
+            } else {
+              o.pts[at] = p[r];
+              o.src[at] = local0 + wbase + r * 32 + lane;
+              o.frame[at] = frame;
+            }
+          }
+          const u32 kx = f2ord(p[r].x), ky = f2ord(p[r].y), kz = f2ord(p[r].z);
+          mnx = min(mnx, kx); mxx = max(mxx, kx);
+          mny = min(mny, ky); mxy = max(mxy, ky);
+          mnz = min(mnz, kz); mxz = max(mxz, kz);
+        }
+        pos += __popc(bal[r]);
+      }
+      if (!OUT32) {
+        if (pad && threadIdx.x == 0) {
+          if (!park) {
+            const u32 at = excl + total;
+            if (at < o.cap) {
+              o.pts[at] = make_float4(0.f, 0.f, 0.f, 0.f);
+              o.src[at] = 0xFFFFFFFFu;
+              o.frame[at] = frame;
+            }
+          }
+          const u32 kz = f2ord(0.0f);
+          mnx = min(mnx, kz); mxx = max(mxx, kz);
+          mny = min(mny, kz); mxy = max(mxy, kz);
+          mnz = min(mnz, kz); mxz = max(mxz, kz);
+        }
+        mnx = __reduce_min_sync(kFull, mnx); mny = __reduce_min_sync(kFull, mny);
+        mnz = __reduce_min_sync(kFull, mnz); mxx = __reduce_max_sync(kFull, mxx);
+        mxy = __reduce_max_sync(kFull, mxy); mxz = __reduce_max_sync(kFull, mxz);
+        if (lane == 0 && mxx >= mnx) {
+          atomicMin(&s_bb[0], mnx); atomicMin(&s_bb[1], mny); atomicMin(&s_bb[2], mnz);
+          atomicMax(&s_bb[4], mxx); atomicMax(&s_bb[5], mxy); atomicMax(&s_bb[6], mxz);
+        }
+        __syncthreads();
+        if (threadIdx.x < 8 && (threadIdx.x & 3u) != 3u && s_bb[4] >= s_bb[0]) {
+          u32* bb = o.bbox_key + frame * 8;
+          if (threadIdx.x < 4) atomicMin(bb + threadIdx.x, s_bb[threadIdx.x]);
+          else atomicMax(bb + threadIdx.x, s_bb[threadIdx.x]);
+        }
       }
     }
+    // ---- the tile parked one round ago: its prefix, then its survivors out of shared memory
+    if (!OUT32 && parked) {
+      if (warp == 0) {
+        const u32 e = lookback_resolve(desc, p_tile, p_total + p_pad);
+        if (lane == 0) s_excl = e;
+      }
+      __syncthreads();   // (also orders this round's stash writes; the parked tile sits in the other buffer)
+      const u32 excl = s_excl;
+      if (threadIdx.x == 0) {
+        const u32 run = excl + p_total + p_pad;
+        if (p_last) c_off[p_frame + 1] = run;
+        if (p_tile + 1 == g.n_tiles) {
+          ctl->n_surv = run < o.cap ? run : o.cap;
+          if (run > o.cap) atomicOr(&ctl->error, kErrSurvivors);
+        }
+        if (p_pad) {
+          const u32 at = excl + p_total;
+          if (at < o.cap) {
+            o.pts[at] = make_float4(0.f, 0.f, 0.f, 0.f);
+            o.src[at] = 0xFFFFFFFFu;
+            o.frame[at] = p_frame;
+          }
+        }
+      }
+      for (u32 i = threadIdx.x; i < p_total; i += kStreamThreads) {
+        const u32 at = excl + i;
+        if (at < o.cap) {
+          o.pts[at] = st_pts[cur ^ 1u][i];
+          o.src[at] = p_local0 + st_idx[cur ^ 1u][i];
+          o.frame[at] = p_frame;
+        }
+      }
+    }
+    parked = park;
+    p_tile = tile; p_frame = frame; p_local0 = local0; p_total = total; p_pad = pad; p_last = last_of_frame ? 1u : 0u;
+    cur ^= 1u;
+    if (!valid) break;
   }
+  my_rows = __shfl_sync(kFull, my_rows, 0);
+  if (lane == 0 && my_rows) atomicAdd(&ctl->rows_loaded, my_rows);
 }
 
 }  // namespace cp

@@ -69,34 +69,46 @@ __global__ void voxel_setup_kernel(u32 n_frames, VoxelK k, const u32* __restrict
   if (lane_id() == 0 && bits) atomicMax(&ctl->voxel_key_bits, bits);
 }
 
-// after voxel_setup: total sort width = key bits + frame bits
-__global__ void voxel_bits_kernel(Ctl* ctl, u32 frame_bits) {
-  ctl->vsort_bits = ctl->voxel_key_bits + frame_bits;
-}
-
-// one thread per survivor: PCL idx (uint32) prefixed by the frame id
-__global__ void voxel_key_kernel(const Ctl* __restrict__ ctl, VoxelK k, const float4* __restrict__ pts,
-                                 const u32* __restrict__ frame, const u32* __restrict__ c_off,
-                                 const VoxelFrame* __restrict__ vf, u64* __restrict__ keys,
-                                 u32* __restrict__ vals) {
+// one thread per survivor: PCL idx (uint32) prefixed by the frame id.  The kernel also fixes the total sort width
+// (key bits + frame bits, after voxel_setup) and feeds the voxel sort: digit histograms of every live pass and
+// clean look-back words for pass 0 (radix_sort.cuh, sort_feed_*).
+__global__ void __launch_bounds__(256) voxel_key_kernel(Ctl* ctl, VoxelK k, const float4* __restrict__ pts,
+                                                        const u32* __restrict__ frame,
+                                                        const u32* __restrict__ c_off,
+                                                        const VoxelFrame* __restrict__ vf, u64* __restrict__ keys,
+                                                        u32* __restrict__ vals, u32* sort_hdr, u32* sort_state) {
+  __shared__ SortFeedSmem feed;
   const u32 n = ctl->n_surv;
   const u32 kb = ctl->voxel_key_bits;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const u32 f = frame[i];
-    const VoxelFrame v = vf[f];
-    u32 idx;
-    if (v.passthrough) {
-      idx = i - c_off[f];
-    } else {
-      const float4 p = pts[i];
-      const i32 i0 = (i32)__fsub_rn(floorf(__fmul_rn(p.x, k.inv[0])), (float)v.min_b[0]);
-      const i32 i1 = (i32)__fsub_rn(floorf(__fmul_rn(p.y, k.inv[1])), (float)v.min_b[1]);
-      const i32 i2 = (i32)__fsub_rn(floorf(__fmul_rn(p.z, k.inv[2])), (float)v.min_b[2]);
-      idx = (u32)i0 + (u32)i1 * v.mul1 + (u32)i2 * v.mul2;
+  const u32 bits = kb + k.frame_bits;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->vsort_bits = bits;
+  const u32 passes = sort_feed_passes(bits, n);
+  sort_feed_begin(feed, passes);
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 base = blockIdx.x * blockDim.x; base < n; base += stride) {   // warp-uniform bounds (sort_feed_key)
+    const u32 i = base + threadIdx.x;
+    const bool valid = i < n;
+    u64 key = 0;
+    if (valid) {
+      const u32 f = frame[i];
+      const VoxelFrame v = vf[f];
+      u32 idx;
+      if (v.passthrough) {
+        idx = i - c_off[f];
+      } else {
+        const float4 p = pts[i];
+        const i32 i0 = (i32)__fsub_rn(floorf(__fmul_rn(p.x, k.inv[0])), (float)v.min_b[0]);
+        const i32 i1 = (i32)__fsub_rn(floorf(__fmul_rn(p.y, k.inv[1])), (float)v.min_b[1]);
+        const i32 i2 = (i32)__fsub_rn(floorf(__fmul_rn(p.z, k.inv[2])), (float)v.min_b[2]);
+        idx = (u32)i0 + (u32)i1 * v.mul1 + (u32)i2 * v.mul2;
+      }
+      key = ((u64)f << kb) | (u64)idx;
+      keys[i] = key;
+      vals[i] = i;
     }
-    keys[i] = ((u64)f << kb) | (u64)idx;
-    vals[i] = i;
+    sort_feed_key(feed, key, valid, passes);
   }
+  sort_feed_flush(feed, sort_hdr, sort_state, passes, n);
 }
 
 // ---- generic "segment heads" pass over a sorted key array ---------------------------------
@@ -119,7 +131,34 @@ struct HeadArgs {
   u32* ticket;
   u32* error;
   u32 err_bit;
+  // optional: every head also enters (its key -> its segment number) into an open-addressing hash table
+  // (the neighbour grid's cell -> cell id map, cluster_kernels.cuh); hash_mask is read from device memory
+  u64* hkeys;
+  u32* hvals;
+  const u32* d_hash_mask;
 };
+
+constexpr u64 kHashEmpty = 0xFFFFFFFFFFFFFFFFull;
+__device__ __forceinline__ u32 hash_u64(u64 k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (u32)k;
+}
+__device__ __forceinline__ void hash_insert_one(u64* hkeys, u32* hvals, u32 mask, u64 key, u32 val) {
+  u32 slot = hash_u64(key) & mask;
+  for (u32 probe = 0; probe <= mask; ++probe) {
+    const u64 old = atomicCAS((unsigned long long*)&hkeys[slot], (unsigned long long)kHashEmpty,
+                              (unsigned long long)key);
+    if (old == kHashEmpty || old == key) {
+      hvals[slot] = val;
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
 
 __global__ void __launch_bounds__(kHeadThreads) segment_heads_kernel(HeadArgs a) {
   const u32 n = *a.d_n;
@@ -136,11 +175,14 @@ __global__ void __launch_bounds__(kHeadThreads) segment_heads_kernel(HeadArgs a)
     const u32 i0 = tile * kHeadTile + threadIdx.x * kHeadItems;
     u64 prev = (i0 > 0 && i0 <= n) ? keys[i0 - 1] : 0ull;
     u32 flags = 0, cnt = 0;
+    u64 kk[kHeadItems];
 #pragma unroll
     for (int j = 0; j < kHeadItems; ++j) {
       const u32 i = i0 + j;
+      kk[j] = 0ull;
       if (i < n) {
         const u64 kcur = keys[i];
+        kk[j] = kcur;
         if (i == 0 || kcur != prev) {
           flags |= 1u << j;
           ++cnt;
@@ -179,7 +221,10 @@ __global__ void __launch_bounds__(kHeadThreads) segment_heads_kernel(HeadArgs a)
       if (i < n) {
         if (a.excl) a.excl[i] = run;
         if (flags & (1u << j)) {
-          if (run < a.starts_cap) a.starts[run] = i;
+          if (run < a.starts_cap) {
+            a.starts[run] = i;
+            if (a.hkeys) hash_insert_one(a.hkeys, a.hvals, *a.d_hash_mask, kk[j], run);
+          }
           ++run;
         }
       }
@@ -203,9 +248,11 @@ __global__ void voxel_mean_kernel(const Ctl* __restrict__ ctl, const u64* keys_a
                                   const u32* vals_a, const u32* vals_b, const u32* __restrict__ starts,
                                   const float4* __restrict__ pts, const u32* __restrict__ src,
                                   const u32* __restrict__ frame_n, u32 uniform_n,
-                                  const u32* __restrict__ gcount, VoxelOut o) {
+                                  const u32* __restrict__ gcount, int pad_possible, u32 n_frames, VoxelOut o) {
   constexpr u32 G = 8;
   const u32 nv = ctl->n_vox, n = ctl->n_surv;
+  if (nv == 0 && blockIdx.x == 0)
+    for (u32 f = threadIdx.x; f <= n_frames; f += blockDim.x) o.v_off[f] = 0;
   const bool inb = sorted_in_b(ctl->vsort_bits);
   const u64* keys = inb ? keys_b : keys_a;
   const u32* vals = inb ? vals_b : vals_a;
@@ -226,7 +273,7 @@ __global__ void voxel_mean_kernel(const Ctl* __restrict__ ctl, const u64* keys_a
       if (r < e) {
         const u32 pi = vals[r];
         p = pts[pi];
-        pad = src[pi] == 0xFFFFFFFFu;
+        pad = pad_possible && src[pi] == 0xFFFFFFFFu;   // (only read when the zero padding can survive the crop)
       }
       const u32 m = e - r0 < G ? e - r0 : G;
       for (u32 k = 0; k < m; ++k) {
@@ -246,22 +293,17 @@ __global__ void voxel_mean_kernel(const Ctl* __restrict__ ctl, const u64* keys_a
       const float c = (float)cnt;
       o.vox[v] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
       o.vox_frame[v] = f;
+      // v_off[f'] = voxels in frames < f': voxels are sorted by frame, so the first voxel of a frame (and the last
+      // voxel of all) settle the offsets of the frames between its predecessor's frame and its own
+      const u32 fprev = v ? (u32)(keys[b - 1] >> kb) : 0u;
+      if (v == 0)
+        for (u32 g = 0; g <= f; ++g) o.v_off[g] = 0;
+      else
+        for (u32 g = fprev + 1; g <= f; ++g) o.v_off[g] = v;
+      if (v == nv - 1)
+        for (u32 g = f + 1; g <= n_frames; ++g) o.v_off[g] = nv;
     }
   }
-}
-
-// v_off[f] = number of voxels in frames < f  (from the heads' exclusive counts)
-__global__ void voxel_offsets_kernel(const Ctl* __restrict__ ctl, u32 n_frames, const u32* __restrict__ c_off,
-                                     const u32* __restrict__ excl, u32* __restrict__ v_off) {
-  const u32 f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f > n_frames) return;
-  const u32 n = ctl->n_surv, nv = ctl->n_vox;
-  if (f == n_frames) {
-    v_off[f] = nv;
-    return;
-  }
-  const u32 c = c_off[f];
-  v_off[f] = (c < n) ? excl[c] : nv;
 }
 
 }  // namespace cp
