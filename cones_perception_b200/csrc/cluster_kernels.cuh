@@ -197,24 +197,17 @@ __global__ void __launch_bounds__(256) cell_union_kernel(const Ctl* __restrict__
           }
         }
       }
-      // Which of the found neighbour cells are not in the cell's tree yet?  Every lane answers for its own
-      // neighbour at once (one find each, in parallel) instead of lane 0 answering for one neighbour after the
-      // other: in dense data most of the 62 are connected through some other chain of cells already, and the
-      // serial version paid two dependent find chains for each of them.
-      const bool have = nb_e > nb_b;
-      const u32 nb_first = have ? vals[nb_b] : 0u;
-      u32 rm = uf_find(parent, m);
-      bool apart = false;
-      if (have) apart = uf_find(parent, nb_first) != rm;
-      __syncwarp();
-      u32 pending = __ballot_sync(kFull, apart);
-      while (pending) {
-        const int src = __ffs(pending) - 1;
-        pending &= pending - 1;
+      u32 found = __ballot_sync(kFull, nb_e > nb_b);
+      while (found) {
+        const int src = __ffs(found) - 1;
+        found &= found - 1;
         const u32 ob = __shfl_sync(kFull, nb_b, src), oe = __shfl_sync(kFull, nb_e, src);
+        // already one tree (through this or any other chain of cells): nothing to test
+        u32 same = 0;
+        if (lane == 0) same = uf_find(parent, m) == uf_find(parent, vals[ob]) ? 1u : 0u;
+        if (__shfl_sync(kFull, same, 0)) continue;
         const u32 nb = oe - ob;
         const unsigned long long total = (unsigned long long)(e - b) * nb;
-        bool linked = false;
         for (unsigned long long t0 = 0; t0 < total; t0 += 32ull) {
           const unsigned long long t = t0 + lane;
           bool hit = false;
@@ -231,19 +224,10 @@ __global__ void __launch_bounds__(256) cell_union_kernel(const Ctl* __restrict__
           const u32 hits = __ballot_sync(kFull, hit);
           if (hits) {
             if ((int)lane == __ffs(hits) - 1) uf_union(parent, vi, vj);
-            linked = true;
             break;
           }
         }
         __syncwarp();
-        // a new link may have brought other waiting neighbours into the tree: ask again, in parallel
-        if (linked && pending) {
-          rm = uf_find(parent, m);
-          apart = false;
-          if ((pending >> lane) & 1u) apart = uf_find(parent, nb_first) != rm;
-          __syncwarp();
-          pending = __ballot_sync(kFull, apart);
-        }
       }
     }
   }
@@ -417,18 +401,29 @@ __global__ void __launch_bounds__(256) emit_clusters_kernel(const Ctl* __restric
     const u32 e = (c + 1 < ncomp) ? comp_start[c + 1] : nv;
     const u32 root = (u32)lkeys[b];
     float x = 0.0f, y = 0.0f;
-    for (u32 j0 = b; j0 < e; j0 += 32u) {
-      const u32 j = j0 + lane;
-      float px = 0.f, py = 0.f;
-      if (j < e) {
-        const float4 p = vox[lvals[j]];
-        px = p.x;
-        py = p.y;
+    // four rounds of members (128) are fetched before the first is added: a cone is one or two rounds, so the
+    // index -> voxel load chain is paid once per cluster, not once per 32 members
+    for (u32 j0 = b; j0 < e; j0 += 128u) {
+      float px[4], py[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const u32 j = j0 + u * 32u + lane;
+        px[u] = 0.f;
+        py[u] = 0.f;
+        if (j < e) {
+          const float4 p = vox[lvals[j]];
+          px[u] = p.x;
+          py[u] = p.y;
+        }
       }
-      const u32 m = e - j0 < 32u ? e - j0 : 32u;
-      for (u32 q = 0; q < m; ++q) {
-        x = __fadd_rn(x, __shfl_sync(kFull, px, q));
-        y = __fadd_rn(y, __shfl_sync(kFull, py, q));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const u32 r0 = j0 + u * 32u;
+        const u32 m = r0 >= e ? 0u : (e - r0 < 32u ? e - r0 : 32u);
+        for (u32 q = 0; q < m; ++q) {
+          x = __fadd_rn(x, __shfl_sync(kFull, px[u], q));
+          y = __fadd_rn(y, __shfl_sync(kFull, py[u], q));
+        }
       }
     }
     if (lane == 0) {

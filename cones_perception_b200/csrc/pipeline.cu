@@ -809,7 +809,7 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
                                                    h->d_tap_keys, h->d_tap_order);
     h->launches++;
   }
-  const u32 hgrid = grid_for(work_c, kHeadTile, h->sms, h->tile_ctas ? (1 << 20) : 4);
+  const u32 hgrid = grid_for(work_c, kHeadTile, h->sms, 4);   // persistent: look-backs are resolved one tile later
   {
     HeadArgs ha = {};
     ha.keys_a = h->d_keys_a;
@@ -831,7 +831,7 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
   vo.vox = h->d_vox;
   vo.vox_frame = h->d_vox_frame;
   vo.v_off = h->d_v_off;
-  voxel_mean_kernel<<<grid_for(work_v * 8ull, 256, h->sms, 8), 256, 0, h->stream>>>(
+  voxel_mean_kernel<<<grid_for(work_v * 32ull, 256, h->sms, 8), 256, 0, h->stream>>>(
       h->d_ctl, h->d_keys_a, h->d_keys_b, h->d_vals_a, h->d_vals_b, h->d_vstart, h->d_pts, h->d_src, h->d_frame_n,
       h->hg.uniform_n, h->d_gcount, rp.gk.pad_survives, F, vo);
   h->launches += 2;
@@ -845,7 +845,7 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
     h->launches++;
     h->launches += radix_sort_passes(h->stream, sa, csort_bits, (u32)work_v, h->sms, persistent);
   }
-  const u32 hvgrid = grid_for(work_v, kHeadTile, h->sms, h->tile_ctas ? (1 << 20) : 4);
+  const u32 hvgrid = grid_for(work_v, kHeadTile, h->sms, 4);
   {
     HeadArgs ha = {};
     ha.keys_a = h->d_keys_a;

@@ -160,6 +160,9 @@ __device__ __forceinline__ void hash_insert_one(u64* hkeys, u32* hvals, u32 mask
   }
 }
 
+// The look-back of a tile is resolved one tile later (see mask_compact_kernel): a tile publishes its head count,
+// its CTA counts the heads of its next tile, and only then comes back for the prefix — which the tiles before it
+// have published by then — and writes the parked tile's segment starts.  A parked tile is a few registers.
 __global__ void __launch_bounds__(kHeadThreads) segment_heads_kernel(HeadArgs a) {
   const u32 n = *a.d_n;
   const u64* keys = sorted_in_b(*a.d_bits) ? a.keys_b : a.keys_a;
@@ -167,69 +170,78 @@ __global__ void __launch_bounds__(kHeadThreads) segment_heads_kernel(HeadArgs a)
   __shared__ u32 wsum[kHeadThreads / 32];
   __shared__ u32 s_tile, s_excl;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
+  bool parked = false;
+  u32 p_tile = 0, p_total = 0, p_i0 = 0, p_flags = 0, p_before = 0;   // p_before: heads of the tile before this thread
   while (true) {
+    __syncthreads();
     if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
     __syncthreads();
     const u32 tile = s_tile;
-    if (tile >= tiles) break;
-    const u32 i0 = tile * kHeadTile + threadIdx.x * kHeadItems;
-    u64 prev = (i0 > 0 && i0 <= n) ? keys[i0 - 1] : 0ull;
-    u32 flags = 0, cnt = 0;
-    u64 kk[kHeadItems];
+    const bool valid = tile < tiles;
+    u32 i0 = 0, flags = 0, before = 0, total = 0;
+    if (valid) {
+      i0 = tile * kHeadTile + threadIdx.x * kHeadItems;
+      u64 prev = (i0 > 0 && i0 <= n) ? keys[i0 - 1] : 0ull;
+      u32 cnt = 0;
 #pragma unroll
-    for (int j = 0; j < kHeadItems; ++j) {
-      const u32 i = i0 + j;
-      kk[j] = 0ull;
-      if (i < n) {
-        const u64 kcur = keys[i];
-        kk[j] = kcur;
-        if (i == 0 || kcur != prev) {
-          flags |= 1u << j;
-          ++cnt;
-        }
-        prev = kcur;
-      }
-    }
-    u32 inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 t = __shfl_up_sync(kFull, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    u32 woff = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kHeadThreads / 32; ++w) {
-      const u32 t = wsum[w];
-      if (w < warp) woff += t;
-      total += t;
-    }
-    if (warp == 0) {
-      const u32 e = lookback_exclusive(a.desc, tile, total);
-      if (lane == 0) s_excl = e;
-    }
-    __syncthreads();
-    u32 run = s_excl + woff + inc - cnt;
-    if (threadIdx.x == 0 && tile == tiles - 1) {
-      *a.d_total = min(s_excl + total, a.starts_cap);
-      if (s_excl + total > a.starts_cap) atomicOr(a.error, a.err_bit);
-    }
-#pragma unroll
-    for (int j = 0; j < kHeadItems; ++j) {
-      const u32 i = i0 + j;
-      if (i < n) {
-        if (a.excl) a.excl[i] = run;
-        if (flags & (1u << j)) {
-          if (run < a.starts_cap) {
-            a.starts[run] = i;
-            if (a.hkeys) hash_insert_one(a.hkeys, a.hvals, *a.d_hash_mask, kk[j], run);
+      for (int j = 0; j < kHeadItems; ++j) {
+        const u32 i = i0 + j;
+        if (i < n) {
+          const u64 kcur = keys[i];
+          if (i == 0 || kcur != prev) {
+            flags |= 1u << j;
+            ++cnt;
           }
-          ++run;
+          prev = kcur;
+        }
+      }
+      u32 inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();
+      u32 woff = 0;
+#pragma unroll
+      for (int w = 0; w < kHeadThreads / 32; ++w) {
+        const u32 t = wsum[w];
+        if (w < warp) woff += t;
+        total += t;
+      }
+      before = woff + inc - cnt;
+      if (threadIdx.x == 0) lookback_publish(a.desc, tile, total);
+    }
+    if (parked) {
+      if (warp == 0) {
+        const u32 e = lookback_resolve(a.desc, p_tile, p_total);
+        if (lane == 0) s_excl = e;
+      }
+      __syncthreads();
+      u32 run = s_excl + p_before;
+      if (threadIdx.x == 0 && p_tile == tiles - 1) {
+        *a.d_total = min(s_excl + p_total, a.starts_cap);
+        if (s_excl + p_total > a.starts_cap) atomicOr(a.error, a.err_bit);
+      }
+#pragma unroll
+      for (int j = 0; j < kHeadItems; ++j) {
+        const u32 i = p_i0 + j;
+        if (i < n) {
+          if (a.excl) a.excl[i] = run;
+          if (p_flags & (1u << j)) {
+            if (run < a.starts_cap) {
+              a.starts[run] = i;
+              if (a.hkeys) hash_insert_one(a.hkeys, a.hvals, *a.d_hash_mask, keys[i], run);
+            }
+            ++run;
+          }
         }
       }
     }
-    __syncthreads();
+    parked = valid;
+    p_tile = tile; p_total = total; p_i0 = i0; p_flags = flags; p_before = before;
+    if (!valid) break;
   }
 }
 
@@ -241,24 +253,21 @@ struct VoxelOut {
   u32* v_off;        // [F+1]
 };
 
-// Eight lanes per voxel: the lanes fetch eight records of the segment at a time (index, then point: two dependent
-// loads per record, which one thread walking the segment alone would serialise), and every lane then adds the eight
-// points in record order — the fp32 sums stay sequential, as the reference's accumulator is.
-__global__ void voxel_mean_kernel(const Ctl* __restrict__ ctl, const u64* keys_a, const u64* keys_b,
-                                  const u32* vals_a, const u32* vals_b, const u32* __restrict__ starts,
-                                  const float4* __restrict__ pts, const u32* __restrict__ src,
-                                  const u32* __restrict__ frame_n, u32 uniform_n,
-                                  const u32* __restrict__ gcount, int pad_possible, u32 n_frames, VoxelOut o) {
-  constexpr u32 G = 8;
-  const u32 nv = ctl->n_vox, n = ctl->n_surv;
-  if (nv == 0 && blockIdx.x == 0)
-    for (u32 f = threadIdx.x; f <= n_frames; f += blockDim.x) o.v_off[f] = 0;
-  const bool inb = sorted_in_b(ctl->vsort_bits);
-  const u64* keys = inb ? keys_b : keys_a;
-  const u32* vals = inb ? vals_b : vals_a;
-  const u32 kb = ctl->voxel_key_bits;
+// G lanes per voxel: the lanes fetch G records of the segment at a time (index, then point: two dependent loads per
+// record, which one thread walking the segment alone would serialise), and every lane then adds the G points in
+// record order — the fp32 sums stay sequential, as the reference's accumulator is.  G follows the average segment
+// length of the run: a warp per voxel on dense clouds (config 4: 34 points per voxel), two lanes where nearly every
+// point is its own voxel (config 5) — with eight lanes throughout, config 4 walked five dependent rounds per voxel
+// and config 5 kept six of eight lanes idle.
+template <u32 G>
+__device__ __forceinline__ void voxel_mean_body(u32 nv, u32 n, u32 kb, const u64* __restrict__ keys,
+                                                const u32* __restrict__ vals, const u32* __restrict__ starts,
+                                                const float4* __restrict__ pts, const u32* __restrict__ src,
+                                                const u32* __restrict__ frame_n, u32 uniform_n,
+                                                const u32* __restrict__ gcount, int pad_possible, u32 n_frames,
+                                                const VoxelOut& o) {
   const u32 sub = threadIdx.x & (G - 1);
-  const u32 gmask = 0xFFu << (threadIdx.x & 24u);           // the eight lanes of this group
+  const u32 gmask = G == 32 ? kFull : (((1u << (G & 31)) - 1u) << (threadIdx.x & 31u & ~(G - 1)));   // this group's lanes
   const u32 ngroups = gridDim.x * blockDim.x / G;
   for (u32 v = (blockIdx.x * blockDim.x + threadIdx.x) / G; v < nv; v += ngroups) {
     const u32 b = starts[v];
@@ -282,7 +291,7 @@ __global__ void voxel_mean_kernel(const Ctl* __restrict__ ctl, const u64* keys_a
         sz = __fadd_rn(sz, __shfl_sync(gmask, p.z, k, G));
         si = __fadd_rn(si, __shfl_sync(gmask, p.w, k, G));
       }
-      if (__ballot_sync(gmask, pad) & gmask) {
+      if (pad_possible && (__ballot_sync(gmask, pad) & gmask)) {
         // the record standing for the ground node's zero padding: adding zeros leaves the
         // sums unchanged, only the count grows by (N - G) - 1
         const u32 nf = uniform_n ? uniform_n : frame_n[f];
@@ -304,6 +313,31 @@ __global__ void voxel_mean_kernel(const Ctl* __restrict__ ctl, const u64* keys_a
         for (u32 g = f + 1; g <= n_frames; ++g) o.v_off[g] = nv;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) voxel_mean_kernel(const Ctl* __restrict__ ctl, const u64* keys_a,
+                                                         const u64* keys_b, const u32* vals_a, const u32* vals_b,
+                                                         const u32* __restrict__ starts,
+                                                         const float4* __restrict__ pts,
+                                                         const u32* __restrict__ src,
+                                                         const u32* __restrict__ frame_n, u32 uniform_n,
+                                                         const u32* __restrict__ gcount, int pad_possible,
+                                                         u32 n_frames, VoxelOut o) {
+  const u32 nv = ctl->n_vox, n = ctl->n_surv;
+  if (nv == 0 && blockIdx.x == 0)
+    for (u32 f = threadIdx.x; f <= n_frames; f += blockDim.x) o.v_off[f] = 0;
+  if (nv == 0) return;
+  const bool inb = sorted_in_b(ctl->vsort_bits);
+  const u64* keys = inb ? keys_b : keys_a;
+  const u32* vals = inb ? vals_b : vals_a;
+  const u32 kb = ctl->voxel_key_bits;
+  const u32 avg = n / nv;   // points per voxel
+  if (avg >= 16u)
+    voxel_mean_body<32>(nv, n, kb, keys, vals, starts, pts, src, frame_n, uniform_n, gcount, pad_possible, n_frames, o);
+  else if (avg >= 3u)
+    voxel_mean_body<8>(nv, n, kb, keys, vals, starts, pts, src, frame_n, uniform_n, gcount, pad_possible, n_frames, o);
+  else
+    voxel_mean_body<2>(nv, n, kb, keys, vals, starts, pts, src, frame_n, uniform_n, gcount, pad_possible, n_frames, o);
 }
 
 }  // namespace cp
