@@ -107,6 +107,15 @@ __device__ __forceinline__ void sort_feed_flush(SortFeedSmem& s, u32* hdr, u32* 
 // one pass.  Warp w of a tile owns the contiguous items [w*256, (w+1)*256) and walks them 32 at a time, so ranks
 // follow input order (stable).
 __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs a, u32 pass) {
+  __shared__ u32 whist[kSortWarps][kRadix];
+  __shared__ u32 gbase[kRadix];
+  __shared__ u32 excl_s[kRadix];
+  __shared__ u32 s_tile;
+  // the first ticket, the sizes and this pass's digit totals are independent loads: all in flight together (one
+  // L2 round trip instead of three in front of a tile's first key load — a small sort is one wave of tiles, and
+  // its passes are as long as that chain)
+  if (threadIdx.x == 0) s_tile = atomicAdd(&a.hdr[pass], 1u);   // ticket: earlier tiles are already running
+  u32 v = a.hdr[kSortMaxPasses + pass * kRadix + threadIdx.x];
   const u32 bits = *a.d_bits, n = *a.d_n;
   if (pass * 8 >= bits || n == 0) return;
   const u32 tiles = (n + kSortTile - 1) / kSortTile;
@@ -118,16 +127,10 @@ __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs
   const u32 shift = pass * 8;
   u32* st = a.state + (u64)(pass & 1u) * a.tiles_cap * kRadix;
   u32* st_next = a.state + (u64)((pass + 1u) & 1u) * a.tiles_cap * kRadix;
-
-  __shared__ u32 whist[kSortWarps][kRadix];
-  __shared__ u32 gbase[kRadix];
-  __shared__ u32 excl_s[kRadix];
-  __shared__ u32 s_tile;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
 
   // exclusive scan of this pass's 256 digit totals (every CTA recomputes it; 256 values)
   {
-    u32 v = a.hdr[kSortMaxPasses + pass * kRadix + threadIdx.x];
     u32 inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -142,9 +145,11 @@ __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs
     gbase[threadIdx.x] = off + inc - v;
   }
 
+  bool first = true;
   while (true) {
     __syncthreads();
-    if (threadIdx.x == 0) s_tile = atomicAdd(&a.hdr[pass], 1u);   // ticket: earlier tiles are already running
+    if (!first && threadIdx.x == 0) s_tile = atomicAdd(&a.hdr[pass], 1u);
+    first = false;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) whist[w][threadIdx.x] = 0;
     __syncthreads();
@@ -152,13 +157,16 @@ __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs
     if (tile >= tiles) break;
     const u32 base = tile * kSortTile + warp * (32 * kSortRounds);
     u64 key[kSortRounds];
+    u32 val[kSortRounds];
     u32 off[kSortRounds];
-    // all eight loads first: the __syncwarp() of the ranking rounds would otherwise put one memory round trip
-    // between every two rounds
+    // all loads first (the values too: fetched before the scatter they would be one more round trip at the end
+    // of every tile): the __syncwarp() of the ranking rounds would otherwise put one memory round trip between
+    // every two rounds
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
       const u32 i = base + r * 32 + lane;
       key[r] = i < n ? ksrc[i] : 0ull;
+      val[r] = i < n ? vsrc[i] : 0u;
     }
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs
         i32 t = (i32)tile - 1;
         bool done = false;
         while (!done) {
-          constexpr int kLook = 16;
+          constexpr int kLook = 8;
           u32 sv[kLook];
 #pragma unroll
           for (int q = 0; q < kLook; ++q) sv[q] = (t - q >= 0) ? col[(u64)(t - q) * kRadix] : kFlagPre;
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs
         const u32 d = (u32)(key[r] >> shift) & 0xFFu;
         const u32 pos = gbase[d] + excl_s[d] + whist[warp][d] + off[r];
         kdst[pos] = key[r];
-        vdst[pos] = vsrc[i];
+        vdst[pos] = val[r];
       }
     }
   }
