@@ -109,7 +109,11 @@ __device__ __forceinline__ void sort_feed_flush(SortFeedSmem& s, u32* hdr, u32* 
 __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs a, u32 pass) {
   __shared__ u32 whist[kSortWarps][kRadix];
   __shared__ u32 gbase[kRadix];
-  __shared__ u32 excl_s[kRadix];
+  __shared__ u32 lbase[kRadix];          // first slot of a digit inside the tile's staged (sorted) order
+  __shared__ u32 dbase[kRadix];          // global position of staged slot i of digit d = dbase[d] + i
+  __shared__ u32 wsum2[kSortWarps];
+  __shared__ u64 st_key[kSortTile];      // the tile in sorted order: runs of equal digits leave with coalesced
+  __shared__ u32 st_val[kSortTile];      // stores (scattered from registers, every 8-byte store was its own sector)
   __shared__ u32 s_tile;
   // the first ticket, the sizes and this pass's digit totals are independent loads: all in flight together (one
   // L2 round trip instead of three in front of a tile's first key load — a small sort is one wave of tiles, and
@@ -194,6 +198,14 @@ __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs
         whist[w][threadIdx.x] = run;
         run += t;
       }
+      // where the digit's run starts inside the tile: exclusive scan of the 256 runs (finished after the look-back)
+      u32 inc2 = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(kFull, inc2, o);
+        if (lane >= o) inc2 += t;
+      }
+      if (lane == 31) wsum2[warp] = inc2;
       volatile u32* mine = st + (u64)tile * kRadix + threadIdx.x;
       u32 ex = 0;
       if (tile == 0) {
@@ -228,7 +240,11 @@ __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs
         *mine = kFlagPre | (ex + run);
       }
       st_next[(u64)tile * kRadix + threadIdx.x] = 0u;   // clean look-back words for the next pass
-      excl_s[threadIdx.x] = ex;
+      __syncthreads();
+      u32 tstart = inc2 - run;
+      for (int w = 0; w < warp; ++w) tstart += wsum2[w];
+      lbase[threadIdx.x] = tstart;
+      dbase[threadIdx.x] = gbase[threadIdx.x] + ex - tstart;
     }
     __syncthreads();
 #pragma unroll
@@ -236,9 +252,21 @@ __global__ void __launch_bounds__(kSortThreads, 4) sort_onesweep_kernel(SortArgs
       const u32 i = base + r * 32 + lane;
       if (i < n) {
         const u32 d = (u32)(key[r] >> shift) & 0xFFu;
-        const u32 pos = gbase[d] + excl_s[d] + whist[warp][d] + off[r];
-        kdst[pos] = key[r];
-        vdst[pos] = val[r];
+        const u32 slot = lbase[d] + whist[warp][d] + off[r];
+        st_key[slot] = key[r];
+        st_val[slot] = val[r];
+      }
+    }
+    __syncthreads();
+    const u32 in_tile = n - tile * kSortTile < (u32)kSortTile ? n - tile * kSortTile : (u32)kSortTile;
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+      const u32 i = r * kSortThreads + threadIdx.x;
+      if (i < in_tile) {
+        const u64 kk = st_key[i];
+        const u32 pos = dbase[(u32)(kk >> shift) & 0xFFu] + i;
+        kdst[pos] = kk;
+        vdst[pos] = st_val[i];
       }
     }
   }
