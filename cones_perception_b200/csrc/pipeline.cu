@@ -149,7 +149,7 @@ struct cp_handle {
   u64 *d_keys_a = nullptr, *d_keys_b = nullptr, *d_okeys_a = nullptr, *d_okeys_b = nullptr;
   u32 *d_vals_a = nullptr, *d_vals_b = nullptr, *d_ovals_a = nullptr, *d_ovals_b = nullptr;
   u32 *d_sort_hdr = nullptr, *d_sort_state = nullptr;   // radix_sort.cuh: tickets + digit totals, look-back words
-  u32 *d_excl = nullptr, *d_vstart = nullptr, *d_cstart = nullptr, *d_comp_start = nullptr;
+  u32 *d_vstart = nullptr, *d_cstart = nullptr, *d_comp_start = nullptr;
   float4* d_vox = nullptr;
   u32 *d_vox_frame = nullptr, *d_parent = nullptr, *d_label = nullptr;
   u64* d_hkeys = nullptr;
@@ -173,11 +173,10 @@ struct cp_handle {
   int prio_low = 0;
   int k1_ctas_per_sm = 0;  // CONESGPU_K1_CTAS: separate grid cap for pass 1 (0 = stream_ctas_per_sm)
   int frame_ctas_per_sm = 0;  // CONESGPU_FRAME_CTAS: grid cap of the per-frame kernel (0 = what fits)
-  // one CTA per tile in the kernels that end a tile with a decoupled look-back (mask_compact, segment heads, tile
-  // scan, sort passes).  A persistent CTA cannot publish its next tile's aggregate before its current look-back
-  // has resolved, which chains every round of tiles to the slowest CTA of the previous one (ncu: 39 spins per
-  // look-back window, 1.7 TB/s); CTAs that retire after one tile leave the load / judge phases of the tiles behind
-  // them free of that wait.  CONESGPU_TILE_CTAS=0 restores the persistent grids.
+  // one CTA per tile in the sort passes and the tile scan (kernels that end a tile with a decoupled look-back on
+  // the spot): a persistent CTA cannot publish its next tile's counts before its current look-back has resolved.
+  // Measured equal to persistent grids; mask_compact and the segment heads defer their look-back
+  // instead and are always persistent.  CONESGPU_TILE_CTAS=0 restores the persistent grids.
   bool tile_ctas = true;
   u32 run_sgrid = 0;  // grid of the streaming kernels of the current run
   int stream_ctas_per_sm = 8;  // grid cap of the streaming kernels (CONESGPU_STREAM_CTAS: leave room for a second handle)
@@ -816,7 +815,6 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
     ha.keys_b = h->d_keys_b;
     ha.d_bits = &h->d_ctl->vsort_bits;
     ha.d_n = &h->d_ctl->n_surv;
-    ha.excl = nullptr;
     ha.starts = h->d_vstart;
     ha.starts_cap = (u32)h->cap_v;
     ha.d_total = &h->d_ctl->n_vox;
@@ -852,7 +850,6 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
     ha.keys_b = h->d_keys_b;
     ha.d_bits = &h->d_ctl->csort_bits;
     ha.d_n = &h->d_ctl->n_vox;
-    ha.excl = nullptr;
     ha.starts = h->d_cstart;
     ha.starts_cap = (u32)h->cap_v;
     ha.d_total = &h->d_ctl->n_cells;
@@ -882,7 +879,6 @@ void enqueue_back_general(cp_handle* h, const RunParams& rp) {
     ha.keys_b = h->d_keys_b;
     ha.d_bits = &h->d_ctl->lsort_bits;
     ha.d_n = &h->d_ctl->n_vox;
-    ha.excl = nullptr;
     ha.starts = h->d_comp_start;
     ha.starts_cap = (u32)h->cap_v;
     ha.d_total = &h->d_ctl->n_comp;
@@ -1771,7 +1767,6 @@ cp_status cp_create(cp_handle** out, const cp_config* cfg) try {
   A(dalloc(h, &h->d_ovals_b, h->cap_v));
   A(dalloc(h, &h->d_sort_state, (size_t)2 * kRadix * h->sort_tiles_cap));
   A(dalloc(h, &h->d_sort_hdr, kSortHdrWords * 4));   // one header per sort of the general back half
-  // (d_excl — per-survivor voxel ranks — is gone: v_off comes from voxel_mean_kernel)
   A(dalloc(h, &h->d_vstart, h->cap_v));
   A(dalloc(h, &h->d_cstart, h->cap_v));
   A(dalloc(h, &h->d_comp_start, h->cap_v));

@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(256) voxel_key_kernel(Ctl* ctl, VoxelK k, cons
 }
 
 // ---- generic "segment heads" pass over a sorted key array ---------------------------------
-// head[i] = (i == 0 || key[i] != key[i-1]); writes excl[i] = number of heads before i
-// (optional), starts[seg] = i for every head, *d_total = number of segments.
+// head[i] = (i == 0 || key[i] != key[i-1]); writes starts[seg] = i for every head and *d_total = number of
+// segments.
 constexpr int kHeadThreads = 256;
 constexpr int kHeadItems = 4;
 constexpr int kHeadTile = kHeadThreads * kHeadItems;
@@ -123,7 +123,6 @@ struct HeadArgs {
   const u64* keys_b;
   const u32* d_bits;   // selects A or B (result parity of the preceding sort)
   const u32* d_n;
-  u32* excl;           // may be NULL
   u32* starts;
   u32 starts_cap;
   u32* d_total;
@@ -228,7 +227,6 @@ __global__ void __launch_bounds__(kHeadThreads) segment_heads_kernel(HeadArgs a)
       for (int j = 0; j < kHeadItems; ++j) {
         const u32 i = p_i0 + j;
         if (i < n) {
-          if (a.excl) a.excl[i] = run;
           if (p_flags & (1u << j)) {
             if (run < a.starts_cap) {
               a.starts[run] = i;
