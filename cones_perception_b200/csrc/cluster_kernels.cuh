@@ -206,25 +206,46 @@ __global__ void __launch_bounds__(256) cell_union_kernel(const Ctl* __restrict__
         u32 same = 0;
         if (lane == 0) same = uf_find(parent, m) == uf_find(parent, vals[ob]) ? 1u : 0u;
         if (__shfl_sync(kFull, same, 0)) continue;
-        const u32 nb = oe - ob;
-        const unsigned long long total = (unsigned long long)(e - b) * nb;
-        for (unsigned long long t0 = 0; t0 < total; t0 += 32ull) {
-          const unsigned long long t = t0 + lane;
-          bool hit = false;
-          u32 vi = 0, vj = 0;
-          if (t < total) {
-            vi = vals[b + (u32)(t / nb)];
-            vj = vals[ob + (u32)(t % nb)];
-            const float4 p = vox[vi], r = vox[vj];
-            ++n_visited;
-            ++n_tested;
-            // FLANN: dist = L2_Simple(query, point); accepted iff dist < radius (strict)
-            hit = l2_simple(p.x, p.y, p.z, r.x, r.y, r.z) < k.r2;
+        // Every voxel pair of the two cells until the first hit.  A lane keeps one voxel of the cell, a chunk of 32
+        // neighbour voxels is fetched once (one per lane) and handed round by shuffles, so a pair costs arithmetic,
+        // not a dependent index -> voxel load pair (two dense cells that are close but not connected — all 64 x 64
+        // pairs fail — would otherwise be 128 memory round trips for one warp).
+        const u32 nb = oe - ob, na = e - b;
+        bool linked = false;
+        for (u32 a0 = 0; a0 < na && !linked; a0 += 32u) {
+          const bool pv = a0 + lane < na;
+          u32 vi = 0;
+          float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pv) {
+            vi = vals[b + a0 + lane];
+            p = vox[vi];
           }
-          const u32 hits = __ballot_sync(kFull, hit);
-          if (hits) {
-            if ((int)lane == __ffs(hits) - 1) uf_union(parent, vi, vj);
-            break;
+          for (u32 c0 = 0; c0 < nb && !linked; c0 += 32u) {
+            u32 vj = 0;
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + lane < nb) {
+              vj = vals[ob + c0 + lane];
+              r = vox[vj];
+            }
+            const u32 cnt = nb - c0 < 32u ? nb - c0 : 32u;
+            for (u32 j = 0; j < cnt; ++j) {
+              const float rx = __shfl_sync(kFull, r.x, j), ry = __shfl_sync(kFull, r.y, j),
+                          rz = __shfl_sync(kFull, r.z, j);
+              bool hit = false;
+              if (pv) {
+                ++n_visited;
+                ++n_tested;
+                // FLANN: dist = L2_Simple(query, point); accepted iff dist < radius (strict)
+                hit = l2_simple(p.x, p.y, p.z, rx, ry, rz) < k.r2;
+              }
+              const u32 hits = __ballot_sync(kFull, hit);
+              if (hits) {
+                const u32 vjj = __shfl_sync(kFull, vj, j);
+                if ((int)lane == __ffs(hits) - 1) uf_union(parent, vi, vjj);
+                linked = true;
+                break;
+              }
+            }
           }
         }
         __syncwarp();
