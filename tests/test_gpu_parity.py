@@ -728,3 +728,49 @@ def test_results_do_not_depend_on_batching_or_frame_order():
         for f in (0, 17, F - 1):
             one, c1 = h1.detect(msgs[f], cfg.detect, cfg.ground)
             assert one.tobytes() == cl[off[f]:off[f + 1]].tobytes() and c1.tobytes() == ctr[f].tobytes()
+
+
+@pytest.mark.parametrize("ground", [False, True])
+def test_general_front_end_parks_sparse_tiles_and_resolves_dense_ones_on_the_spot(ground):
+    """mask_compact_kernel (general back half) parks a tile with at most 1024 survivors in shared memory and
+    resolves its look-back one tile later; a tile with more survivors resolves on the spot and stores from
+    registers.  A batch that interleaves both kinds of tiles — whole 2048-point tiles that survive the crop next to
+    tiles where nothing or little does, with and without the pad record of the ground node — must come out of the
+    general path exactly like the oracle, frame by frame, also when the run is replayed from a graph."""
+    cfg = scans.config(3)
+    d = cfg.detect
+    g = cfg.ground if ground else None
+    rng = np.random.default_rng(77 + int(ground))
+    frames = []
+    for f in range(3):
+        base = scans.generate(cfg, 1, base_seed=400 + f)[0]
+        n_dense = 3 * 2048 + 700                       # three tiles and a bit in which every point survives
+        dense = np.zeros((n_dense, 4), np.float32)
+        ang = rng.uniform(-0.6, 0.6, n_dense)
+        rad = rng.uniform(3.0, 9.0, n_dense)
+        dense[:, 0], dense[:, 1] = rad * np.cos(ang), rad * np.sin(ang)
+        dense[:, 2] = rng.uniform(0.3, 0.6, n_dense)    # above the ground band, below the level threshold's cut
+        dense[:, 3] = rng.uniform(0, 100, n_dense)
+        far = np.zeros((2 * 2048 + 100, 4), np.float32)   # beyond distance_treshold_max: tiles without a survivor
+        fa, fr_ = rng.uniform(-np.pi, np.pi, len(far)), rng.uniform(30, 60, len(far))
+        far[:, 0], far[:, 1], far[:, 2] = fr_ * np.cos(fa), fr_ * np.sin(fa), rng.uniform(-0.5, 2.0, len(far))
+        for c in range(6):                              # six cones' worth of returns scattered through those tiles
+            ca, cr = 1.2 + 0.25 * c, 4.0 + 0.7 * c
+            idx = rng.choice(len(far), 40, replace=False)
+            far[idx, 0] = cr * np.cos(ca) + rng.uniform(-0.08, 0.08, 40)
+            far[idx, 1] = cr * np.sin(ca) + rng.uniform(-0.08, 0.08, 40)
+            far[idx, 2] = rng.uniform(0.0, 0.3, 40)
+        cut = 2048 * (5 + f) + 13 * f                   # not tile-aligned in frames 1, 2
+        frames.append(np.ascontiguousarray(np.concatenate([far, base[:cut], dense, far[::-1], base[cut:cut + 40_000]])))
+    clouds = [PointCloud2.from_xyzi(fr) for fr in frames]
+    with api.ConesGpu(max_points=sum(len(fr) for fr in frames), max_frames=3, back_mode=3) as h:
+        for rep in range(3):                            # direct run, graph capture, replay
+            ctr, off, cl = h.detect_batch(clouds, d, g)
+            for f, fr in enumerate(frames):
+                exp, octr, _ = O.detect(O.view_of_xyzi(fr), d, g, O.CANONICAL)
+                assert int(ctr["n_cropped"][f]) == octr.n_cropped, (f, rep)
+                assert int(ctr["n_voxels"][f]) == octr.n_voxels, (f, rep)
+                assert np.array_equal(cl[off[f]:off[f + 1]].view(np.uint32), exp.view(np.uint32)), (f, rep)
+                if g is not None:
+                    assert int(ctr["n_ground_kept"][f]) == octr.n_ground_kept, (f, rep)
+            assert int(ctr["n_cropped"].max()) > 3 * 2048 and int(off[-1]) >= 6
