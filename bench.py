@@ -1031,7 +1031,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--frames-per-gpu", type=int, default=512)
     ap.add_argument("--latency-reps", type=int, default=200)
-    ap.add_argument("--lanes", type=int, default=2, help="batches in flight (handles/streams alternating per step)")
+    ap.add_argument("--lanes", type=int, default=4, help="batches in flight (handles/streams alternating per step)")
     ap.add_argument("--cpu-sample-frames", type=int, default=512, help="frames timed on one core for cpu_baseline")
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0, help="minimum CPU time spent on cpu_baseline")
     ap.add_argument("--no-sub-records", dest="sub_records", action="store_false",
