@@ -577,7 +577,7 @@ def run_ours(args):
         "step_bytes_moved": moved, "step_frac_bytes_moved": moved / step_s / 1e9 / peak,
         "step_bytes_single_read": single, "step_frac_single_read": single / step_s / 1e9 / peak,
         "survey_b_alg_bytes_per_step": b_alg_step,
-        "step_note": "fractions of the measured HBM peak over the whole step (all kernels, both lanes); "
+        "step_note": "fractions of the measured HBM peak over the whole step (all kernels, all batches in flight); "
                      "profiles/traffic.json holds the ncu DRAM sum of the same step"})
 
     # ---- end to end through the C ABI with HOST buffers (page-locked): H2D + pipeline + D2H
