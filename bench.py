@@ -324,9 +324,9 @@ def run_ours(args):
     frame_points = np.full(F, N, dtype=np.uint32)
     gpu.set_device_input(dev.data_ptr(), frame_points, keep=dev)
     cone_cap = F * CONE_CAP_PER_FRAME
-    # Two batches in flight: consecutive steps alternate between two handles (two streams, two sets of
-    # intermediates), so the latency-bound tail of one batch (pass 2, per-frame kernel, packing) overlaps
-    # the HBM-bound first pass of the next.  Every step still runs the whole path on the whole batch.
+    # Several batches in flight (--lanes, default 4): consecutive steps go round the handles (one stream and one
+    # set of intermediates each), so the latency-bound per-frame kernel of one batch overlaps the HBM-bound first
+    # pass of another.  Every step still runs the whole path on the whole batch.
     lanes = [gpu]
     for _ in range(1, max(1, args.lanes)):
         h2 = api.ConesGpu(max_points=F * N, max_frames=F, device=dev_index, max_survivors=max(F * N // 8, 1 << 20),
