@@ -687,7 +687,7 @@ def run_ours(args):
             return sizes
 
         weights = [r_ * (1.0 + 0.2 * i_) for i_, r_ in enumerate(probe_rates)] if force_w else list(probe_rates)
-        for attempt in range(3):
+        for attempt in range(5):
             sizes = split(weights)
             if shard_trail and sizes == shard_trail[-1]["frames"]:
                 break
