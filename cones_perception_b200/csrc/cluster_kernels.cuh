@@ -2,17 +2,19 @@
 // (reference call site: euclidan_cluster(), src/cone_detection.cpp:206-220; semantics:
 // SURVEY.md Appendix A.5) plus the centroid loop (src/cone_detection.cpp:261-273, A.6).
 //
-//   cell_key      voxel centroid -> cell of a uniform grid with edge 0.505 x cluster tolerance
+//   cell_key      voxel centroid -> cell of a uniform grid with edge 0.505 x cluster tolerance; also the sort
+//                 widths of the stage, the cell hash's live size and clearing, the cell sort's digit histograms
 //   (radix sort by cell key)
-//   cell heads    -> cell start offsets;  hash_insert: cell key -> cell id (open addressing)
+//   cell heads    -> cell start offsets; every head enters cell key -> cell id into the hash (open addressing)
 //   cell_union    one warp per occupied cell.  The cell's diagonal is shorter than the tolerance, so its voxels
 //                 are one component without a single distance test; the 62 "forward" cells of the 5x5x5
 //                 neighbourhood are then joined cell to cell: already in one tree -> skipped after two finds,
 //                 otherwise voxel pairs are tested (exact FLANN distance) until the first hit.  Lock-free CAS
 //                 union-find linking the larger root under the smaller (root = min index = label).
-//   flatten_count     label = root, component sizes
-//   (radix sort by label) -> component heads -> size filter + ordering key
-//   (radix sort by frame, size desc) -> emit centroids in canonical cluster order
+//   flatten       label = root; keys + digit histograms of the label sort
+//   (radix sort by label) -> component heads -> component: size filter + ordering key (+ order sort histograms)
+//   (radix sort by frame, size desc) -> emit centroids in canonical cluster order; its CTA 0 also writes the
+//                 cluster offsets per frame and the per-frame counters
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"

@@ -1,10 +1,12 @@
 // radix_sort.cuh — hand-written stable LSD radix sort of (u64 key, u32 value) pairs.
 //
 // No CUB / Thrust.  8-bit digits, ONE kernel per pass ("onesweep"): a tile ranks its 2048 items per digit
-// (stable: warp-contiguous chunks + match_any), publishes its 256 digit counts and finds the counts of the tiles
-// before it by decoupled look-back (tiles are handed out by ticket, so every earlier tile is already running);
-// the global digit bases of ALL passes come from one histogram kernel up front — the key multiset does not change
-// between passes.  A sort is therefore 1 small memset + 1 + passes launches instead of 3 x passes.
+// (stable: warp-contiguous chunks + match_any), publishes its 256 digit counts, finds the counts of the tiles
+// before it by decoupled look-back (tiles are handed out by ticket, so every earlier tile is already running) and
+// leaves through shared memory in sorted order, so runs of equal digits store coalesced.  The global digit bases
+// of ALL passes are counted once — the key multiset does not change between passes — either by the kernel that
+// writes the keys (sort_feed_*: the general back half's four sorts, which are then their passes and nothing else)
+// or by sort_prepare_kernel (a sort of keys that are already there: 1 small memset + 1 + passes launches).
 // The element count and the number of significant key bits are read from device memory, so a sort whose size
 // depends on earlier kernels needs no host synchronisation: the host enqueues ceil(max_bits/8) passes and passes
 // beyond the live bit count exit immediately.  Data ping-pongs A -> B -> A ...; after the sort the

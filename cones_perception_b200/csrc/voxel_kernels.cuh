@@ -1,8 +1,8 @@
 // voxel_kernels.cuh — pcl::VoxelGrid<PointXYZI>::applyFilter restated for batches of frames
 // (reference call site: downsample(), src/cone_detection.cpp:240-249; semantics: SURVEY.md
 // Appendix A.4).  Stages: per-frame grid setup from the survivors' bounding box -> voxel key
-// per survivor -> (radix sort, radix_sort.cuh) -> segment heads -> sequential fp32 mean per
-// voxel in ascending point order.
+// per survivor (+ the voxel sort's digit histograms) -> (radix sort, radix_sort.cuh) -> segment
+// heads -> sequential fp32 mean per voxel in ascending point order (+ voxel offsets per frame).
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"
