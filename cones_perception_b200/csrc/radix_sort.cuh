@@ -280,7 +280,10 @@ inline int radix_sort_passes(cudaStream_t st, const SortArgs& a, u32 max_bits, u
   if (passes > kSortMaxPasses) passes = kSortMaxPasses;
   u32 tiles = (max_n + kSortTile - 1) / kSortTile;
   if (tiles == 0) tiles = 1;
-  const u32 grid = (!persistent || tiles < (u32)(sms * 3)) ? tiles : (u32)(sms * 3);
+  // (one CTA per tile up to 16 per SM: a handle's first run has no size hint yet, and launching a CTA for every
+  // tile of the CAPACITY cost 12 us per pass on a sort of a few thousand items; CTAs loop over tickets anyway)
+  const u32 cap = (u32)sms * (persistent ? 3u : 16u);
+  const u32 grid = tiles < cap ? tiles : cap;
   for (u32 p = 0; p < passes; ++p) sort_onesweep_kernel<<<grid, kSortThreads, 0, st>>>(a, p);
   return (int)passes;
 }
@@ -294,7 +297,8 @@ inline int radix_sort_enqueue(cudaStream_t st, const SortArgs& a, u32 max_bits, 
   if (tiles == 0) tiles = 1;
   // tiles by ticket; one CTA per tile unless `persistent` (see cp_handle::tile_ctas in pipeline.cu): a CTA that
   // goes on to another tile cannot publish that tile's counts before its current look-back has resolved
-  u32 grid = (!persistent || tiles < (u32)(sms * 3)) ? tiles : (u32)(sms * 3);
+  const u32 gcap = (u32)sms * (persistent ? 3u : 16u);
+  u32 grid = tiles < gcap ? tiles : gcap;
   cudaMemsetAsync(a.hdr, 0, sizeof(u32) * kSortHdrWords, st);
   const u32 pgrid = tiles < (u32)(sms * 3) ? tiles : (u32)(sms * 3);   // histograms: grid-stride, no look-back
   sort_prepare_kernel<<<pgrid, kSortThreads, 0, st>>>(a);
